@@ -1,0 +1,823 @@
+// C ABI of libmcv_b200.so: plan construction, device workspaces, stream plumbing. See include/mcv_b200.h for the
+// reference interface each entry point replaces. There is no CPU fallback anywhere in this file: every compute entry
+// point launches the sm_100a kernels or fails with an error code.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cfloat>
+
+namespace mcv {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+
+// ---------------------------------------------------------------------------------------------------------
+// device buffer that grows on demand
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    mcv_status reserve(size_t n) {
+        if (n <= bytes) return MCV_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        MCV_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+        return MCV_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned staging
+    void* p = nullptr; size_t bytes = 0;
+    mcv_status reserve(size_t n) {
+        if (n <= bytes) return MCV_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        MCV_CUDA(cudaMallocHost(&p, n));
+        bytes = n;
+        return MCV_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline int cv_round_host(float v) { return (int)lrintf(v); }
+static inline int cv_round_host(double v) { return (int)lrint(v); }
+static inline int cv_floor_host(double v) { int i = (int)v; return i - (i > v); }
+
+}  // namespace mcv
+
+using namespace mcv;
+
+// =========================================================================================================
+// extractor handle
+// =========================================================================================================
+struct mcv_orb {
+    mcv_orb_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // ORBextractor public vectors (ORBextractor.h:96-99) and quotas
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    // plan for the current image size
+    Plan plan{};
+    bool have_plan = false;
+    int cap_images = 0;     // workspace capacity (images)
+    int last_images = 0;    // images processed by the last extract
+    DevBuf tabs, src, pyr, blur, cell_pts, cell_cnt, arena_a, arena_b, out_pts, out_cnt, kps, desc, counts, seeds, misc;
+    HostBuf h_stage;
+    int last_cap = 0;       // per-image keypoint slots of the last extract (layout of kps/desc)
+    int last_launches = 0;
+};
+
+// ORBextractor::init — ORBextractor.cc:407-436 (same float arithmetic, evaluated on the host once)
+static void orb_init_scales(mcv_orb* h) {
+    const int n = h->prm.nlevels;
+    const float sf = h->prm.scale_factor;
+    h->scale.assign(n, 1.f); h->sigma2.assign(n, 1.f); h->inv_scale.assign(n, 1.f); h->inv_sigma2.assign(n, 1.f);
+    for (int i = 1; i < n; i++) {
+        h->scale[i] = h->scale[i - 1] * sf;
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < n; i++) {
+        h->inv_scale[i] = 1.0f / h->scale[i];
+        h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+    }
+    h->quota.assign(n, 0);
+    float factor = 1.0f / sf;
+    float nDesired = h->prm.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)n));
+    int sum = 0;
+    for (int level = 0; level < n - 1; level++) {
+        h->quota[level] = cv_round_host(nDesired);
+        sum += h->quota[level];
+        nDesired *= factor;
+    }
+    h->quota[n - 1] = std::max(h->prm.nfeatures - sum, 0);
+}
+
+// Level geometry for an image size + resize coefficient tables (cv::resize INTER_LINEAR model, see image_kernels.cu)
+static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs) {
+    Plan& P = h->plan;
+    memset(&P, 0, sizeof(P));
+    P.n_levels = h->prm.nlevels; P.w = w; P.h = hgt; P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
+    tabs.clear();
+    int img_off = 0, cell_base = 0, cand_off = 0, out_off = 0;
+    for (int l = 0; l < P.n_levels; ++l) {
+        LevelGeom& g = P.lv[l];
+        g.scale = h->scale[l]; g.inv_scale = h->inv_scale[l];
+        g.w = cv_round_host((float)w * g.inv_scale);   // ORBextractor.cc:904
+        g.h = cv_round_host((float)hgt * g.inv_scale);
+        if (g.w > MAX_DIM || g.h > MAX_DIM) { set_error("image larger than 4128 px is not supported"); return MCV_ERR_BAD_ARG; }
+        g.pitch = (g.w + 15) & ~15;
+        g.img_off = img_off;
+        img_off += ((g.pitch * g.h) + 255) & ~255;
+        // cell grid — ORBextractor.cc:588-602
+        const int max_bx = g.w - BORDER, max_by = g.h - BORDER;
+        const float width = (float)(max_bx - BORDER), height = (float)(max_by - BORDER);
+        g.n_cols = (int)(width / 35.f); g.n_rows = (int)(height / 35.f);
+        if (g.n_cols < 1 || g.n_rows < 1) { set_error("pyramid level smaller than one FAST cell"); return MCV_ERR_IMAGE_TOO_SMALL; }
+        g.w_cell = (int)ceilf(width / g.n_cols); g.h_cell = (int)ceilf(height / g.n_rows);
+        g.cell_base = cell_base;
+        cell_base += g.n_cols * g.n_rows;
+        g.cell_cap = ((g.w_cell + 1) / 2) * ((g.h_cell + 1) / 2);
+        g.cand_off = cand_off;
+        g.cand_cap = g.n_cols * g.n_rows * g.cell_cap;
+        cand_off += g.cand_cap;
+        g.quota = h->quota[l];
+        // quadtree roots — ORBextractor.cc:527-529
+        g.n_ini = (int)roundf(width / (float)(max_by - BORDER));
+        if (g.n_ini < 1) { set_error("image aspect ratio below 0.5 is not supported (reference divides by zero)"); return MCV_ERR_BAD_ARG; }
+        g.h_x = width / (float)g.n_ini;
+        g.out_off = out_off;
+        g.out_cap = g.quota + 3 + g.n_ini;
+        out_off += g.out_cap;
+        g.kp_size = (int)(31 * g.scale);   // ORBextractor.cc:640
+        P.max_cell_w = std::max(P.max_cell_w, g.w_cell); P.max_cell_h = std::max(P.max_cell_h, g.h_cell);
+        P.max_quota = std::max(P.max_quota, g.quota);
+        // resize tables for level l <- l-1
+        g.tab_off = (int)tabs.size();
+        g.area_fast = 0;
+        if (l > 0) {
+            const LevelGeom& s = P.lv[l - 1];
+            const double scale_x = 1. / ((double)g.w / s.w), scale_y = 1. / ((double)g.h / s.h);
+            const int isx = cv_round_host(scale_x), isy = cv_round_host(scale_y);
+            g.area_fast = (std::abs(scale_x - isx) < DBL_EPSILON && std::abs(scale_y - isy) < DBL_EPSILON && isx == 2 && isy == 2) ? 1 : 0;
+            std::vector<int> xofs(g.w), xa0(g.w), xa1(g.w), yofs(g.h), yb0(g.h), yb1(g.h);
+            for (int dx = 0; dx < g.w; ++dx) {
+                float fx = (float)((dx + 0.5) * scale_x - 0.5);
+                int sx = cv_floor_host(fx);
+                fx -= sx;
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= s.w - 1) { fx = 0; sx = s.w - 1; }
+                xofs[dx] = sx;
+                xa0[dx] = (short)cv_round_host((1.f - fx) * 2048.f);
+                xa1[dx] = (short)cv_round_host(fx * 2048.f);
+            }
+            for (int dy = 0; dy < g.h; ++dy) {
+                float fy = (float)((dy + 0.5) * scale_y - 0.5);
+                int sy = cv_floor_host(fy);
+                fy -= sy;
+                yofs[dy] = sy;
+                yb0[dy] = (short)cv_round_host((1.f - fy) * 2048.f);
+                yb1[dy] = (short)cv_round_host(fy * 2048.f);
+            }
+            for (auto* v : {&xofs, &xa0, &xa1, &yofs, &yb0, &yb1}) tabs.insert(tabs.end(), v->begin(), v->end());
+        }
+    }
+    P.pyr_bytes = img_off;
+    P.cells_per_image = cell_base;
+    P.cand_per_image = cand_off;
+    P.out_per_image = out_off;
+    P.max_quad_kp = out_off;
+    return MCV_OK;
+}
+
+static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int cap) {
+    if (!h->have_plan || h->plan.w != w || h->plan.h != hgt) {
+        std::vector<int> tabs;
+        h->have_plan = false;
+        mcv_status st = build_plan(h, w, hgt, tabs);
+        if (st) return st;
+        st = h->tabs.reserve(std::max<size_t>(16, tabs.size() * sizeof(int)));
+        if (st) return st;
+        if (!tabs.empty()) MCV_CUDA(cudaMemcpyAsync(h->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        MCV_CUDA(cudaStreamSynchronize(h->stream));  // tabs is a local
+        h->have_plan = true;
+        h->cap_images = 0;
+    }
+    const Plan& P = h->plan;
+    if (n_images > h->cap_images) {
+        mcv_status st;
+        if ((st = h->pyr.reserve((size_t)P.pyr_bytes * n_images))) return st;
+        if ((st = h->blur.reserve((size_t)P.pyr_bytes * n_images))) return st;
+        if ((st = h->cell_pts.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
+        if ((st = h->arena_a.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
+        if ((st = h->arena_b.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
+        if ((st = h->cell_cnt.reserve((size_t)P.cells_per_image * n_images * 4))) return st;
+        if ((st = h->out_pts.reserve((size_t)P.out_per_image * n_images * 4))) return st;
+        if ((st = h->out_cnt.reserve((size_t)P.n_levels * n_images * 4))) return st;
+        h->cap_images = n_images;
+    }
+    mcv_status st;
+    if ((st = h->kps.reserve((size_t)cap * n_images * sizeof(mcv_keypoint)))) return st;
+    if ((st = h->desc.reserve((size_t)cap * n_images * 32))) return st;
+    if ((st = h->counts.reserve((size_t)n_images * 4))) return st;
+    return MCV_OK;
+}
+
+// Enqueue the whole extraction of n_images device-resident images. d_kps/d_desc/d_counts: device outputs, `cap` slots/image.
+static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_pitch, size_t src_image_stride, int n_images,
+                                  const SeedInfo* seeds, mcv_keypoint* d_kps, uint8_t* d_desc, int* d_counts, int cap) {
+    const Plan& P = h->plan;
+    int n = 0;
+    n += launch_pyramid(P, d_imgs, src_pitch, src_image_stride, h->pyr.as<uint8_t>(), h->tabs.as<int>(), n_images, h->stream);
+    n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
+    n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
+    const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
+                                h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
+    if (r < 0) { set_error("nfeatures too large for the quadtree kernel's shared-memory heap"); return MCV_ERR_CAPACITY; }
+    n += r;
+    n += launch_orient_desc(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), seeds, d_kps,
+                            d_desc, d_counts, cap, n_images, h->stream);
+    MCV_CUDA(cudaGetLastError());
+    h->last_images = n_images; h->last_cap = cap; h->last_launches = n;
+    return MCV_OK;
+}
+
+extern "C" {
+
+const char* mcv_last_error(void) { return g_err.c_str(); }
+const char* mcv_version(void) { return "mcv_b200 0.1 (sm_100a)"; }
+int mcv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+mcv_status mcv_orb_create(const mcv_orb_params* p, int device, void* stream, mcv_orb** out) {
+    if (!p || !out) return MCV_ERR_BAD_ARG;
+    *out = nullptr;
+    if (p->nlevels < 1 || p->nlevels > MAX_LEVELS || p->nfeatures < 1 || !(p->scale_factor > 1.0f) || p->min_th_fast < 1 ||
+        p->ini_th_fast < p->min_th_fast || p->ini_th_fast > 254) {
+        set_error("bad extractor parameters");
+        return MCV_ERR_BAD_ARG;
+    }
+    if (mcv_device_count() <= device) { set_error("no CUDA device"); return MCV_ERR_NO_DEVICE; }
+    MCV_CUDA(cudaSetDevice(device));
+    mcv_orb* h = new mcv_orb();
+    h->prm = *p; h->device = device;
+    if (stream) h->stream = (cudaStream_t)stream;
+    else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; set_error("cudaStreamCreate failed"); return MCV_ERR_CUDA; } h->own_stream = true; }
+    orb_init_scales(h);
+    *out = h;
+    return MCV_OK;
+}
+
+void mcv_orb_destroy(mcv_orb* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->out_pts, &h->out_cnt,
+                      &h->kps, &h->desc, &h->counts, &h->seeds, &h->misc})
+        b->release();
+    h->h_stage.release();
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+mcv_status mcv_orb_get_scales(const mcv_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* fpl) {
+    if (!h) return MCV_ERR_BAD_ARG;
+    for (int i = 0; i < h->prm.nlevels; ++i) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->inv_scale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+        if (fpl) fpl[i] = h->quota[i];
+    }
+    return MCV_OK;
+}
+
+int mcv_orb_max_keypoints(const mcv_orb* h, int n_seeds) {
+    if (!h) return 0;
+    int n = 0;
+    for (int l = 0; l < h->prm.nlevels; ++l) n += h->quota[l] + 3 + 4;  // +n_ini roots (<= 4 for aspect <= 4.5)
+    return n + std::max(0, n_seeds);
+}
+
+mcv_status mcv_orb_extract(mcv_orb* h, const uint8_t* img, int w, int hgt, size_t stride, const mcv_keypoint* seeds, int n_seeds,
+                           mcv_keypoint* kps_out, uint8_t* desc_out, int cap, int* n_out) {
+    if (!h || !n_out) return MCV_ERR_BAD_ARG;
+    *n_out = 0;
+    if (!img || w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;  // ORBextractor.cc:834
+    if (stride < (size_t)w || n_seeds < 0 || (n_seeds > 0 && !seeds) || !kps_out || !desc_out) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaSetDevice(h->device));
+    mcv_status st = ensure_workspace(h, w, hgt, 1, std::max(cap, 1));
+    if (st) return st;
+    const Plan& P = h->plan;
+    if (cap < P.max_quad_kp + n_seeds) { set_error("cap smaller than mcv_orb_max_keypoints()"); return MCV_ERR_CAPACITY; }
+    SeedInfo si{};
+    if (n_seeds > 0) {
+        for (int i = 0; i < n_seeds; ++i) {
+            const mcv_keypoint& k = seeds[i];
+            if (k.octave < 0 || k.octave >= P.n_levels) { set_error("seed octave out of range"); return MCV_ERR_SEED_RANGE; }
+            const LevelGeom& g = P.lv[k.octave];
+            const int cx = cv_round_host(k.x), cy = cv_round_host(k.y);
+            if (cx < EDGE_THRESHOLD || cy < EDGE_THRESHOLD || cx >= g.w - EDGE_THRESHOLD || cy >= g.h - EDGE_THRESHOLD) {
+                set_error("seed keypoint within 19 px of its level border (the reference would read outside the image)");
+                return MCV_ERR_SEED_RANGE;
+            }
+        }
+        if ((st = h->seeds.reserve((size_t)n_seeds * sizeof(mcv_keypoint)))) return st;
+        MCV_CUDA(cudaMemcpyAsync(h->seeds.p, seeds, (size_t)n_seeds * sizeof(mcv_keypoint), cudaMemcpyHostToDevice, h->stream));
+        si.d_seeds = h->seeds.as<mcv_keypoint>(); si.n_seeds = n_seeds;
+    }
+    if ((st = h->src.reserve((size_t)w * hgt))) return st;
+    MCV_CUDA(cudaMemcpy2DAsync(h->src.p, w, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    st = enqueue_extract(h, h->src.as<uint8_t>(), w, (size_t)w * hgt, 1, n_seeds ? &si : nullptr, h->kps.as<mcv_keypoint>(),
+                         h->desc.as<uint8_t>(), h->counts.as<int>(), cap);
+    if (st) return st;
+    int n = 0;
+    MCV_CUDA(cudaMemcpyAsync(&n, h->counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    MCV_CUDA(cudaStreamSynchronize(h->stream));
+    if (n > cap) { set_error("keypoint capacity exceeded"); return MCV_ERR_CAPACITY; }
+    if (n > 0) {
+        MCV_CUDA(cudaMemcpyAsync(kps_out, h->kps.p, (size_t)n * sizeof(mcv_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaMemcpyAsync(desc_out, h->desc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    *n_out = n;
+    return MCV_OK;
+}
+
+mcv_status mcv_orb_extract_batch(mcv_orb* h, const uint8_t* imgs, int n_images, int w, int hgt, int imgs_on_device, mcv_keypoint* kps_out,
+                                 uint8_t* desc_out, int32_t* counts, int cap, int out_on_device) {
+    if (!h || !imgs || n_images <= 0 || !kps_out || !desc_out || !counts) return MCV_ERR_BAD_ARG;
+    if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
+    MCV_CUDA(cudaSetDevice(h->device));
+    mcv_status st = ensure_workspace(h, w, hgt, n_images, out_on_device ? 1 : cap);
+    if (st) return st;
+    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_orb_max_keypoints()"); return MCV_ERR_CAPACITY; }
+    const uint8_t* d_imgs = imgs;
+    const size_t img_bytes = (size_t)w * hgt;
+    if (!imgs_on_device) {
+        if ((st = h->src.reserve(img_bytes * n_images))) return st;
+        MCV_CUDA(cudaMemcpyAsync(h->src.p, imgs, img_bytes * n_images, cudaMemcpyHostToDevice, h->stream));
+        d_imgs = h->src.as<uint8_t>();
+    }
+    mcv_keypoint* d_kps = out_on_device ? kps_out : h->kps.as<mcv_keypoint>();
+    uint8_t* d_desc = out_on_device ? desc_out : h->desc.as<uint8_t>();
+    int* d_counts = out_on_device ? counts : h->counts.as<int>();
+    st = enqueue_extract(h, d_imgs, w, img_bytes, n_images, nullptr, d_kps, d_desc, d_counts, cap);
+    if (st) return st;
+    if (!out_on_device) {
+        MCV_CUDA(cudaMemcpyAsync(kps_out, d_kps, (size_t)cap * n_images * sizeof(mcv_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaMemcpyAsync(desc_out, d_desc, (size_t)cap * n_images * 32, cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaMemcpyAsync(counts, d_counts, (size_t)n_images * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    MCV_CUDA(cudaStreamSynchronize(h->stream));
+    return MCV_OK;
+}
+
+mcv_status mcv_orb_level_device(mcv_orb* h, int image_index, int level, const uint8_t** dev_ptr, int* w, int* hgt, size_t* pitch) {
+    if (!h || !h->have_plan || image_index < 0 || image_index >= h->last_images || level < 0 || level >= h->plan.n_levels) return MCV_ERR_BAD_ARG;
+    const LevelGeom& g = h->plan.lv[level];
+    if (dev_ptr) *dev_ptr = h->pyr.as<uint8_t>() + (size_t)image_index * h->plan.pyr_bytes + g.img_off;
+    if (w) *w = g.w;
+    if (hgt) *hgt = g.h;
+    if (pitch) *pitch = g.pitch;
+    return MCV_OK;
+}
+
+static mcv_status download_plane(mcv_orb* h, const DevBuf& buf, int image_index, int level, uint8_t* dst, size_t dst_stride, int* w, int* hgt) {
+    if (!h || !h->have_plan || image_index < 0 || image_index >= h->last_images || level < 0 || level >= h->plan.n_levels) return MCV_ERR_BAD_ARG;
+    const LevelGeom& g = h->plan.lv[level];
+    if (w) *w = g.w;
+    if (hgt) *hgt = g.h;
+    if (!dst) return MCV_OK;
+    if (dst_stride < (size_t)g.w) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaSetDevice(h->device));
+    MCV_CUDA(cudaMemcpy2DAsync(dst, dst_stride, buf.as<uint8_t>() + (size_t)image_index * h->plan.pyr_bytes + g.img_off, g.pitch, g.w, g.h,
+                               cudaMemcpyDeviceToHost, h->stream));
+    MCV_CUDA(cudaStreamSynchronize(h->stream));
+    return MCV_OK;
+}
+
+mcv_status mcv_orb_download_level(mcv_orb* h, int image_index, int level, uint8_t* dst, size_t dst_stride, int* w, int* hgt) {
+    return download_plane(h, h ? h->pyr : DevBuf(), image_index, level, dst, dst_stride, w, hgt);
+}
+mcv_status mcv_debug_download_blurred(mcv_orb* h, int image_index, int level, uint8_t* dst, size_t dst_stride) {
+    return download_plane(h, h ? h->blur : DevBuf(), image_index, level, dst, dst_stride, nullptr, nullptr);
+}
+
+mcv_status mcv_debug_level_keypoints(mcv_orb* h, int image_index, int level, int which, mcv_keypoint* out, int cap, int* n_out) {
+    if (!h || !h->have_plan || image_index < 0 || image_index >= h->last_images || level < 0 || level >= h->plan.n_levels || !n_out) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaSetDevice(h->device));
+    const Plan& P = h->plan;
+    const LevelGeom& g = P.lv[level];
+    std::vector<uint32_t> pts;
+    if (which == 0) {
+        const int nc = g.n_cols * g.n_rows;
+        std::vector<int> cnt(nc);
+        MCV_CUDA(cudaMemcpy(cnt.data(), h->cell_cnt.as<int>() + (size_t)image_index * P.cells_per_image + g.cell_base, nc * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> all(g.cand_cap);
+        MCV_CUDA(cudaMemcpy(all.data(), h->cell_pts.as<uint32_t>() + (size_t)image_index * P.cand_per_image + g.cand_off, (size_t)g.cand_cap * 4, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < nc; ++c) pts.insert(pts.end(), all.begin() + (size_t)c * g.cell_cap, all.begin() + (size_t)c * g.cell_cap + cnt[c]);
+    } else {
+        int n = 0;
+        MCV_CUDA(cudaMemcpy(&n, h->out_cnt.as<int>() + (size_t)image_index * P.n_levels + level, 4, cudaMemcpyDeviceToHost));
+        pts.resize(n);
+        if (n) MCV_CUDA(cudaMemcpy(pts.data(), h->out_pts.as<uint32_t>() + (size_t)image_index * P.out_per_image + g.out_off, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    *n_out = (int)pts.size();
+    for (int i = 0; i < (int)pts.size() && i < cap; ++i)
+        out[i] = mcv_keypoint{(float)pt_x(pts[i]), (float)pt_y(pts[i]), 7.f, -1.f, (float)pt_r(pts[i]), 0, -1};
+    return MCV_OK;
+}
+
+mcv_status mcv_orb_distribute_octree(mcv_orb* h, const mcv_keypoint* in, int n, int min_x, int max_x, int min_y, int max_y, int n_target,
+                                     mcv_keypoint* out, int cap, int* n_out) {
+    if (!h || !n_out || n < 0 || (n > 0 && !in) || max_x <= min_x || max_y <= min_y || n_target < 0) return MCV_ERR_BAD_ARG;
+    *n_out = 0;
+    if (n == 0) return MCV_OK;
+    MCV_CUDA(cudaSetDevice(h->device));
+    const int bw = max_x - min_x, bh = max_y - min_y;
+    if (bw > 4095 || bh > 4095) return MCV_ERR_BAD_ARG;
+    std::vector<uint32_t> pts(n);
+    for (int i = 0; i < n; ++i) {
+        const int x = (int)in[i].x, y = (int)in[i].y, r = (int)in[i].response;
+        if (x < 0 || y < 0 || x >= bw || y >= bh || r < 0 || r > 255 || (float)x != in[i].x || (float)y != in[i].y || (float)r != in[i].response) {
+            set_error("distribute_octree: keypoints must be integer-valued, inside the box, response in [0,255]");
+            return MCV_ERR_BAD_ARG;
+        }
+        pts[i] = pack_pt(x, y, r);
+    }
+    const int out_cap = n_target + 8 + (int)roundf((float)bw / (float)bh);
+    mcv_status st;
+    if ((st = h->misc.reserve(((size_t)3 * n + out_cap + 4) * 4))) return st;
+    uint32_t* d_in = h->misc.as<uint32_t>(); uint32_t* d_a = d_in + n; uint32_t* d_b = d_a + n; uint32_t* d_out = d_b + n;
+    int* d_cnt = reinterpret_cast<int*>(d_out + out_cap);
+    MCV_CUDA(cudaMemcpyAsync(d_in, pts.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (launch_octree_standalone(d_in, n, bw, bh, n_target, d_a, d_b, d_out, d_cnt, out_cap, h->stream) < 0) { set_error("distribute_octree: unsupported size"); return MCV_ERR_CAPACITY; }
+    MCV_CUDA(cudaGetLastError());
+    int cnt = 0;
+    MCV_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+    MCV_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<uint32_t> res(cnt);
+    if (cnt) MCV_CUDA(cudaMemcpy(res.data(), d_out, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    *n_out = cnt;
+    if (cnt > cap) return MCV_ERR_CAPACITY;
+    for (int i = 0; i < cnt; ++i) out[i] = mcv_keypoint{(float)pt_x(res[i]), (float)pt_y(res[i]), 7.f, -1.f, (float)pt_r(res[i]), 0, -1};
+    return MCV_OK;
+}
+
+}  // extern "C"
+
+// =========================================================================================================
+// matcher (stateless in the reference: process-wide scratch on the current device, default stream 0 unless given)
+// =========================================================================================================
+namespace {
+struct MatchScratch {
+    DevBuf q, t, idx, dist, off, cidx;
+};
+MatchScratch g_ms;
+cudaStream_t g_match_stream = nullptr;
+
+mcv_status match_stream(cudaStream_t* s) {
+    if (mcv_device_count() < 1) { set_error("no CUDA device"); return MCV_ERR_NO_DEVICE; }
+    if (!g_match_stream) MCV_CUDA(cudaStreamCreateWithFlags(&g_match_stream, cudaStreamNonBlocking));
+    *s = g_match_stream;
+    return MCV_OK;
+}
+
+// runs brute-force 2-NN on host descriptors, returns idx/dist vectors (nq*2)
+mcv_status bf_host(const uint8_t* q, int nq, const uint8_t* t, int nt, std::vector<int32_t>& idx, std::vector<int32_t>& dist) {
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    idx.assign((size_t)nq * 2, -1); dist.assign((size_t)nq * 2, 0x7fffffff);
+    if (nq == 0) return MCV_OK;
+    if ((st = g_ms.q.reserve((size_t)nq * 32))) return st;
+    if ((st = g_ms.t.reserve(std::max<size_t>(32, (size_t)nt * 32)))) return st;
+    if ((st = g_ms.idx.reserve((size_t)nq * 8))) return st;
+    if ((st = g_ms.dist.reserve((size_t)nq * 8))) return st;
+    MCV_CUDA(cudaMemcpyAsync(g_ms.q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt) MCV_CUDA(cudaMemcpyAsync(g_ms.t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    if (launch_knn2_bf(g_ms.q.as<uint8_t>(), nq, g_ms.t.as<uint8_t>(), nt, 0, g_ms.idx.as<int32_t>(), g_ms.dist.as<int32_t>(), s) < 0) {
+        set_error("knn2_bf: train set larger than 4M rows per call (tile it with train_offset) or out of memory");
+        return MCV_ERR_CAPACITY;
+    }
+    MCV_CUDA(cudaGetLastError());
+    MCV_CUDA(cudaMemcpyAsync(idx.data(), g_ms.idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(dist.data(), g_ms.dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    return MCV_OK;
+}
+}  // namespace
+
+extern "C" {
+
+mcv_status mcv_knn2_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, mcv_dmatch* out, int* k_out) {
+    if (nq < 0 || nt < 0 || (nq > 0 && (!q || !out)) || (nt > 0 && !t)) return MCV_ERR_BAD_ARG;
+    std::vector<int32_t> idx, dist;
+    mcv_status st = bf_host(q, nq, t, nt, idx, dist);
+    if (st) return st;
+    for (int i = 0; i < nq; ++i)
+        for (int e = 0; e < 2; ++e) {
+            const int j = idx[2 * i + e];
+            out[2 * i + e] = j >= 0 ? mcv_dmatch{i, j, 0, (float)dist[2 * i + e]} : mcv_dmatch{i, -1, 0, 0.f};
+        }
+    if (k_out) *k_out = std::min(2, nt);
+    return MCV_OK;
+}
+
+mcv_status mcv_bf_match(const uint8_t* q, int nq, const uint8_t* t, int nt, mcv_dmatch* out) {
+    if (nq < 0 || nt < 1 || (nq > 0 && (!q || !out)) || !t) return MCV_ERR_BAD_ARG;
+    std::vector<int32_t> idx, dist;
+    mcv_status st = bf_host(q, nq, t, nt, idx, dist);
+    if (st) return st;
+    for (int i = 0; i < nq; ++i) out[i] = mcv_dmatch{i, idx[2 * i], 0, (float)dist[2 * i]};
+    return MCV_OK;
+}
+
+mcv_status mcv_knn2_firstparty(const uint8_t* q, int nq, const uint8_t* t, int nt, mcv_dmatch* out) {
+    if (nq < 0 || nt < 0 || (nq > 0 && (!q || !out)) || (nt > 0 && !t)) return MCV_ERR_BAD_ARG;
+    std::vector<int32_t> idx, dist;
+    mcv_status st = bf_host(q, nq, t, nt, idx, dist);
+    if (st) return st;
+    for (int i = 0; i < nq; ++i)
+        for (int e = 0; e < 2; ++e) {
+            const int j = idx[2 * i + e];  // padding: d = 999, idx = 0 (src/Matcher.cpp:258-259)
+            out[2 * i + e] = j >= 0 ? mcv_dmatch{i, j, -1, (float)dist[2 * i + e]} : mcv_dmatch{i, 0, -1, 999.f};
+        }
+    return MCV_OK;
+}
+
+mcv_status mcv_knn2_candidates(const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* cand_off, const int32_t* cand_idx, mcv_dmatch* out) {
+    if (nq < 0 || nt < 0 || (nq > 0 && (!q || !out || !cand_off))) return MCV_ERR_BAD_ARG;
+    if (nq == 0) return MCV_OK;
+    const int total = cand_off[nq];
+    if (total < 0 || (total > 0 && (!cand_idx || !t))) return MCV_ERR_BAD_ARG;
+    for (int i = 0; i < nq; ++i) if (cand_off[i + 1] < cand_off[i] || cand_off[i + 1] - cand_off[i] >= (1 << 20)) return MCV_ERR_BAD_ARG;
+    for (int i = 0; i < total; ++i) if (cand_idx[i] < 0 || cand_idx[i] >= nt) return MCV_ERR_BAD_ARG;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    if ((st = g_ms.q.reserve((size_t)nq * 32))) return st;
+    if ((st = g_ms.t.reserve(std::max<size_t>(32, (size_t)nt * 32)))) return st;
+    if ((st = g_ms.idx.reserve((size_t)nq * 8))) return st;
+    if ((st = g_ms.dist.reserve((size_t)nq * 8))) return st;
+    if ((st = g_ms.off.reserve((size_t)(nq + 1) * 4))) return st;
+    if ((st = g_ms.cidx.reserve(std::max<size_t>(4, (size_t)total * 4)))) return st;
+    MCV_CUDA(cudaMemcpyAsync(g_ms.q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt) MCV_CUDA(cudaMemcpyAsync(g_ms.t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(g_ms.off.p, cand_off, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (total) MCV_CUDA(cudaMemcpyAsync(g_ms.cidx.p, cand_idx, (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    launch_knn2_candidates(g_ms.q.as<uint8_t>(), nq, g_ms.t.as<uint8_t>(), g_ms.off.as<int32_t>(), g_ms.cidx.as<int32_t>(), g_ms.idx.as<int32_t>(),
+                           g_ms.dist.as<int32_t>(), s);
+    MCV_CUDA(cudaGetLastError());
+    std::vector<int32_t> idx((size_t)nq * 2), dist((size_t)nq * 2);
+    MCV_CUDA(cudaMemcpyAsync(idx.data(), g_ms.idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(dist.data(), g_ms.dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < nq; ++i)
+        for (int e = 0; e < 2; ++e) out[2 * i + e] = mcv_dmatch{i, idx[2 * i + e], -1, (float)dist[2 * i + e]};
+    return MCV_OK;
+}
+
+mcv_status mcv_knn2_bf_device(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, void* stream) {
+    if (nq < 0 || nt < 0 || (nq > 0 && (!d_q || !d_idx || !d_dist)) || (nt > 0 && !d_t)) return MCV_ERR_BAD_ARG;
+    if (launch_knn2_bf(d_q, nq, d_t, nt, train_offset, d_idx, d_dist, (cudaStream_t)stream) < 0) {
+        set_error("knn2_bf_device: train set larger than 4M rows per call or out of memory");
+        return MCV_ERR_CAPACITY;
+    }
+    MCV_CUDA(cudaGetLastError());
+    return MCV_OK;
+}
+
+mcv_status mcv_project_match(const mcv_keypoint* kps, const uint8_t* desc, int n, int w, int hgt, const float* scale_factors, int nlevels,
+                             const float* Rcw, const float* tcw, const float* intr, const float* mp_xyz, const uint8_t* mp_desc,
+                             const int32_t* mp_level, int n_mp, float r_threshold, int32_t* out_idx, int32_t* out_dist, int* n_matched) {
+    if (n < 0 || n_mp < 0 || w <= 0 || hgt <= 0 || nlevels < 1 || !scale_factors || !Rcw || !tcw || !intr || n >= (1 << 21)) return MCV_ERR_BAD_ARG;
+    if (n_mp > 0 && (!mp_xyz || !mp_desc || !mp_level || !out_idx || !out_dist)) return MCV_ERR_BAD_ARG;
+    if (n > 0 && (!kps || !desc)) return MCV_ERR_BAD_ARG;
+    for (int m = 0; m < n_mp; ++m) if (mp_level[m] < 0 || mp_level[m] >= nlevels) return MCV_ERR_BAD_ARG;
+    if (n_matched) *n_matched = 0;
+    if (n_mp == 0) return MCV_OK;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b_kps, b_desc, b_f, b_xyz, b_mpd, b_lvl, b_oi, b_od;
+    if ((st = b_kps.reserve(std::max<size_t>(28, (size_t)n * sizeof(mcv_keypoint))))) return st;
+    if ((st = b_desc.reserve(std::max<size_t>(32, (size_t)n * 32)))) return st;
+    if ((st = b_f.reserve((size_t)(nlevels + 16) * 4))) return st;
+    if ((st = b_xyz.reserve((size_t)n_mp * 12))) return st;
+    if ((st = b_mpd.reserve((size_t)n_mp * 32))) return st;
+    if ((st = b_lvl.reserve((size_t)n_mp * 4))) return st;
+    if ((st = b_oi.reserve((size_t)n_mp * 4))) return st;
+    if ((st = b_od.reserve((size_t)n_mp * 4))) return st;
+    std::vector<float> f(nlevels + 16);
+    memcpy(f.data(), Rcw, 36); memcpy(f.data() + 9, tcw, 12); memcpy(f.data() + 12, intr, 16);
+    memcpy(f.data() + 16, scale_factors, (size_t)nlevels * 4);
+    if (n) {
+        MCV_CUDA(cudaMemcpyAsync(b_kps.p, kps, (size_t)n * sizeof(mcv_keypoint), cudaMemcpyHostToDevice, s));
+        MCV_CUDA(cudaMemcpyAsync(b_desc.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    }
+    MCV_CUDA(cudaMemcpyAsync(b_f.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_xyz.p, mp_xyz, (size_t)n_mp * 12, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_mpd.p, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_lvl.p, mp_level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, s));
+    launch_project(b_kps.as<mcv_keypoint>(), b_desc.as<uint8_t>(), n, w, hgt, b_f.as<float>() + 16, b_f.as<float>(), b_xyz.as<float>(),
+                   b_mpd.as<uint8_t>(), b_lvl.as<int32_t>(), n_mp, r_threshold, b_oi.as<int32_t>(), b_od.as<int32_t>(), s);
+    MCV_CUDA(cudaGetLastError());
+    MCV_CUDA(cudaMemcpyAsync(out_idx, b_oi.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(out_dist, b_od.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    if (n_matched) { int c = 0; for (int m = 0; m < n_mp; ++m) c += out_idx[m] >= 0; *n_matched = c; }
+    return MCV_OK;
+}
+
+mcv_status mcv_debug_sincosf(const float* a, int n, float* so, float* co) {
+    if (n <= 0 || !a || !so || !co) return MCV_ERR_BAD_ARG;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b;
+    if ((st = b.reserve((size_t)n * 12))) return st;
+    float* d = b.as<float>();
+    MCV_CUDA(cudaMemcpyAsync(d, a, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    launch_debug_sincosf(d, n, d + n, d + 2 * (size_t)n, s);
+    MCV_CUDA(cudaGetLastError());
+    MCV_CUDA(cudaMemcpyAsync(so, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(co, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    return MCV_OK;
+}
+
+mcv_status mcv_debug_fast_atan2(const float* y, const float* x, int n, float* out) {
+    if (n <= 0 || !y || !x || !out) return MCV_ERR_BAD_ARG;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b;
+    if ((st = b.reserve((size_t)n * 12))) return st;
+    float* d = b.as<float>();
+    MCV_CUDA(cudaMemcpyAsync(d, y, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(d + n, x, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    launch_debug_atan2(d, d + n, n, d + 2 * (size_t)n, s);
+    MCV_CUDA(cudaGetLastError());
+    MCV_CUDA(cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    return MCV_OK;
+}
+
+mcv_status mcv_debug_popc_peak(int iters, double* popc_per_s, double* ms_out) {
+    if (iters <= 0) return MCV_ERR_BAD_ARG;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b;
+    if ((st = b.reserve(64))) return st;
+    const int blocks = NUM_SMS * 8, threads = 256;
+    launch_popc_peak(iters, b.as<unsigned>(), blocks, threads, s);  // warm-up
+    cudaEvent_t e0, e1;
+    MCV_CUDA(cudaEventCreate(&e0)); MCV_CUDA(cudaEventCreate(&e1));
+    MCV_CUDA(cudaEventRecord(e0, s));
+    launch_popc_peak(iters, b.as<unsigned>(), blocks, threads, s);
+    MCV_CUDA(cudaEventRecord(e1, s));
+    MCV_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MCV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    if (popc_per_s) *popc_per_s = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+    return MCV_OK;
+}
+
+}  // extern "C"
+
+// =========================================================================================================
+// three-camera rig
+// =========================================================================================================
+struct mcv_rig {
+    mcv_rig_params prm{};
+    mcv_orb* orb = nullptr;
+    DevBuf imgs, u_right, depth, best_dist;
+    int last_launches = 0;
+};
+
+extern "C" {
+
+mcv_status mcv_rig_create(const mcv_rig_params* p, int device, void* stream, mcv_rig** out) {
+    if (!p || !out) return MCV_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!(p->baseline > 0.f) || !(p->bf > 0.f)) { set_error("bad rig parameters"); return MCV_ERR_BAD_ARG; }
+    mcv_orb* o = nullptr;
+    mcv_status st = mcv_orb_create(&p->orb, device, stream, &o);
+    if (st) return st;
+    mcv_rig* r = new mcv_rig();
+    r->prm = *p; r->orb = o;
+    *out = r;
+    return MCV_OK;
+}
+
+void mcv_rig_destroy(mcv_rig* r) {
+    if (!r) return;
+    cudaSetDevice(r->orb->device);
+    cudaStreamSynchronize(r->orb->stream);
+    for (DevBuf* b : {&r->imgs, &r->u_right, &r->depth, &r->best_dist}) b->release();
+    mcv_orb_destroy(r->orb);
+    delete r;
+}
+
+int mcv_rig_max_keypoints(const mcv_rig* r) { return r ? mcv_orb_max_keypoints(r->orb, 0) : 0; }
+mcv_orb* mcv_rig_extractor(mcv_rig* r) { return r ? r->orb : nullptr; }
+int mcv_rig_last_launches(const mcv_rig* r) { return r ? r->last_launches : 0; }
+
+mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps, uint8_t* d_desc,
+                                 int32_t* d_counts, float* d_u_right, float* d_depth, int cap) {
+    if (!r || !d_imgs || n_frames <= 0 || !d_kps || !d_desc || !d_counts || !d_u_right || !d_depth) return MCV_ERR_BAD_ARG;
+    if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
+    if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
+    mcv_orb* h = r->orb;
+    MCV_CUDA(cudaSetDevice(h->device));
+    mcv_status st = ensure_workspace(h, w, hgt, 3 * n_frames, 1);
+    if (st) return st;
+    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints()"); return MCV_ERR_CAPACITY; }
+    if ((st = r->best_dist.reserve((size_t)n_frames * cap * 4))) return st;
+    st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap);
+    if (st) return st;
+    int n = h->last_launches;
+    n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
+                       d_depth, r->best_dist.as<int>(), nullptr, h->stream);
+    MCV_CUDA(cudaGetLastError());
+    r->last_launches = n;
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_sync(mcv_rig* r) {
+    if (!r) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaStreamSynchronize(r->orb->stream));
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, int imgs_on_device, mcv_keypoint* kps_out,
+                           uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device) {
+    if (!r || !imgs || n_frames <= 0 || !kps_out || !desc_out || !counts || !u_right || !depth_left) return MCV_ERR_BAD_ARG;
+    if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
+    mcv_orb* h = r->orb;
+    MCV_CUDA(cudaSetDevice(h->device));
+    mcv_status st;
+    const size_t img_bytes = (size_t)w * hgt, n_img = (size_t)3 * n_frames;
+    const uint8_t* d_imgs = imgs;
+    if (!imgs_on_device) {
+        if ((st = r->imgs.reserve(img_bytes * n_img))) return st;
+        MCV_CUDA(cudaMemcpyAsync(r->imgs.p, imgs, img_bytes * n_img, cudaMemcpyHostToDevice, h->stream));
+        d_imgs = r->imgs.as<uint8_t>();
+    }
+    mcv_keypoint* d_kps = kps_out; uint8_t* d_desc = desc_out; int* d_counts = counts; float* d_ur = u_right; float* d_dp = depth_left;
+    if (!out_on_device) {
+        if ((st = h->kps.reserve(n_img * cap * sizeof(mcv_keypoint)))) return st;
+        if ((st = h->desc.reserve(n_img * cap * 32))) return st;
+        if ((st = h->counts.reserve(n_img * 4))) return st;
+        if ((st = r->u_right.reserve((size_t)n_frames * cap * 4))) return st;
+        if ((st = r->depth.reserve((size_t)n_frames * cap * 4))) return st;
+        d_kps = h->kps.as<mcv_keypoint>(); d_desc = h->desc.as<uint8_t>(); d_counts = h->counts.as<int>();
+        d_ur = r->u_right.as<float>(); d_dp = r->depth.as<float>();
+    }
+    st = mcv_rig_process_async(r, d_imgs, n_frames, w, hgt, d_kps, d_desc, d_counts, d_ur, d_dp, cap);
+    if (st) return st;
+    if (!out_on_device) {
+        MCV_CUDA(cudaMemcpyAsync(kps_out, d_kps, n_img * cap * sizeof(mcv_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaMemcpyAsync(desc_out, d_desc, n_img * cap * 32, cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaMemcpyAsync(counts, d_counts, n_img * 4, cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaMemcpyAsync(u_right, d_ur, (size_t)n_frames * cap * 4, cudaMemcpyDeviceToHost, h->stream));
+        MCV_CUDA(cudaMemcpyAsync(depth_left, d_dp, (size_t)n_frames * cap * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    MCV_CUDA(cudaStreamSynchronize(h->stream));
+    return MCV_OK;
+}
+
+mcv_status mcv_stereo_match(mcv_orb* left, mcv_orb* right, const mcv_keypoint* kps_l, const uint8_t* desc_l, int n_l, const mcv_keypoint* kps_r,
+                            const uint8_t* desc_r, int n_r, float bf, float baseline, float* u_right, float* depth_left, int32_t* best_dist,
+                            int32_t* best_r) {
+    if (!left || !right || n_l < 0 || n_r < 0 || !u_right || !depth_left || !(baseline > 0.f)) return MCV_ERR_BAD_ARG;
+    if (!left->have_plan || !right->have_plan || left->last_images < 1 || right->last_images < 1) { set_error("stereo_match: extract on both handles first"); return MCV_ERR_BAD_ARG; }
+    if (left->device != right->device || memcmp(&left->plan, &right->plan, sizeof(Plan)) != 0) { set_error("stereo_match: handles must share device, parameters and image size"); return MCV_ERR_BAD_ARG; }
+    if (n_l == 0) return MCV_OK;
+    if (n_r >= (1 << 20) || !kps_l || !desc_l || (n_r > 0 && (!kps_r || !desc_r))) return MCV_ERR_BAD_ARG;
+    for (int i = 0; i < n_l; ++i) if (kps_l[i].octave < 0 || kps_l[i].octave >= left->plan.n_levels) return MCV_ERR_BAD_ARG;
+    for (int i = 0; i < n_r; ++i) if (kps_r[i].octave < 0 || kps_r[i].octave >= left->plan.n_levels) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaSetDevice(left->device));
+    cudaStream_t s = left->stream;
+    MCV_CUDA(cudaStreamSynchronize(right->stream));
+    mcv_status st;
+    const size_t kb = sizeof(mcv_keypoint);
+    const size_t need = (size_t)n_l * (kb + 32 + 16) + (size_t)std::max(n_r, 1) * (kb + 32) + 256;
+    if ((st = left->misc.reserve(need))) return st;
+    uint8_t* base = left->misc.as<uint8_t>();
+    float* d_ur = reinterpret_cast<float*>(base); float* d_dp = d_ur + n_l; int* d_bd = reinterpret_cast<int*>(d_dp + n_l); int* d_br = d_bd + n_l;
+    uint8_t* d_dl = reinterpret_cast<uint8_t*>(d_br + n_l); uint8_t* d_dr = d_dl + (size_t)n_l * 32;
+    mcv_keypoint* d_kl = reinterpret_cast<mcv_keypoint*>(d_dr + (size_t)std::max(n_r, 1) * 32); mcv_keypoint* d_kr = d_kl + n_l;
+    MCV_CUDA(cudaMemcpyAsync(d_kl, kps_l, n_l * kb, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(d_dl, desc_l, (size_t)n_l * 32, cudaMemcpyHostToDevice, s));
+    if (n_r) {
+        MCV_CUDA(cudaMemcpyAsync(d_kr, kps_r, n_r * kb, cudaMemcpyHostToDevice, s));
+        MCV_CUDA(cudaMemcpyAsync(d_dr, desc_r, (size_t)n_r * 32, cudaMemcpyHostToDevice, s));
+    }
+    launch_stereo_pair(left->plan, left->pyr.as<uint8_t>(), right->pyr.as<uint8_t>(), d_kl, d_dl, n_l, d_kr, d_dr, n_r, bf, baseline, d_ur, d_dp, d_bd,
+                       d_br, s);
+    MCV_CUDA(cudaGetLastError());
+    MCV_CUDA(cudaMemcpyAsync(u_right, d_ur, (size_t)n_l * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(depth_left, d_dp, (size_t)n_l * 4, cudaMemcpyDeviceToHost, s));
+    if (best_dist) MCV_CUDA(cudaMemcpyAsync(best_dist, d_bd, (size_t)n_l * 4, cudaMemcpyDeviceToHost, s));
+    if (best_r) MCV_CUDA(cudaMemcpyAsync(best_r, d_br, (size_t)n_l * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    return MCV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+// Hamming 2-NN matching kernels (sm_100a). Integer pipe only: LOP3 (xor), POPC, IADD3, IMNMX.
+//
+//   k_knn2_bf          : brute force, replaces cv::BFMatcher(NORM_HAMMING).knnMatch as used by Matcher::KnnMatch(Mat, Mat)
+//                        (src/Matcher.cpp:304-308) and the O(Q*T) LoopBody (src/Matcher.cpp:245-281). Result per query =
+//                        the two smallest (distance, trainIdx) pairs in lexicographic order, which is what both the
+//                        OpenCV matcher and the first-party strict-'<' streaming loop produce.
+//   k_knn2_candidates  : the same 2-NN over a per-query candidate list (src/Frame.cpp:199-225, src/Object.cpp:217-226,
+//                        src/Map.cpp:495-527, src/Matcher.cpp:162-181); ties resolve by position in the list.
+//   k_project_match    : Object::ProjectBunchMapPoints (src/Object.cpp:208-236) incl. the 30x30 grid window query
+//                        (src/Object.cpp:249-308) and FilterRatio(0.6) / FilterThreshold(46).
+//
+// A (distance, index) pair is packed into one unsigned key, distance in the high bits, so a lexicographic top-2 update is
+// three integer min/max instructions and a cross-lane / cross-CTA merge is the same operation.
+#include "devmath.cuh"
+#include "engine.h"
+
+namespace mcv {
+
+constexpr int BF_THREADS = 128;        // queries per CTA (one per thread)
+constexpr int BF_TILE = 256;           // train descriptors staged in shared memory per step
+constexpr int BF_IDX_BITS = 22;        // trainIdx bits in the key; distance (<= 256) above them
+constexpr unsigned BF_SENT = 0xffffffffu;
+
+__device__ __forceinline__ void top2_update(unsigned& k0, unsigned& k1, unsigned key) {
+    k1 = min(k1, max(k0, key));
+    k0 = min(k0, key);
+}
+
+// grid = (ceil(nq / BF_THREADS), n_splits). Each CTA scans train rows [split * per_split, ...) for its queries and writes
+// the partial top-2 keys to part[split][q][2].
+__global__ void __launch_bounds__(BF_THREADS) k_knn2_bf(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
+                                                        int per_split, unsigned* __restrict__ part) {
+    __shared__ uint4 s_t[BF_TILE * 2];
+    const int qi = blockIdx.x * BF_THREADS + threadIdx.x;
+    const int t_begin = blockIdx.y * per_split, t_end = min(nt, t_begin + per_split);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (qi < nq) {
+        a0 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)qi * 32));
+        a1 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)qi * 32 + 16));
+    }
+    unsigned k0 = BF_SENT, k1 = BF_SENT;
+    for (int base = t_begin; base < t_end; base += BF_TILE) {
+        const int n = min(BF_TILE, t_end - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * n; i += BF_THREADS) s_t[i] = __ldg(reinterpret_cast<const uint4*>(t + (size_t)base * 32) + i);
+        __syncthreads();
+        unsigned key_base = (unsigned)base;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const uint4 b0 = s_t[2 * j], b1 = s_t[2 * j + 1];
+            const unsigned d = (unsigned)hamming256(a0, a1, b0, b1);
+            top2_update(k0, k1, (d << BF_IDX_BITS) + key_base + (unsigned)j);
+        }
+    }
+    if (qi < nq) {
+        unsigned* o = part + ((size_t)blockIdx.y * nq + qi) * 2;
+        o[0] = k0; o[1] = k1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_knn2_merge(const unsigned* __restrict__ part, int nq, int n_splits, int train_offset,
+                                                    int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned k0 = BF_SENT, k1 = BF_SENT;
+    for (int s = 0; s < n_splits; ++s) {
+        const unsigned* p = part + ((size_t)s * nq + qi) * 2;
+        top2_update(k0, k1, p[0]);
+        top2_update(k0, k1, p[1]);
+    }
+    const unsigned mask = (1u << BF_IDX_BITS) - 1;
+    idx[2 * qi] = k0 == BF_SENT ? -1 : (int)(k0 & mask) + train_offset;
+    dist[2 * qi] = k0 == BF_SENT ? 0x7fffffff : (int)(k0 >> BF_IDX_BITS);
+    idx[2 * qi + 1] = k1 == BF_SENT ? -1 : (int)(k1 & mask) + train_offset;
+    dist[2 * qi + 1] = k1 == BF_SENT ? 0x7fffffff : (int)(k1 >> BF_IDX_BITS);
+}
+
+// scratch for the partial keys: grown on demand, one per device (the matcher is stateless in the reference)
+static unsigned* g_part = nullptr;
+static size_t g_part_bytes = 0;
+
+int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, cudaStream_t s) {
+    if (nq <= 0) return 0;
+    if (nt > (1 << BF_IDX_BITS)) return -1;
+    const int q_blocks = (nq + BF_THREADS - 1) / BF_THREADS;
+    // enough CTAs for ~4 per SM, but at least BF_TILE train rows each
+    int n_splits = std::max(1, std::min((4 * NUM_SMS + q_blocks - 1) / q_blocks, (nt + BF_TILE - 1) / BF_TILE));
+    int per_split = nt > 0 ? ((nt + n_splits - 1) / n_splits + BF_TILE - 1) / BF_TILE * BF_TILE : BF_TILE;
+    n_splits = nt > 0 ? (nt + per_split - 1) / per_split : 1;
+    const size_t need = (size_t)n_splits * nq * 2 * sizeof(unsigned);
+    if (need > g_part_bytes) {
+        if (g_part) cudaFree(g_part);
+        if (cudaMalloc(&g_part, need) != cudaSuccess) { g_part = nullptr; g_part_bytes = 0; return -1; }
+        g_part_bytes = need;
+    }
+    k_knn2_bf<<<dim3(q_blocks, n_splits), BF_THREADS, 0, s>>>(d_q, nq, d_t, nt, per_split, g_part);
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(g_part, nq, n_splits, train_offset, d_idx, d_dist);
+    return 2;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// candidate lists: one warp per query
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_top2_merge(unsigned& k0, unsigned& k1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned n0 = min(k0, o0), n1 = min(max(k0, o0), min(k1, o1));
+        k0 = n0; k1 = n1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_knn2_candidates(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t,
+                                                         const int32_t* __restrict__ off, const int32_t* __restrict__ cidx,
+                                                         int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)qi * 32));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)qi * 32 + 16));
+    const int b = off[qi], e = off[qi + 1];
+    const unsigned SENT = 999u << 20;  // the reference's d = {999, 999}, idx = {0, 0} (src/Matcher.cpp:258-259)
+    unsigned k0 = SENT, k1 = SENT;
+    for (int p = b + lane; p < e; p += 32) {
+        const int j = cidx[p];
+        const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(t + (size_t)j * 32));
+        const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(t + (size_t)j * 32 + 16));
+        top2_update(k0, k1, ((unsigned)hamming256(a0, a1, b0, b1) << 20) | (unsigned)(p - b));
+    }
+    warp_top2_merge(k0, k1);
+    if (lane == 0) {
+        idx[2 * qi] = (int)(k0 & 0xfffffu); dist[2 * qi] = (int)(k0 >> 20);
+        idx[2 * qi + 1] = (int)(k1 & 0xfffffu); dist[2 * qi + 1] = (int)(k1 >> 20);
+    }
+}
+
+int launch_knn2_candidates(const uint8_t* d_q, int nq, const uint8_t* d_t, const int32_t* d_off, const int32_t* d_cidx, int32_t* d_idx,
+                           int32_t* d_dist, cudaStream_t s) {
+    if (nq <= 0) return 0;
+    k_knn2_candidates<<<(nq + 7) / 8, 256, 0, s>>>(d_q, nq, d_t, d_off, d_cidx, d_idx, d_dist);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// projection matching: one warp per MapPoint, brute-force gate over the camera's keypoints with a 64-bit key
+// (distance, grid-cell-major candidate order) so ties resolve exactly like the reference's candidate list.
+// pose = Rcw (9, row-major) | tcw (3) | fx fy cx cy
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GRID_N = 30;  // FRAME_GRID_COLS / ROWS, include/Object.hpp:27-28
+
+__global__ void __launch_bounds__(256) k_project_match(const mcv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int n, int w,
+                                                       int h, const float* __restrict__ scale, const float* __restrict__ pose,
+                                                       const float* __restrict__ xyz, const uint8_t* __restrict__ mp_desc,
+                                                       const int32_t* __restrict__ mp_level, int n_mp, float r_th,
+                                                       int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= n_mp) return;
+    if (lane == 0) { out_idx[m] = -1; out_dist[m] = -1; }
+    const float X = xyz[3 * m], Y = xyz[3 * m + 1], Z = xyz[3 * m + 2];
+    float pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)  // cv::Mat 3x3 * 3x1 + 3x1 in float, left to right (small-matrix gemm path)
+        pc[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pose[3 * r], X), __fmul_rn(pose[3 * r + 1], Y)), __fmul_rn(pose[3 * r + 2], Z)), pose[9 + r]);
+    if (pc[2] < 0.f) return;
+    // Pinhole::project (modules/camera/Pinhole.cpp:45-47)
+    const float x = __fadd_rn(__fdiv_rn(__fmul_rn(pose[12], pc[0]), pc[2]), pose[14]);
+    const float y = __fadd_rn(__fdiv_rn(__fmul_rn(pose[13], pc[1]), pc[2]), pose[15]);
+    const float r = __fmul_rn(r_th, scale[mp_level[m]]);
+    // GetFeaturesInArea (src/Object.cpp:263-308)
+    if (!(x >= 0.f && y >= 0.f && x < (float)w && y < (float)h)) return;
+    const float winv = (float)((double)GRID_N / w), hinv = (float)((double)GRID_N / h);
+    const int min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(x, r), winv)));
+    const int max_cx = min(GRID_N - 1, (int)ceilf(__fmul_rn(__fadd_rn(x, r), winv)));
+    const int min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(y, r), hinv)));
+    const int max_cy = min(GRID_N - 1, (int)ceilf(__fmul_rn(__fadd_rn(y, r), hinv)));
+    if (min_cx >= GRID_N || max_cx < 0 || min_cy >= GRID_N || max_cy < 0) return;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(mp_desc + (size_t)m * 32));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(mp_desc + (size_t)m * 32 + 16));
+    const unsigned long long SENT = 999ull << 32;
+    unsigned long long k0 = SENT, k1 = SENT;
+    for (int j = lane; j < n; j += 32) {
+        const float kx = kps[j].x, ky = kps[j].y;
+        // PosInGrid (src/Object.cpp:249-257): round(), cells outside [0, 30) are not in the grid at all
+        const int gx = (int)roundf(__fmul_rn(kx, winv)), gy = (int)roundf(__fmul_rn(ky, hinv));
+        if (gx < 0 || gx >= GRID_N || gy < 0 || gy >= GRID_N) continue;
+        if (gx < min_cx || gx > max_cx || gy < min_cy || gy > max_cy) continue;
+        if (!(fabsf(__fsub_rn(kx, x)) < r && fabsf(__fsub_rn(ky, y)) < r)) continue;
+        const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32));
+        const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32 + 16));
+        // candidate order: ix outer, iy inner, ascending keypoint index inside a cell
+        const unsigned long long key = ((unsigned long long)hamming256(a0, a1, b0, b1) << 32) | ((unsigned long long)(gx * GRID_N + gy) << 21) | (unsigned)j;
+        const unsigned long long hi = key > k0 ? key : k0;
+        k1 = k1 < hi ? k1 : hi;
+        k0 = k0 < key ? k0 : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0, l1 = k1 < o1 ? k1 : o1;
+        k0 = lo; k1 = hi < l1 ? hi : l1;
+    }
+    if (k0 == SENT) return;
+    const float d0 = (float)(unsigned)(k0 >> 32), d1 = (float)(unsigned)(k1 >> 32);
+    if (!(__fdiv_rn(d0, d1) <= 0.6f)) return;  // FilterRatio() default
+    if (d0 > 46.0f) return;                    // FilterThreshold() default ORB_GOOD_THRESHOLD
+    if (lane == 0) { out_idx[m] = (int)(k0 & 0x1fffffu); out_dist[m] = (int)(k0 >> 32); }
+}
+
+int launch_project(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_scale, const float* d_pose,
+                   const float* d_xyz, const uint8_t* d_mp_desc, const int32_t* d_level, int n_mp, float r_th, int32_t* d_idx,
+                   int32_t* d_dist, cudaStream_t s) {
+    if (n_mp <= 0) return 0;
+    k_project_match<<<(n_mp + 7) / 8, 256, 0, s>>>(d_kps, d_desc, n, w, h, d_scale, d_pose, d_xyz, d_mp_desc, d_level, n_mp, r_th, d_idx, d_dist);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// test taps + integer-pipe peak
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_debug_sincosf(const float* a, int n, float* s, float* c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sincosf_glibc(a[i], &s[i], &c[i]);
+}
+__global__ void k_debug_atan2(const float* y, const float* x, int n, float* o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = fast_atan2_deg(y[i], x[i]);
+}
+int launch_debug_sincosf(const float* d_a, int n, float* d_s, float* d_c, cudaStream_t s) {
+    k_debug_sincosf<<<(n + 255) / 256, 256, 0, s>>>(d_a, n, d_s, d_c);
+    return 1;
+}
+int launch_debug_atan2(const float* d_y, const float* d_x, int n, float* d_o, cudaStream_t s) {
+    k_debug_atan2<<<(n + 255) / 256, 256, 0, s>>>(d_y, d_x, n, d_o);
+    return 1;
+}
+
+// Sustained xor+popc throughput: 8 independent (xor, popc, add) chains per thread, `iters` rounds.
+__global__ void __launch_bounds__(256) k_popc_peak(int iters, unsigned* sink) {
+    unsigned a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = threadIdx.x * 2654435761u + k * 40503u + blockIdx.x; acc[k] = 0; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[k] += __popc(a[k] ^ (unsigned)i); a[k] += acc[k]; }
+    }
+    unsigned r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += acc[k];
+    if (r == 0x12345678u) sink[0] = r;
+}
+int launch_popc_peak(int iters, unsigned* d_sink, int blocks, int threads, cudaStream_t s) {
+    k_popc_peak<<<blocks, threads, 0, s>>>(iters, d_sink);
+    return 1;
+}
+
+}  // namespace mcv

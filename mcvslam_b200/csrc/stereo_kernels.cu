@@ -1,0 +1,217 @@
+// Left/right stereo matching for a batch of frames (sm_100a). Replaces Frame::ComputeStereoMatch (src/Frame.cpp:150-328).
+//
+// k_stereo_match: one warp per left keypoint.
+//   * candidate gate, evaluated for all right keypoints in ascending index order (== the order vRowIndices[row] lists them):
+//     row band floor(yR - r) <= (int)vL <= ceil(yR + r) with r = 10 * scale[octR]  (src/Frame.cpp:160-168),
+//     |octR - octL| <= 1, uL - maxD <= uR <= uL - 1                                 (src/Frame.cpp:199-215);
+//   * Hamming 2-NN over the candidates with strict '<' streaming semantics == lexicographic (distance, index) top-2
+//     (Matcher::KnnMatch + LoopBody, src/Matcher.cpp:245-302), sentinel distance 999;
+//   * FilterRatio(0.70) and FilterThreshold(int(46 * 0.75) = 34)                    (src/Frame.cpp:225);
+//   * 11x11 SAD of centre-subtracted patches at 11 integer shifts on the keypoint's pyramid level, parabola sub-pixel fit,
+//     disparity / depth                                                            (src/Frame.cpp:228-303).
+// k_stereo_median: one CTA per frame; the (size/2)-th smallest SAD via a two-pass radix select, then invalidates matches
+//     with SAD > 1.6 * median or < 0.4 * median                                    (src/Frame.cpp:307-323).
+#include "devmath.cuh"
+#include "engine.h"
+
+namespace mcv {
+
+constexpr int ST_WARPS = 8;
+
+struct StereoArgs {
+    const uint8_t* pyr_l; const uint8_t* pyr_r;    // image-0 pyramid bases; frame f adds f * frame_pyr_stride
+    size_t frame_pyr_stride;
+    const mcv_keypoint* kl; const mcv_keypoint* kr; const uint8_t* dl; const uint8_t* dr;
+    const int* nl; const int* nr;                  // per-frame counts (stride count_stride), or NULL -> nl_fixed / nr_fixed
+    int nl_fixed, nr_fixed;
+    size_t frame_kp_stride;                        // keypoints between consecutive frames (kl/kr/dl/dr/outputs of L)
+    int count_stride;
+    float bf, baseline;
+    float* u_right; float* depth; int* best_dist; int* best_r;
+    size_t out_stride;
+};
+
+__global__ void __launch_bounds__(32 * ST_WARPS) k_stereo_match(const __grid_constant__ StereoArgs A, const __grid_constant__ Plan P) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * ST_WARPS + (threadIdx.x >> 5);
+    const int nl = A.nl ? A.nl[(size_t)f * A.count_stride] : A.nl_fixed;
+    const int nr = A.nr ? A.nr[(size_t)f * A.count_stride] : A.nr_fixed;
+    if (iL >= nl) return;
+    const mcv_keypoint* kl = A.kl + (size_t)f * A.frame_kp_stride;
+    const mcv_keypoint* kr = A.kr + (size_t)f * A.frame_kp_stride;
+    const uint8_t* dl = A.dl + (size_t)f * A.frame_kp_stride * 32;
+    const uint8_t* dr = A.dr + (size_t)f * A.frame_kp_stride * 32;
+    float* o_ur = A.u_right + (size_t)f * A.out_stride;
+    float* o_dp = A.depth + (size_t)f * A.out_stride;
+    int* o_bd = A.best_dist + (size_t)f * A.out_stride;
+    int* o_br = A.best_r ? A.best_r + (size_t)f * A.out_stride : nullptr;
+    if (lane == 0) { o_ur[iL] = -1.0f; o_dp[iL] = -1.0f; o_bd[iL] = -1; if (o_br) o_br[iL] = -1; }
+
+    const int n_rows = P.h;
+    const float uL = kl[iL].x, vL = kl[iL].y;
+    const int levelL = kl[iL].octave;
+    const float maxD = fminf(__fdiv_rn(A.bf, A.baseline), 1000.0f);
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, 1.0f);
+    if (vL < 0.f || (int)vL >= n_rows || maxU < 0.f) return;
+    const int row = (int)vL;
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(dl + (size_t)iL * 32));
+    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(dl + (size_t)iL * 32 + 16));
+    // per-lane streaming top-2 over this lane's candidates (ascending iR), keys = dist << 20 | iR
+    const unsigned SENT = 999u << 20;
+    unsigned k0 = SENT, k1 = SENT;
+    for (int i0 = 0; i0 < nr; i0 += 32) {
+        const int iR = i0 + lane;
+        if (iR < nr) {
+            const float uR = kr[iR].x, yR = kr[iR].y;
+            const int octR = kr[iR].octave;
+            const float r = __fmul_rn(10.f, P.lv[octR].scale);
+            const int maxr = (int)ceilf(__fadd_rn(yR, r)), minr = (int)floorf(__fsub_rn(yR, r));
+            if (row >= minr && row <= maxr && octR >= levelL - 1 && octR <= levelL + 1 && uR >= minU && uR <= maxU) {
+                const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(dr + (size_t)iR * 32));
+                const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(dr + (size_t)iR * 32 + 16));
+                const unsigned key = ((unsigned)hamming256(q0, q1, t0, t1) << 20) | (unsigned)iR;
+                if (key < k0) { k1 = k0; k0 = key; } else if (key < k1) k1 = key;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned n0 = min(k0, o0), n1 = min(max(k0, o0), min(k1, o1));
+        k0 = n0; k1 = n1;
+    }
+    if (k0 == SENT) return;  // no candidate
+    const int d0 = (int)(k0 >> 20), d1 = (int)(k1 >> 20), bestR = (int)(k0 & 0xfffffu);
+    if (!(__fdiv_rn((float)d0, (float)d1) <= 0.70f)) return;   // FilterRatio(0.70)
+    if ((float)d0 > 34.0f) return;                             // FilterThreshold(46 * 0.75 -> int 34)
+
+    // sub-pixel refinement on level `levelL` of both pyramids
+    const LevelGeom& g = P.lv[levelL];
+    const float uR0 = kr[bestR].x;
+    const float sc = g.inv_scale;
+    const float suL = roundf(__fmul_rn(uL, sc)), svL = roundf(__fmul_rn(vL, sc)), suR0 = roundf(__fmul_rn(uR0, sc));
+    const int w = 5, L = 5;
+    if (svL - w < 0 || svL + w + 1 >= g.h || suL - w < 0 || suL + w + 1 >= g.w) return;
+    if (suR0 + L - w < 0 || suR0 + L + w + 1 >= g.w) return;
+    if (suR0 - L - w < 0) return;  // the reference would throw on this negative colRange; unreachable for quadtree keypoints
+    const uint8_t* IL = A.pyr_l + (size_t)f * A.frame_pyr_stride + g.img_off;
+    const uint8_t* IR = A.pyr_r + (size_t)f * A.frame_pyr_stride + g.img_off;
+    const int cy = (int)svL, cxL = (int)suL, cxR = (int)suR0;
+    const int lc = IL[(size_t)cy * g.pitch + cxL];
+    int sad[11];
+#pragma unroll
+    for (int s = 0; s < 11; ++s) sad[s] = 0;
+    const uint8_t* rrow_c = IR + (size_t)cy * g.pitch + cxR;
+    for (int p = lane; p < 121; p += 32) {
+        const int yy = p / 11 - w, xx = p % 11 - w;
+        const int lv = IL[(size_t)(cy + yy) * g.pitch + cxL + xx] - lc;
+        const uint8_t* rr = IR + (size_t)(cy + yy) * g.pitch + cxR + xx;
+#pragma unroll
+        for (int s = 0; s < 11; ++s) sad[s] += abs(lv - ((int)rr[s - L] - (int)rrow_c[s - L]));
+    }
+#pragma unroll
+    for (int s = 0; s < 11; ++s)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sad[s] += __shfl_xor_sync(0xffffffffu, sad[s], o);
+    int bestDist = 0x7fffffff, bestinc = 0;
+#pragma unroll
+    for (int s = 0; s < 11; ++s) if (sad[s] < bestDist) { bestDist = sad[s]; bestinc = s - L; }
+    if (bestinc == -L || bestinc == L) return;
+    float dist1 = 0.f, dist2 = 0.f, dist3 = 0.f;
+#pragma unroll
+    for (int s = 1; s < 10; ++s) if (s - L == bestinc) { dist1 = (float)sad[s - 1]; dist2 = (float)sad[s]; dist3 = (float)sad[s + 1]; }
+    const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+    if (deltaR < -1.f || deltaR > 1.f) return;
+    const float bestuR = __fmul_rn(g.scale, __fadd_rn(__fadd_rn(suR0, (float)bestinc), deltaR));
+    const float disparity = __fsub_rn(uL, bestuR);
+    if (disparity >= 1.0f && disparity < maxD) {
+        if (lane == 0) {
+            o_dp[iL] = __fdiv_rn(A.bf, disparity);
+            o_ur[iL] = bestuR;
+            o_bd[iL] = bestDist;
+            if (o_br) o_br[iL] = bestR;
+        }
+    }
+}
+
+// SAD values are < 2^16 (121 * 510 = 61710).
+__global__ void __launch_bounds__(256) k_stereo_median(const __grid_constant__ StereoArgs A) {
+    __shared__ int hist[256];
+    __shared__ int s_sel, s_rem, s_total;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int nl = A.nl ? A.nl[(size_t)f * A.count_stride] : A.nl_fixed;
+    float* o_ur = A.u_right + (size_t)f * A.out_stride;
+    float* o_dp = A.depth + (size_t)f * A.out_stride;
+    const int* o_bd = A.best_dist + (size_t)f * A.out_stride;
+    hist[tid] = 0;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < nl; i += 256) { const int d = o_bd[i]; if (d >= 0) { atomicAdd(&hist[d >> 8], 1); ++mine; } }
+    if (mine) atomicAdd(&s_total, mine);
+    __syncthreads();
+    const int total = s_total;
+    if (total == 0) return;
+    if (tid == 0) {
+        int k = total / 2, b = 0;  // index (size_t)(size * 1.0 / 2) of the sorted list
+        while (k >= hist[b]) { k -= hist[b]; ++b; }
+        s_sel = b; s_rem = k;
+    }
+    __syncthreads();
+    const int hi = s_sel, k2 = s_rem;
+    __syncthreads();
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < nl; i += 256) { const int d = o_bd[i]; if (d >= 0 && (d >> 8) == hi) atomicAdd(&hist[d & 255], 1); }
+    __syncthreads();
+    if (tid == 0) {
+        int k = k2, b = 0;
+        while (k >= hist[b]) { k -= hist[b]; ++b; }
+        s_sel = (hi << 8) | b;
+    }
+    __syncthreads();
+    const float median = (float)s_sel;
+    const float th_max = __fmul_rn(1.6f, median);
+    const float th_min = (float)(0.4 * (double)median);
+    for (int i = tid; i < nl; i += 256) {
+        const int d = o_bd[i];
+        if (d >= 0 && ((float)d > th_max || (float)d < th_min)) { o_ur[i] = -1.0f; o_dp[i] = -1.0f; }
+    }
+}
+
+static int run_stereo(const StereoArgs& A, const Plan& P, int n_frames, int max_left, cudaStream_t s) {
+    dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, n_frames);
+    k_stereo_match<<<grid, 32 * ST_WARPS, 0, s>>>(A, P);
+    k_stereo_median<<<n_frames, 256, 0, s>>>(A);
+    return 2;
+}
+
+int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps, const uint8_t* d_desc, const int* d_counts, int cap,
+                  int n_frames, int left_cam, int right_cam, int cams_per_frame, float bf, float baseline, float* d_u_right, float* d_depth,
+                  int* d_best_dist, int* d_best_r, cudaStream_t s) {
+    StereoArgs A{};
+    A.pyr_l = d_pyr + (size_t)left_cam * P.pyr_bytes; A.pyr_r = d_pyr + (size_t)right_cam * P.pyr_bytes;
+    A.frame_pyr_stride = (size_t)cams_per_frame * P.pyr_bytes;
+    A.kl = d_kps + (size_t)left_cam * cap; A.kr = d_kps + (size_t)right_cam * cap;
+    A.dl = d_desc + (size_t)left_cam * cap * 32; A.dr = d_desc + (size_t)right_cam * cap * 32;
+    A.nl = d_counts + left_cam; A.nr = d_counts + right_cam; A.count_stride = cams_per_frame;
+    A.frame_kp_stride = (size_t)cams_per_frame * cap;
+    A.bf = bf; A.baseline = baseline;
+    A.u_right = d_u_right; A.depth = d_depth; A.best_dist = d_best_dist; A.best_r = d_best_r; A.out_stride = cap;
+    return run_stereo(A, P, n_frames, cap, s);
+}
+
+int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_pyr_r, const mcv_keypoint* d_kl, const uint8_t* d_dl, int nl,
+                       const mcv_keypoint* d_kr, const uint8_t* d_dr, int nr, float bf, float baseline, float* d_u_right, float* d_depth,
+                       int* d_best_dist, int* d_best_r, cudaStream_t s) {
+    StereoArgs A{};
+    A.pyr_l = d_pyr_l; A.pyr_r = d_pyr_r; A.frame_pyr_stride = 0;
+    A.kl = d_kl; A.kr = d_kr; A.dl = d_dl; A.dr = d_dr;
+    A.nl = nullptr; A.nr = nullptr; A.nl_fixed = nl; A.nr_fixed = nr; A.frame_kp_stride = 0; A.count_stride = 0;
+    A.bf = bf; A.baseline = baseline;
+    A.u_right = d_u_right; A.depth = d_depth; A.best_dist = d_best_dist; A.best_r = d_best_r; A.out_stride = 0;
+    if (nl <= 0) return 0;
+    return run_stereo(A, P, 1, nl, s);
+}
+
+}  // namespace mcv

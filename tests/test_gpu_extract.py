@@ -1,0 +1,120 @@
+"""GPU parity: ORB extraction through the C ABI vs the CPU oracle and the committed cv2-generated fixtures.
+Bit-exact bar for coordinates, octaves, responses, angles (0 ulp — required for descriptor parity) and descriptors."""
+import numpy as np
+import pytest
+
+from mcvslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_same_kps(k, d, gk, gd, tag):
+    assert len(k) == len(gk), f"{tag}: count {len(k)} vs {len(gk)}"
+    for f in gk.dtype.names:
+        bad = np.nonzero(k[f].view(np.uint32) != gk[f].view(np.uint32))[0] if k[f].dtype.kind == "f" else np.nonzero(k[f] != gk[f])[0]
+        assert len(bad) == 0, f"{tag}: field {f} differs at {bad[:8]} ({len(bad)} of {len(k)}): {k[f][bad[:4]]} vs {gk[f][bad[:4]]}"
+    bad = np.nonzero((d != gd).any(axis=1))[0]
+    assert len(bad) == 0, f"{tag}: descriptors differ in {len(bad)} rows, first {bad[:8]}"
+
+
+def test_float_ports(api, oracle):
+    rng = np.random.default_rng(0)
+    a = rng.uniform(0, 6.5, 2_000_000).astype(np.float32)
+    a[:8] = [0, 1e-6, np.pi / 4, 0.7853982, np.pi / 2, np.pi, 2 * np.pi, 6.2831855]
+    s, c = api.debug_sincosf(a)
+    so, co = oracle.sincosf(a)
+    assert (s.view(np.uint32) == so.view(np.uint32)).all() and (c.view(np.uint32) == co.view(np.uint32)).all()
+    y = rng.integers(-300000, 300000, 1_000_000).astype(np.float32); x = rng.integers(-300000, 300000, 1_000_000).astype(np.float32)
+    y[:200] = 0; x[100:300] = 0
+    assert (api.debug_fast_atan2(y, x).view(np.uint32) == oracle.fast_atan2(y, x).view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("shape,seed", [((480, 640), 1234), ((720, 1280), 7), ((512, 512), 9)])
+def test_stages_vs_oracle(api, oracle, shape, seed):
+    h, w = shape
+    img = synth.scene(seed, w, h)
+    nf = 5000 if w == 1280 else 2000
+    E = api.ORB(nf, 1.2, 8, 28, 15)
+    O = oracle.Orb(nf, 1.2, 8, 28, 15, debug=True)
+    n, k, d = E.Extract(img)
+    no, ko, do = O.extract(img)
+    assert (E.mvScaleFactor == O.scale).all() and (E.mnFeaturesPerLevel == O.quota).all()
+    assert (E.mvInvLevelSigma2 == O.inv_sigma2).all()
+    for l in range(8):
+        assert np.array_equal(E.mvImagePyramid(l), O.level(l)), f"pyramid level {l}"
+        assert np.array_equal(E.debug_blurred(l), O.blurred(l)), f"blurred level {l}"
+        for which, name in ((0, "FAST candidates"), (1, "quadtree output")):
+            a = E.debug_level_keypoints(l, which); b = O.debug_kps(which, l)
+            assert len(a) == len(b), f"{name} level {l}: {len(a)} vs {len(b)}"
+            for f in ("x", "y", "response"):
+                bad = np.nonzero(a[f] != b[f])[0]
+                assert len(bad) == 0, f"{name} level {l} field {f}: first mismatch at {bad[:5]}"
+    assert n == no
+    _assert_same_kps(k, d, ko, do, f"{w}x{h}")
+
+
+def test_golden_fixtures(api, golden):
+    E = api.ORB(2000, 1.2, 8, 28, 15)
+    for i, s in enumerate((1000, 1001)):
+        n, k, d = E.Extract(synth.scene(s))
+        _assert_same_kps(k, d, golden[f"g1_kps{i}"], golden[f"g1_desc{i}"], f"g1[{i}]")
+        assert np.array_equal(E.mvImagePyramid(7), golden[f"g1_level7_{i}"])
+    E1 = api.ORB(2000, 1.2, 1, 28, 15)   # shipped config/extractor.yaml: nlevels 1
+    n, k, d = E1.Extract(synth.scene(42, 512, 512))
+    _assert_same_kps(k, d, golden["g2_kps"], golden["g2_desc"], "g2")
+    E3 = api.ORB(300, 1.2, 4, 28, 15)    # low-texture: minTh fallback + quota shortfall
+    n, k, d = E3.Extract(golden["g3_img"])
+    _assert_same_kps(k, d, golden["g3_kps"], golden["g3_desc"], "g3")
+
+
+def test_batch_equals_single(api, oracle):
+    imgs = np.stack([synth.scene(s) for s in (1, 2, 3, 4, 5)])
+    E = api.ORB(2000, 1.2, 8, 28, 15)
+    O = oracle.Orb(2000, 1.2, 8, 28, 15)
+    res = E.ExtractBatch(imgs)
+    for i, (k, d) in enumerate(res):
+        no, ko, do = O.extract(imgs[i])
+        _assert_same_kps(k, d, ko, do, f"batch[{i}]")
+
+
+def test_seeds_and_strided_input(api, oracle):
+    big = np.zeros((480, 700), np.uint8)
+    big[:, :640] = synth.scene(11)
+    img = big[:, :640]  # row stride 700
+    seeds = np.zeros(5, api.KP_DTYPE)
+    seeds["x"] = [100.4, 222.5, 50.25, 300.75, 90.5]; seeds["y"] = [80.6, 140.5, 60.1, 100.9, 70.5]
+    seeds["angle"] = [10.5, 200.25, 359.9, 0.0, 45.0]; seeds["octave"] = [0, 0, 2, 1, 0]
+    seeds["size"] = 31; seeds["response"] = 99; seeds["class_id"] = 7
+    E = api.ORB(1000, 1.2, 8, 20, 7)
+    O = oracle.Orb(1000, 1.2, 8, 20, 7)
+    n, k, d = E.Extract(img, seeds)
+    no, ko, do = O.extract(np.ascontiguousarray(img), seeds)
+    _assert_same_kps(k, d, ko, do, "seeds")
+
+
+def test_error_behaviour(api):
+    E = api.ORB(2000, 1.2, 8, 28, 15)
+    n, k, d = E.Extract(np.zeros((0, 0), np.uint8))
+    assert n == -1                                   # ORBextractor.cc:834
+    with pytest.raises(api.McvError) as e:
+        E.Extract(synth.scene(1, 160, 120))          # level 7 narrower than one cell: the reference divides by zero
+    assert e.value.status == -3
+    seeds = np.zeros(1, api.KP_DTYPE); seeds["x"] = 5; seeds["y"] = 5
+    with pytest.raises(api.McvError) as e:
+        E.Extract(synth.scene(1), seeds)
+    assert e.value.status == -7
+
+
+def test_distribute_octree_static(api, oracle):
+    rng = np.random.default_rng(5)
+    for n, N, (bw, bh) in ((3000, 500, (608, 448)), (50, 200, (300, 120)), (4000, 1000, (1248, 688)), (1, 10, (100, 100))):
+        pts = np.unique(np.stack([rng.integers(0, bw, n), rng.integers(0, bh, n)], 1), axis=0)
+        rng.shuffle(pts)
+        k = np.zeros(len(pts), api.KP_DTYPE)
+        k["x"], k["y"] = pts[:, 0], pts[:, 1]
+        k["response"] = rng.integers(15, 60, len(pts))   # many response ties
+        E = api.ORB(2000, 1.2, 8, 28, 15)
+        a = E.DistributeOctTree(k, 16, 16 + bw, 16, 16 + bh, N)
+        b = oracle.distribute_octree(k, 16, 16 + bw, 16, 16 + bh, N)
+        assert len(a) == len(b)
+        assert (a["x"] == b["x"]).all() and (a["y"] == b["y"]).all() and (a["response"] == b["response"]).all()

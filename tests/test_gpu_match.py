@@ -1,0 +1,141 @@
+"""GPU parity: Hamming 2-NN kernels, filters, stereo and projection matching through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from mcvslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq_dm(a, b, fields=("queryIdx", "trainIdx", "imgIdx", "distance")):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    for f in fields:
+        bad = np.nonzero(a[f] != b[f])
+        assert len(bad[0]) == 0, f"{f} differs at {[x[:5] for x in bad]}"
+
+
+@pytest.mark.parametrize("nq,nt,low", [(2000, 2000, False), (300, 500, True), (1, 2001, False), (129, 1, False), (5, 0, False),
+                                       (1000, 70000, True)])
+def test_knn2_bf(api, oracle, nq, nt, low):
+    q = synth.descriptors(nq, 1, low); t = synth.descriptors(nt, 2, low)
+    if low:
+        q[:, 3:] = 0; t[:, 3:] = 0          # heavy ties
+    res = api.Matcher.KnnMatch(q, t)
+    ref, k = oracle.knn2_bf(q, t)
+    _eq_dm(res.knn, ref[:, :k])
+    fp = api.Matcher.KnnMatchRows(q, t)
+    _eq_dm(fp.knn, oracle.knn2_firstparty(q, t))
+    if nt > 0:
+        bm = api.Matcher.BFMatch(q, t)
+        _eq_dm(bm.m, ref[:, 0])
+
+
+def test_knn2_golden(api, golden):
+    res = api.Matcher.KnnMatch(golden["g4_q"], golden["g4_t"])
+    assert np.array_equal(res.knn["trainIdx"], golden["g4_idx"]) and np.array_equal(res.knn["distance"], golden["g4_dist"])
+    res = api.Matcher.KnnMatch(golden["g1_desc0"], golden["g1_desc1"])
+    assert np.array_equal(res.knn["trainIdx"], golden["g1_bf_idx"]) and np.array_equal(res.knn["distance"], golden["g1_bf_dist"])
+
+
+def test_knn2_candidates_and_filters(api, oracle):
+    rng = np.random.default_rng(3)
+    q = synth.descriptors(700, 5, True); t = synth.descriptors(900, 6, True)
+    q[:, 2:] = 0; t[:, 2:] = 0
+    lens = rng.integers(0, 70, 700); lens[:5] = [0, 1, 2, 33, 64]
+    off = np.zeros(701, np.int32); off[1:] = np.cumsum(lens)
+    cidx = rng.integers(0, 900, off[-1]).astype(np.int32)
+    res = api.Matcher.KnnMatchCandidates(q, t, off, cidx)
+    ref = oracle.knn2_candidates(q, t, off, cidx)
+    _eq_dm(res.knn, ref)
+    for ratio in (0.6, 0.7, 1.0):
+        a = res.FilterRatio(ratio); b = oracle.filter_ratio(ref, ratio)
+        _eq_dm(a.m, b)
+        _eq_dm(a.FilterThreshold(3).m, oracle.filter_threshold(b, 3))
+    # orientation histogram on random angles
+    k1 = np.zeros(700, api.KP_DTYPE); k2 = np.zeros(900, api.KP_DTYPE)
+    k1["angle"] = rng.uniform(0, 360, 700).astype(np.float32); k2["angle"] = rng.uniform(0, 360, 900).astype(np.float32)
+    m = oracle.filter_ratio(oracle.knn2_bf(q, t)[0], 1.0)
+    _eq_dm(api.MatchRes(m).FilterOrientation(k1, k2).m, oracle.filter_orientation(m, k1, k2))
+
+
+def test_dbow_match(api, oracle):
+    rng = np.random.default_rng(8)
+    d1 = synth.descriptors(400, 1, True); d2 = synth.descriptors(500, 2, True)
+    n1 = rng.integers(0, 40, 400); n2 = rng.integers(0, 40, 500)
+    fv1 = {}; fv2 = {}
+    for i, n in enumerate(n1): fv1.setdefault(int(n) * 3, []).append(i)
+    for i, n in enumerate(n2): fv2.setdefault(int(n) * 3 if n % 5 else int(n) * 3 + 1, []).append(i)
+    res = api.Matcher.DBowMatch(d1, fv1, d2, fv2).knn
+    # restatement of src/Matcher.cpp:146-193 with the oracle's candidate 2-NN
+    exp = []
+    for nid in sorted(set(fv1) & set(fv2)):
+        c = np.array(fv2[nid], np.int32)
+        for f1 in fv1[nid]:
+            r = oracle.knn2_candidates(d1[f1:f1 + 1], d2, np.array([0, len(c)], np.int32), c)[0]
+            if r[1]["distance"] != 999:
+                exp.append([(f1, c[r[0]["trainIdx"]], -1, r[0]["distance"]), (f1, c[r[1]["trainIdx"]], -1, r[1]["distance"])])
+    exp = np.array(exp, api.DM_DTYPE).reshape(-1, 2)
+    _eq_dm(res, exp)
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_stereo(api, oracle, seed):
+    trip = synth.triplet(seed)
+    EL, ER = api.ORB(2000, 1.2, 8, 28, 15), api.ORB(2000, 1.2, 8, 28, 15)
+    OL, OR = oracle.Orb(2000, 1.2, 8, 28, 15), oracle.Orb(2000, 1.2, 8, 28, 15)
+    nl, kl, dl = EL.Extract(trip[0]); nr, kr, dr = ER.Extract(trip[1])
+    OL.extract(trip[0]); OR.extract(trip[1])
+    bf, b = 955.40503, 1.0
+    ur, dp, bd, br = api.ComputeStereoMatch(EL, ER, kl, dl, kr, dr, bf, b)
+    n, uro, dpo, bdo, bro = oracle.stereo_match(OL, OR, kl, dl, kr, dr, 480, bf, b)
+    assert n > 200, "synthetic stereo pair should match"
+    assert np.array_equal(bd, bdo) and np.array_equal(br, bro)
+    assert np.array_equal(ur.view(np.uint32), uro.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dpo.view(np.uint32))
+
+
+def test_rig_batch(api, oracle):
+    frames = np.stack([synth.triplet(s) for s in (31, 32, 33)])
+    R = api.Rig()
+    out = R.process(frames)
+    O = [oracle.Orb(2000, 1.2, 8, 28, 15) for _ in range(3)]
+    for f in range(3):
+        ks, ds = [], []
+        for c in range(3):
+            n, k, d = O[c].extract(frames[f, c])
+            assert out["counts"][f, c] == n
+            assert out["kps"][f, c, :n].tobytes() == k.tobytes() and out["desc"][f, c, :n].tobytes() == d.tobytes()
+            ks.append(k); ds.append(d)
+        n, ur, dp, bd, br = oracle.stereo_match(O[0], O[1], ks[0], ds[0], ks[1], ds[1], 480, 955.40503, 1.0)
+        nl = len(ks[0])
+        assert np.array_equal(out["u_right"][f, :nl].view(np.uint32), ur.view(np.uint32))
+        assert np.array_equal(out["depth_left"][f, :nl].view(np.uint32), dp.view(np.uint32))
+    assert R.last_launches() > 0
+
+
+def test_projection(api, oracle):
+    img = synth.scene(55)
+    E = api.ORB(2000, 1.2, 8, 28, 15)
+    n, k, d = E.Extract(img)
+    rng = np.random.default_rng(9)
+    n_mp = 10000
+    fx = fy = 955.40503 * 640 / 512; cx, cy = 320.0, 240.0
+    th = 0.01
+    R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], np.float32)
+    t = np.array([0.02, -0.01, 0.03], np.float32)
+    src = rng.integers(0, n, n_mp)
+    z = rng.uniform(2, 50, n_mp).astype(np.float32)
+    u = k["x"][src] + rng.normal(0, 2.0, n_mp).astype(np.float32); v = k["y"][src] + rng.normal(0, 2.0, n_mp).astype(np.float32)
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1).astype(np.float32)
+    pw = ((pc - t) @ R).astype(np.float32)      # Pc = R Pw + t  ->  Pw = R^T (Pc - t)
+    pw[:50, 2] = -5 - pw[:50, 2]                 # some behind the camera
+    md = d[src].copy()
+    flips = rng.integers(0, 41, n_mp)
+    for m in range(n_mp):
+        bits = rng.choice(256, flips[m], replace=False)
+        np.bitwise_xor.at(md[m], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    lvl = k["octave"][src].astype(np.int32)
+    for r_th in (5.0, 7.0, 10.0):
+        cnt, oi, od = api.ProjectBunchMapPoints(k, d, 640, 480, E.mvScaleFactor, R, t, [fx, fy, cx, cy], pw, md, lvl, r_th)
+        cnto, oio, odo = oracle.project_match(k, d, 640, 480, E.mvScaleFactor, R, t, [fx, fy, cx, cy], pw, md, lvl, r_th)
+        assert cnt == cnto and cnt > 1000
+        assert np.array_equal(oi, oio) and np.array_equal(od, odo)
