@@ -29,7 +29,8 @@ EXPORTS = [
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
-    "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_stereo_match",
+    "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
+    "mcv_rig_stage_ms", "mcv_stereo_match",
     "mcv_project_match", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak",
 ]
@@ -92,6 +93,8 @@ def lib():
         L.mcv_rig_process_async.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, i]
         L.mcv_rig_sync.argtypes = [vp]
         L.mcv_rig_last_launches.argtypes = [vp]
+        L.mcv_rig_set_profiling.argtypes = [vp, i]
+        L.mcv_rig_stage_ms.argtypes = [vp, vp, i, C.POINTER(i)]
         L.mcv_stereo_match.argtypes = [vp, vp, vp, vp, i, vp, vp, i, f, f, vp, vp, vp, vp]
         L.mcv_project_match.argtypes = [vp, vp, i, i, i, vp, i, vp, vp, vp, vp, vp, vp, i, f, vp, vp, C.POINTER(i)]
         L.mcv_debug_sincosf.argtypes = [vp, i, vp, vp]
@@ -398,6 +401,18 @@ class Rig:
 
     def last_launches(self):
         return lib().mcv_rig_last_launches(self._r)
+
+    STAGES = ("pyramid", "blur", "fast_cells", "quadtree", "orient_desc", "stereo_match", "stereo_median")
+
+    def set_profiling(self, on):
+        _check(lib().mcv_rig_set_profiling(self._r, int(on)))
+
+    def stage_ms(self):
+        """Returns ({stage: total ms}, n_calls) since profiling was switched on."""
+        ms = np.zeros(len(self.STAGES), np.float32)
+        n = C.c_int(0)
+        _check(lib().mcv_rig_stage_ms(self._r, _p(ms), len(ms), C.byref(n)))
+        return dict(zip(self.STAGES, ms.tolist())), n.value
 
 
 def debug_sincosf(a):

@@ -73,7 +73,17 @@ struct mcv_orb {
     HostBuf h_stage;
     int last_cap = 0;       // per-image keypoint slots of the last extract (layout of kps/desc)
     int last_launches = 0;
+    // optional per-stage timing: CUDA events recorded between the stages of every call (no synchronisation added)
+    bool profile = false;
+    std::vector<cudaEvent_t> ev;   // PROF_RING calls x (N_STAGES + 1) events
+    int prof_calls = 0;
 };
+
+constexpr int N_STAGES = 7;   // pyramid, blur, fast_cells, quadtree, orient_desc, stereo_match, stereo_median
+constexpr int PROF_RING = 512;
+static inline void prof_mark(mcv_orb* h, int stage_boundary) {
+    if (h->profile && h->prof_calls < PROF_RING) cudaEventRecord(h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + stage_boundary], h->stream);
+}
 
 // ORBextractor::init — ORBextractor.cc:407-436 (same float arithmetic, evaluated on the host once)
 static void orb_init_scales(mcv_orb* h) {
@@ -215,15 +225,21 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
                                   const SeedInfo* seeds, mcv_keypoint* d_kps, uint8_t* d_desc, int* d_counts, int cap) {
     const Plan& P = h->plan;
     int n = 0;
+    prof_mark(h, 0);
     n += launch_pyramid(P, d_imgs, src_pitch, src_image_stride, h->pyr.as<uint8_t>(), h->tabs.as<int>(), n_images, h->stream);
+    prof_mark(h, 1);
     n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
+    prof_mark(h, 2);
     n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
+    prof_mark(h, 3);
     const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
                                 h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
     if (r < 0) { set_error("nfeatures too large for the quadtree kernel's shared-memory heap"); return MCV_ERR_CAPACITY; }
     n += r;
+    prof_mark(h, 4);
     n += launch_orient_desc(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), seeds, d_kps,
                             d_desc, d_counts, cap, n_images, h->stream);
+    prof_mark(h, 5);
     MCV_CUDA(cudaGetLastError());
     h->last_images = n_images; h->last_cap = cap; h->last_launches = n;
     return MCV_OK;
@@ -266,6 +282,7 @@ void mcv_orb_destroy(mcv_orb* h) {
                       &h->kps, &h->desc, &h->counts, &h->seeds, &h->misc})
         b->release();
     h->h_stage.release();
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -732,10 +749,42 @@ mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames
     st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap);
     if (st) return st;
     int n = h->last_launches;
+    cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 6] : nullptr;
     n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
-                       d_depth, r->best_dist.as<int>(), nullptr, h->stream);
+                       d_depth, r->best_dist.as<int>(), nullptr, h->stream, mid);
+    prof_mark(h, 7);
+    if (h->profile && h->prof_calls < PROF_RING) ++h->prof_calls;
     MCV_CUDA(cudaGetLastError());
     r->last_launches = n;
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_set_profiling(mcv_rig* r, int on) {
+    if (!r) return MCV_ERR_BAD_ARG;
+    mcv_orb* h = r->orb;
+    MCV_CUDA(cudaSetDevice(h->device));
+    if (on && h->ev.empty()) {
+        h->ev.resize((size_t)PROF_RING * (N_STAGES + 1));
+        for (auto& e : h->ev) MCV_CUDA(cudaEventCreate(&e));
+    }
+    h->profile = on != 0;
+    h->prof_calls = 0;
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_stage_ms(mcv_rig* r, float* total_ms, int n_stages, int* n_calls) {
+    if (!r || !total_ms || n_stages < N_STAGES) return MCV_ERR_BAD_ARG;
+    mcv_orb* h = r->orb;
+    MCV_CUDA(cudaSetDevice(h->device));
+    MCV_CUDA(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < n_stages; ++s) total_ms[s] = 0.f;
+    for (int c = 0; c < h->prof_calls; ++c)
+        for (int s = 0; s < N_STAGES; ++s) {
+            float ms = 0.f;
+            MCV_CUDA(cudaEventElapsedTime(&ms, h->ev[(size_t)c * (N_STAGES + 1) + s], h->ev[(size_t)c * (N_STAGES + 1) + s + 1]));
+            total_ms[s] += ms;
+        }
+    if (n_calls) *n_calls = h->prof_calls;
     return MCV_OK;
 }
 

@@ -79,7 +79,7 @@ int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blu
                        cudaStream_t s);
 int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps, const uint8_t* d_desc, const int* d_counts, int cap,
                   int n_frames, int left_cam, int right_cam, int cams_per_frame, float bf, float baseline, float* d_u_right,
-                  float* d_depth, int* d_best_dist, int* d_best_r, cudaStream_t s);
+                  float* d_depth, int* d_best_dist, int* d_best_r, cudaStream_t s, cudaEvent_t mid = nullptr);
 // stereo across two separate pyramids (mcv_stereo_match on two handles): one "frame", explicit pointers
 int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_pyr_r, const mcv_keypoint* d_kl, const uint8_t* d_dl, int nl,
                        const mcv_keypoint* d_kr, const uint8_t* d_dr, int nr, float bf, float baseline, float* d_u_right, float* d_depth,

@@ -179,16 +179,17 @@ __global__ void __launch_bounds__(256) k_stereo_median(const __grid_constant__ S
     }
 }
 
-static int run_stereo(const StereoArgs& A, const Plan& P, int n_frames, int max_left, cudaStream_t s) {
+static int run_stereo(const StereoArgs& A, const Plan& P, int n_frames, int max_left, cudaStream_t s, cudaEvent_t mid = nullptr) {
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, n_frames);
     k_stereo_match<<<grid, 32 * ST_WARPS, 0, s>>>(A, P);
+    if (mid) cudaEventRecord(mid, s);
     k_stereo_median<<<n_frames, 256, 0, s>>>(A);
     return 2;
 }
 
 int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps, const uint8_t* d_desc, const int* d_counts, int cap,
                   int n_frames, int left_cam, int right_cam, int cams_per_frame, float bf, float baseline, float* d_u_right, float* d_depth,
-                  int* d_best_dist, int* d_best_r, cudaStream_t s) {
+                  int* d_best_dist, int* d_best_r, cudaStream_t s, cudaEvent_t mid) {
     StereoArgs A{};
     A.pyr_l = d_pyr + (size_t)left_cam * P.pyr_bytes; A.pyr_r = d_pyr + (size_t)right_cam * P.pyr_bytes;
     A.frame_pyr_stride = (size_t)cams_per_frame * P.pyr_bytes;
@@ -198,7 +199,7 @@ int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps
     A.frame_kp_stride = (size_t)cams_per_frame * cap;
     A.bf = bf; A.baseline = baseline;
     A.u_right = d_u_right; A.depth = d_depth; A.best_dist = d_best_dist; A.best_r = d_best_r; A.out_stride = cap;
-    return run_stereo(A, P, n_frames, cap, s);
+    return run_stereo(A, P, n_frames, cap, s, mid);
 }
 
 int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_pyr_r, const mcv_keypoint* d_kl, const uint8_t* d_dl, int nl,
