@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Headline benchmark: three-camera frames/s — per frame 3x ORB extraction (2000 features, 8 levels x 1.2, FAST 28/15) on
+640x480 images plus left/right stereo matching (BASELINE.json configs[1]) — on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of B synthetic triplets per GPU (weak scaling: every rank owns its own
+batch; frames are independent, so there is no data-path collective — only a per-step gather of the per-image keypoint
+counts, the job's result directory, over NCCL). One JSON line on rank 0:
+  value      device-resident throughput: inputs already in HBM, CUDA-event timed on the engine's stream, max over ranks
+  e2e        same metric through the C ABI with HOST buffers (pinned): H2D of the images and D2H of all results inside
+             the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (port of the reference's algorithm) on the host cores, bounded sample, rank 0 at N=1 only
+--impl reference times the CPU oracle on this box's host cores with all threads (the reference itself cannot be built
+here: no OpenCV C++/Eigen/Boost/ROS/pyp); it is the only place besides cpu_baseline where bench.py executes oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+ORB = dict(nkeypoints=2000, scale_factor=1.2, nlevels=8, ini_th_fast=28, min_th_fast=15)
+BF, BASELINE = 955.40503, 1.0
+METRIC = "three_camera_frames_per_s"
+UNIT = "frames/s"
+# compulsory traffic per three-camera frame = 3 x (input 307200 + pyramid levels 1..7 643332 + 2000 x 60 B
+# of keypoints/descriptors) + 16000 B of stereo outputs
+ALGO_BYTES_PER_FRAME = 3 * (307200 + 643332 + 2000 * 60) + 16000
+PYR_BYTES_PER_IMAGE = 950532          # all 8 levels
+# algorithmic bytes per IMAGE of each stage (DESIGN.md "Kernels"): what the stage must read + write at least once
+STAGE_BYTES_PER_IMAGE = {
+    "pyramid": 307200 + 950532,                 # read input, write 8 levels
+    "blur": 2 * 950532,                         # read pyramid, write smoothed pyramid
+    "fast_cells": 950532 + 4 * 6500,            # read pyramid, write ~6.5k packed candidates
+    "quadtree": 2 * 4 * 6500 + 4 * 2000,        # read candidates, write them ordered, write 2000 selected
+    "orient_desc": 2000 * (31 * 31 + 37 * 37 + 60),  # per keypoint: intensity patch + smoothed patch + 60 B out
+    "stereo_match": (2 * 2000 * 60 + 2000 * 16) / 3.0,   # per frame / 3 images
+    "stereo_median": 2000 * 12 / 3.0,
+}
+
+
+def make_frames(n_frames, seed0):
+    from mcvslam_b200 import synth
+    base = [synth.triplet(seed0 + s, W, H) for s in range(min(n_frames, 16))]
+    return np.stack([base[i % len(base)] for i in range(n_frames)])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows = []
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(n_threads, budget_s=15.0):
+    """The CPU oracle (a port of the reference's algorithm, oracle/) on the host cores over a bounded sample."""
+    from oracle import oracle as O
+    O.build()
+    frames = make_frames(8, 100)
+    s1, _ = O.bench_frames(frames[:2], ORB["nkeypoints"], ORB["scale_factor"], ORB["nlevels"], ORB["ini_th_fast"], ORB["min_th_fast"],
+                           BF, BASELINE, n_threads, repeat=max(1, n_threads // 2))
+    done = 2 * max(1, n_threads // 2)
+    rate = done / s1
+    repeat = max(1, int(rate * budget_s / len(frames)))
+    s, _ = O.bench_frames(frames, ORB["nkeypoints"], ORB["scale_factor"], ORB["nlevels"], ORB["ini_th_fast"], ORB["min_th_fast"],
+                          BF, BASELINE, n_threads, repeat=repeat)
+    n = len(frames) * repeat
+    return {"value": n / s, "unit": UNIT, "cores": n_threads, "kind": "port",
+            "sample": "%d three-camera frames (8 distinct synthetic 640x480 triplets x %d), %d threads, %.1f s" % (n, repeat, n_threads, s)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    t_all = time.time()
+    for _ in range(args.warmup):
+        cpu_baseline(cores, budget_s=1.0)
+    per_step = max(1.0, min(20.0, 150.0 / max(1, args.steps)))
+    last = None
+    for _ in range(args.steps):
+        last = cpu_baseline(cores, budget_s=per_step)
+        vals.append(last["value"])
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * args.frames / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": {"workload": "configs[1]: 3-camera rig triplet 640x480, 2000 ORB x 8 levels x 1.2, extract + L/R stereo",
+                                            "frames_per_step": args.frames, "note": "CPU oracle (port of the reference algorithm); step = bounded sample"},
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=128, help="three-camera frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=None, help="frames per pipelined chunk inside the engine (default: engine default 32)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mcvslam_b200.api as A
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.frames
+    stream = torch.cuda.Stream(device=dev)
+    rig = A.Rig(bf=BF, baseline=BASELINE, device=local_rank, stream=stream.cuda_stream, **ORB)
+    cap = rig.cap
+    if args.chunk is not None:
+        rig.set_chunk_frames(args.chunk)
+    frames_np = make_frames(B, 1000 * (rank + 1))
+    # pinned host buffers (e2e leg) and device-resident copies (kernel leg)
+    h_imgs = torch.from_numpy(frames_np).pin_memory()
+    d_imgs = h_imgs.to(dev)
+    kp_bytes = B * 3 * cap * 28
+    d_kps = torch.empty(kp_bytes, dtype=torch.uint8, device=dev); d_desc = torch.empty(B * 3 * cap * 32, dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(B * 3, dtype=torch.int32, device=dev)
+    d_ur = torch.empty(B * cap, dtype=torch.float32, device=dev); d_dp = torch.empty(B * cap, dtype=torch.float32, device=dev)
+    h_kps = torch.empty(kp_bytes, dtype=torch.uint8).pin_memory(); h_desc = torch.empty(B * 3 * cap * 32, dtype=torch.uint8).pin_memory()
+    h_cnt = torch.zeros(B * 3, dtype=torch.int32).pin_memory()
+    h_ur = torch.empty(B * cap, dtype=torch.float32).pin_memory(); h_dp = torch.empty(B * cap, dtype=torch.float32).pin_memory()
+    gathered = torch.zeros(world * B * 3, dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step_device():
+        rig.process_async(d_imgs.data_ptr(), B, W, H, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), d_ur.data_ptr(), d_dp.data_ptr())
+        if world > 1:  # the only collective: gather of the per-image keypoint counts (result directory)
+            dist.all_gather_into_tensor(gathered, d_cnt)
+
+    def step_host():
+        rig.process_ptrs(h_imgs.data_ptr(), B, W, H, h_kps.data_ptr(), h_desc.data_ptr(), h_cnt.data_ptr(), h_ur.data_ptr(), h_dp.data_ptr(), False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = rig.last_launches() * args.steps
+        # per-kernel durations: same steps again with the engine's stage events on (whole batch on one stream, no chunk overlap)
+        rig.set_profiling(True)
+        for _ in range(max(3, min(10, args.steps))):
+            step_device()
+        barrier()
+        stage_ms, n_calls = rig.stage_ms()
+        rig.set_profiling(False)
+        # e2e leg: host buffers through the C ABI, copies inside the timed region
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, args.steps // 2)
+        for _ in range(e2e_steps):
+            step_host()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    n_kp = int(d_cnt.sum().item())
+
+    if rank == 0:
+        value = world * B * args.steps / (ms * 1e-3)
+        e2e_v = world * B * e2e_steps / e2e_s
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        dom = max(stage_ms, key=stage_ms.get)
+        dom_ms = stage_ms[dom] / max(1, n_calls)
+        launches_per_call = 8 if dom == "pyramid" else 1
+        dom_bytes = STAGE_BYTES_PER_IMAGE[dom] * 3 * B
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: 3-camera rig triplet (left/right/wide) 640x480, 2000 ORB x 8 levels x 1.2, FAST 28/15, "
+                                   "extract + L/R stereo match", "frames_per_step_per_gpu": B, "keypoints_per_frame": n_kp / B,
+                       "l2": "inputs larger than L2: %d MB of images + %d MB of pyramids per step" % (B * 3 * W * H >> 20, B * 3 * PYR_BYTES_PER_IMAGE >> 20),
+                       "collective": "all_gather of per-image keypoint counts per step (N>1 only)"},
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h_imgs.numel()),
+                    "d2h_bytes_per_step": int(h_kps.numel() + h_desc.numel() + h_cnt.numel() * 4 + h_ur.numel() * 4 + h_dp.numel() * 4),
+                    "steps": e2e_steps, "how": "mcv_rig_process with pinned host buffers, wall clock around synchronous calls"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "launches_per_step": launches_per_call,
+                         "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms,
+                         "whole_path_frac": (ALGO_BYTES_PER_FRAME * value / world) / 1e9 / peak},
+            "stage_ms_per_step": {k: v / max(1, n_calls) for k, v in stage_ms.items()},
+            "stage_ms_note": "per-kernel CUDA-event durations from %d extra steps run unchunked on one stream right after the timed region" % n_calls,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

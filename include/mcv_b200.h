@@ -169,7 +169,12 @@ typedef struct mcv_rig_params {
 mcv_status mcv_rig_create(const mcv_rig_params* params, int device, void* stream, mcv_rig** out);
 void mcv_rig_destroy(mcv_rig* r);
 int mcv_rig_max_keypoints(const mcv_rig* r);
-mcv_orb* mcv_rig_extractor(mcv_rig* r);   /* the batched extractor (image index = 3*frame + cam; cam 0=L,1=R,2=W) */
+/* The extractor of slot 0 (image index = 3*frame + cam within the chunk it processed last; cam 0=L,1=R,2=W). The whole batch
+ * is in it when it ran as one chunk: n_frames <= chunk_frames/... see mcv_rig_set_chunk_frames(r, 0). */
+mcv_orb* mcv_rig_extractor(mcv_rig* r);
+/* Batches are cut into chunks of `chunk_frames` triplets pipelined over 3 internal streams (H2D / kernels / D2H overlap
+ * inside one synchronous call). Default 32 (env MCV_RIG_CHUNK); 0 = never chunk. */
+mcv_status mcv_rig_set_chunk_frames(mcv_rig* r, int chunk_frames);
 
 /* Frame::Frame ORBE + SMatch stages for a batch of n_frames triplets. imgs: [n_frames][3][hgt][w] u8 (L, R, W), host
  * or device. Outputs (host or device): kps [n_frames*3][cap], desc [n_frames*3][cap][32], counts [n_frames*3],

@@ -29,7 +29,7 @@ EXPORTS = [
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
-    "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
+    "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
     "mcv_project_match", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak",
@@ -93,6 +93,7 @@ def lib():
         L.mcv_rig_process_async.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, i]
         L.mcv_rig_sync.argtypes = [vp]
         L.mcv_rig_last_launches.argtypes = [vp]
+        L.mcv_rig_set_chunk_frames.argtypes = [vp, i]
         L.mcv_rig_set_profiling.argtypes = [vp, i]
         L.mcv_rig_stage_ms.argtypes = [vp, vp, i, C.POINTER(i)]
         L.mcv_stereo_match.argtypes = [vp, vp, vp, vp, i, vp, vp, i, f, f, vp, vp, vp, vp]
@@ -398,6 +399,9 @@ class Rig:
 
     def sync(self):
         _check(lib().mcv_rig_sync(self._r))
+
+    def set_chunk_frames(self, n):
+        _check(lib().mcv_rig_set_chunk_frames(self._r, int(n)))
 
     def last_launches(self):
         return lib().mcv_rig_last_launches(self._r)

@@ -4,6 +4,7 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -69,7 +70,7 @@ struct mcv_orb {
     bool have_plan = false;
     int cap_images = 0;     // workspace capacity (images)
     int last_images = 0;    // images processed by the last extract
-    DevBuf tabs, src, pyr, blur, cell_pts, cell_cnt, arena_a, arena_b, out_pts, out_cnt, kps, desc, counts, seeds, misc;
+    DevBuf tabs, src, pyr, blur, score, cell_pts, cell_cnt, arena_a, arena_b, out_pts, out_cnt, kps, desc, counts, seeds, misc;
     HostBuf h_stage;
     int last_cap = 0;       // per-image keypoint slots of the last extract (layout of kps/desc)
     int last_launches = 0;
@@ -205,6 +206,7 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
         mcv_status st;
         if ((st = h->pyr.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->blur.reserve((size_t)P.pyr_bytes * n_images))) return st;
+        if ((st = h->score.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->cell_pts.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->arena_a.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->arena_b.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
@@ -230,7 +232,7 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     prof_mark(h, 1);
     n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
     prof_mark(h, 2);
-    n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
+    n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
     prof_mark(h, 3);
     const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
                                 h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
@@ -278,7 +280,7 @@ void mcv_orb_destroy(mcv_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->out_pts, &h->out_cnt,
+    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->score, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->out_pts, &h->out_cnt,
                       &h->kps, &h->desc, &h->counts, &h->seeds, &h->misc})
         b->release();
     h->h_stage.release();
@@ -699,13 +701,57 @@ mcv_status mcv_debug_popc_peak(int iters, double* popc_per_s, double* ms_out) {
 
 // =========================================================================================================
 // three-camera rig
+//
+// A batch is cut into chunks of `chunk_frames` triplets that run round-robin on RIG_SLOTS slots. Every slot owns a stream
+// and a full extractor workspace, so within ONE synchronous call the host->device copy of chunk i+1, the kernels of chunk i
+// and the device->host copy of chunk i-1 overlap, and the latency-bound quadtree kernel of one chunk shares the SMs with
+// the throughput-bound stencils of another (CUDA streams replace the reference's ThreadPool(3), src/Frame.cpp:22).
 // =========================================================================================================
+constexpr int RIG_SLOTS = 3;
+
+struct RigSlot {
+    mcv_orb* orb = nullptr;
+    DevBuf imgs, kps, desc, counts, u_right, depth, best_dist;
+    cudaEvent_t done = nullptr;
+};
+
 struct mcv_rig {
     mcv_rig_params prm{};
-    mcv_orb* orb = nullptr;
-    DevBuf imgs, u_right, depth, best_dist;
+    int device = 0;
+    cudaStream_t stream = nullptr;   // the caller-visible stream: async work is ordered after / joined back into it
+    bool own_stream = false;
+    RigSlot slot[RIG_SLOTS];
+    cudaEvent_t fork = nullptr;
+    int chunk_frames = 32;
     int last_launches = 0;
 };
+
+// ORBE + SMatch of n_frames device-resident triplets on one slot (its stream); all pointers are device pointers.
+static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
+                            uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth, int cap, int* launches) {
+    mcv_orb* h = sl.orb;
+    mcv_status st = ensure_workspace(h, w, hgt, 3 * n_frames, 1);
+    if (st) return st;
+    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints()"); return MCV_ERR_CAPACITY; }
+    if ((st = sl.best_dist.reserve((size_t)n_frames * cap * 4))) return st;
+    st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap);
+    if (st) return st;
+    int n = h->last_launches;
+    cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 6] : nullptr;
+    n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
+                       d_depth, sl.best_dist.as<int>(), nullptr, h->stream, mid);
+    prof_mark(h, 7);
+    if (h->profile && h->prof_calls < PROF_RING) ++h->prof_calls;
+    MCV_CUDA(cudaGetLastError());
+    *launches += n;
+    return MCV_OK;
+}
+
+static inline int rig_chunk_size(const mcv_rig* r, int n_frames) {
+    // profiling measures whole-batch kernels on one stream; otherwise chunk so that all slots get work
+    if (r->slot[0].orb->profile || r->chunk_frames <= 0) return n_frames;
+    return std::max(1, std::min(r->chunk_frames, (n_frames + RIG_SLOTS - 1) / RIG_SLOTS));
+}
 
 extern "C" {
 
@@ -713,55 +759,75 @@ mcv_status mcv_rig_create(const mcv_rig_params* p, int device, void* stream, mcv
     if (!p || !out) return MCV_ERR_BAD_ARG;
     *out = nullptr;
     if (!(p->baseline > 0.f) || !(p->bf > 0.f)) { set_error("bad rig parameters"); return MCV_ERR_BAD_ARG; }
-    mcv_orb* o = nullptr;
-    mcv_status st = mcv_orb_create(&p->orb, device, stream, &o);
-    if (st) return st;
     mcv_rig* r = new mcv_rig();
-    r->prm = *p; r->orb = o;
+    r->prm = *p; r->device = device;
+    for (int i = 0; i < RIG_SLOTS; ++i) {
+        mcv_status st = mcv_orb_create(&p->orb, device, nullptr, &r->slot[i].orb);
+        if (st) { for (int k = 0; k < i; ++k) mcv_orb_destroy(r->slot[k].orb); delete r; return st; }
+        cudaEventCreateWithFlags(&r->slot[i].done, cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&r->fork, cudaEventDisableTiming);
+    if (stream) r->stream = (cudaStream_t)stream;
+    else { cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking); r->own_stream = true; }
+    if (const char* e = getenv("MCV_RIG_CHUNK")) r->chunk_frames = atoi(e);
     *out = r;
     return MCV_OK;
 }
 
 void mcv_rig_destroy(mcv_rig* r) {
     if (!r) return;
-    cudaSetDevice(r->orb->device);
-    cudaStreamSynchronize(r->orb->stream);
-    for (DevBuf* b : {&r->imgs, &r->u_right, &r->depth, &r->best_dist}) b->release();
-    mcv_orb_destroy(r->orb);
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    for (RigSlot& sl : r->slot) {
+        cudaStreamSynchronize(sl.orb->stream);
+        for (DevBuf* b : {&sl.imgs, &sl.kps, &sl.desc, &sl.counts, &sl.u_right, &sl.depth, &sl.best_dist}) b->release();
+        if (sl.done) cudaEventDestroy(sl.done);
+        mcv_orb_destroy(sl.orb);
+    }
+    if (r->fork) cudaEventDestroy(r->fork);
+    if (r->own_stream) cudaStreamDestroy(r->stream);
     delete r;
 }
 
-int mcv_rig_max_keypoints(const mcv_rig* r) { return r ? mcv_orb_max_keypoints(r->orb, 0) : 0; }
-mcv_orb* mcv_rig_extractor(mcv_rig* r) { return r ? r->orb : nullptr; }
+int mcv_rig_max_keypoints(const mcv_rig* r) { return r ? mcv_orb_max_keypoints(r->slot[0].orb, 0) : 0; }
+mcv_orb* mcv_rig_extractor(mcv_rig* r) { return r ? r->slot[0].orb : nullptr; }
 int mcv_rig_last_launches(const mcv_rig* r) { return r ? r->last_launches : 0; }
+mcv_status mcv_rig_set_chunk_frames(mcv_rig* r, int chunk_frames) {
+    if (!r) return MCV_ERR_BAD_ARG;
+    r->chunk_frames = chunk_frames;
+    return MCV_OK;
+}
 
 mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps, uint8_t* d_desc,
                                  int32_t* d_counts, float* d_u_right, float* d_depth, int cap) {
     if (!r || !d_imgs || n_frames <= 0 || !d_kps || !d_desc || !d_counts || !d_u_right || !d_depth) return MCV_ERR_BAD_ARG;
     if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
     if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
-    mcv_orb* h = r->orb;
-    MCV_CUDA(cudaSetDevice(h->device));
-    mcv_status st = ensure_workspace(h, w, hgt, 3 * n_frames, 1);
-    if (st) return st;
-    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints()"); return MCV_ERR_CAPACITY; }
-    if ((st = r->best_dist.reserve((size_t)n_frames * cap * 4))) return st;
-    st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap);
-    if (st) return st;
-    int n = h->last_launches;
-    cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 6] : nullptr;
-    n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
-                       d_depth, r->best_dist.as<int>(), nullptr, h->stream, mid);
-    prof_mark(h, 7);
-    if (h->profile && h->prof_calls < PROF_RING) ++h->prof_calls;
-    MCV_CUDA(cudaGetLastError());
-    r->last_launches = n;
+    MCV_CUDA(cudaSetDevice(r->device));
+    // device-resident batches are throughput-bound: one chunk per call unless the batch is several chunks of 64+ frames
+    const int chunk = std::max(rig_chunk_size(r, n_frames), std::min(n_frames, 128));
+    const size_t img3 = (size_t)3 * w * hgt;
+    int launches = 0, used = 0;
+    MCV_CUDA(cudaEventRecord(r->fork, r->stream));
+    for (int f0 = 0, c = 0; f0 < n_frames; f0 += chunk, ++c) {
+        RigSlot& sl = r->slot[c % RIG_SLOTS];
+        if (c < RIG_SLOTS) { MCV_CUDA(cudaStreamWaitEvent(sl.orb->stream, r->fork, 0)); ++used; }
+        const int nf = std::min(chunk, n_frames - f0);
+        mcv_status st = rig_chunk(r, sl, d_imgs + f0 * img3, nf, w, hgt, d_kps + (size_t)3 * f0 * cap, d_desc + (size_t)3 * f0 * cap * 32,
+                                  d_counts + 3 * f0, d_u_right + (size_t)f0 * cap, d_depth + (size_t)f0 * cap, cap, &launches);
+        if (st) return st;
+    }
+    for (int i = 0; i < used; ++i) {
+        MCV_CUDA(cudaEventRecord(r->slot[i].done, r->slot[i].orb->stream));
+        MCV_CUDA(cudaStreamWaitEvent(r->stream, r->slot[i].done, 0));
+    }
+    r->last_launches = launches;
     return MCV_OK;
 }
 
 mcv_status mcv_rig_set_profiling(mcv_rig* r, int on) {
     if (!r) return MCV_ERR_BAD_ARG;
-    mcv_orb* h = r->orb;
+    mcv_orb* h = r->slot[0].orb;
     MCV_CUDA(cudaSetDevice(h->device));
     if (on && h->ev.empty()) {
         h->ev.resize((size_t)PROF_RING * (N_STAGES + 1));
@@ -774,7 +840,7 @@ mcv_status mcv_rig_set_profiling(mcv_rig* r, int on) {
 
 mcv_status mcv_rig_stage_ms(mcv_rig* r, float* total_ms, int n_stages, int* n_calls) {
     if (!r || !total_ms || n_stages < N_STAGES) return MCV_ERR_BAD_ARG;
-    mcv_orb* h = r->orb;
+    mcv_orb* h = r->slot[0].orb;
     MCV_CUDA(cudaSetDevice(h->device));
     MCV_CUDA(cudaStreamSynchronize(h->stream));
     for (int s = 0; s < n_stages; ++s) total_ms[s] = 0.f;
@@ -790,7 +856,9 @@ mcv_status mcv_rig_stage_ms(mcv_rig* r, float* total_ms, int n_stages, int* n_ca
 
 mcv_status mcv_rig_sync(mcv_rig* r) {
     if (!r) return MCV_ERR_BAD_ARG;
-    MCV_CUDA(cudaStreamSynchronize(r->orb->stream));
+    MCV_CUDA(cudaSetDevice(r->device));
+    MCV_CUDA(cudaStreamSynchronize(r->stream));
+    for (RigSlot& sl : r->slot) MCV_CUDA(cudaStreamSynchronize(sl.orb->stream));
     return MCV_OK;
 }
 
@@ -798,36 +866,53 @@ mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w,
                            uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device) {
     if (!r || !imgs || n_frames <= 0 || !kps_out || !desc_out || !counts || !u_right || !depth_left) return MCV_ERR_BAD_ARG;
     if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
-    mcv_orb* h = r->orb;
-    MCV_CUDA(cudaSetDevice(h->device));
-    mcv_status st;
-    const size_t img_bytes = (size_t)w * hgt, n_img = (size_t)3 * n_frames;
-    const uint8_t* d_imgs = imgs;
-    if (!imgs_on_device) {
-        if ((st = r->imgs.reserve(img_bytes * n_img))) return st;
-        MCV_CUDA(cudaMemcpyAsync(r->imgs.p, imgs, img_bytes * n_img, cudaMemcpyHostToDevice, h->stream));
-        d_imgs = r->imgs.as<uint8_t>();
+    if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaSetDevice(r->device));
+    if (imgs_on_device && out_on_device) {
+        mcv_status st = mcv_rig_process_async(r, imgs, n_frames, w, hgt, kps_out, desc_out, counts, u_right, depth_left, cap);
+        if (st) return st;
+        return mcv_rig_sync(r);
     }
-    mcv_keypoint* d_kps = kps_out; uint8_t* d_desc = desc_out; int* d_counts = counts; float* d_ur = u_right; float* d_dp = depth_left;
-    if (!out_on_device) {
-        if ((st = h->kps.reserve(n_img * cap * sizeof(mcv_keypoint)))) return st;
-        if ((st = h->desc.reserve(n_img * cap * 32))) return st;
-        if ((st = h->counts.reserve(n_img * 4))) return st;
-        if ((st = r->u_right.reserve((size_t)n_frames * cap * 4))) return st;
-        if ((st = r->depth.reserve((size_t)n_frames * cap * 4))) return st;
-        d_kps = h->kps.as<mcv_keypoint>(); d_desc = h->desc.as<uint8_t>(); d_counts = h->counts.as<int>();
-        d_ur = r->u_right.as<float>(); d_dp = r->depth.as<float>();
+    // host side involved: per-chunk H2D -> kernels -> D2H on the slot's stream, chunks overlapping across slots
+    const int chunk = rig_chunk_size(r, n_frames);
+    const size_t img3 = (size_t)3 * w * hgt, kb = sizeof(mcv_keypoint);
+    int launches = 0;
+    MCV_CUDA(cudaStreamSynchronize(r->stream));
+    for (int f0 = 0, c = 0; f0 < n_frames; f0 += chunk, ++c) {
+        RigSlot& sl = r->slot[c % RIG_SLOTS];
+        cudaStream_t s = sl.orb->stream;
+        const int nf = std::min(chunk, n_frames - f0);
+        const size_t n_img = (size_t)3 * nf;
+        mcv_status st;
+        const uint8_t* d_imgs = imgs + f0 * img3;
+        if (!imgs_on_device) {
+            if ((st = sl.imgs.reserve(img3 * nf))) return st;
+            MCV_CUDA(cudaMemcpyAsync(sl.imgs.p, imgs + f0 * img3, img3 * nf, cudaMemcpyHostToDevice, s));
+            d_imgs = sl.imgs.as<uint8_t>();
+        }
+        mcv_keypoint* d_kps = kps_out + (size_t)3 * f0 * cap; uint8_t* d_desc = desc_out + (size_t)3 * f0 * cap * 32;
+        int* d_counts = counts + 3 * f0; float* d_ur = u_right + (size_t)f0 * cap; float* d_dp = depth_left + (size_t)f0 * cap;
+        if (!out_on_device) {
+            if ((st = sl.kps.reserve(n_img * cap * kb))) return st;
+            if ((st = sl.desc.reserve(n_img * cap * 32))) return st;
+            if ((st = sl.counts.reserve(n_img * 4))) return st;
+            if ((st = sl.u_right.reserve((size_t)nf * cap * 4))) return st;
+            if ((st = sl.depth.reserve((size_t)nf * cap * 4))) return st;
+            d_kps = sl.kps.as<mcv_keypoint>(); d_desc = sl.desc.as<uint8_t>(); d_counts = sl.counts.as<int>();
+            d_ur = sl.u_right.as<float>(); d_dp = sl.depth.as<float>();
+        }
+        st = rig_chunk(r, sl, d_imgs, nf, w, hgt, d_kps, d_desc, d_counts, d_ur, d_dp, cap, &launches);
+        if (st) return st;
+        if (!out_on_device) {
+            MCV_CUDA(cudaMemcpyAsync(kps_out + (size_t)3 * f0 * cap, d_kps, n_img * cap * kb, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(desc_out + (size_t)3 * f0 * cap * 32, d_desc, n_img * cap * 32, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(counts + 3 * f0, d_counts, n_img * 4, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(u_right + (size_t)f0 * cap, d_ur, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(depth_left + (size_t)f0 * cap, d_dp, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
+        }
     }
-    st = mcv_rig_process_async(r, d_imgs, n_frames, w, hgt, d_kps, d_desc, d_counts, d_ur, d_dp, cap);
-    if (st) return st;
-    if (!out_on_device) {
-        MCV_CUDA(cudaMemcpyAsync(kps_out, d_kps, n_img * cap * sizeof(mcv_keypoint), cudaMemcpyDeviceToHost, h->stream));
-        MCV_CUDA(cudaMemcpyAsync(desc_out, d_desc, n_img * cap * 32, cudaMemcpyDeviceToHost, h->stream));
-        MCV_CUDA(cudaMemcpyAsync(counts, d_counts, n_img * 4, cudaMemcpyDeviceToHost, h->stream));
-        MCV_CUDA(cudaMemcpyAsync(u_right, d_ur, (size_t)n_frames * cap * 4, cudaMemcpyDeviceToHost, h->stream));
-        MCV_CUDA(cudaMemcpyAsync(depth_left, d_dp, (size_t)n_frames * cap * 4, cudaMemcpyDeviceToHost, h->stream));
-    }
-    MCV_CUDA(cudaStreamSynchronize(h->stream));
+    for (RigSlot& sl : r->slot) MCV_CUDA(cudaStreamSynchronize(sl.orb->stream));
+    r->last_launches = launches;
     return MCV_OK;
 }
 

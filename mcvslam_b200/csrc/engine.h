@@ -51,6 +51,11 @@ struct Plan {
     LevelGeom lv[MAX_LEVELS];
 };
 
+struct StripTable {         // prefix of per-level strip counts: linear strip id -> (level, strip)
+    int first[MAX_LEVELS + 1];
+    int strips_x[MAX_LEVELS];
+};
+
 struct SeedInfo {          // single-image path only
     const mcv_keypoint* d_seeds;  // device copy, original order
     int n_seeds;
@@ -71,7 +76,8 @@ void set_error(const std::string& s);
 int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, uint8_t* d_pyr,
                    const int* d_tabs, int n_images, cudaStream_t s);
 int launch_blur(const Plan& P, const uint8_t* d_pyr, uint8_t* d_blur, int n_images, cudaStream_t s);
-int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s);
+int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, uint32_t* d_cell_pts, int* d_cell_cnt, int n_images,
+                      cudaStream_t s);
 int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
                   uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s);
 int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blur, const uint32_t* d_out_pts, const int* d_out_cnt,

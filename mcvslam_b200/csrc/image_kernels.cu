@@ -103,9 +103,16 @@ int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 7x7 Gaussian, separable, all levels of all images in one launch. Tile = 64 x 32 outputs per CTA.
+// 7x7 Gaussian (Q8 taps 18,34,48,56,48,34,18; two exact integer passes), all levels of all images in one launch.
+//
+// Register-marching separable filter, no shared memory: a warp owns a 128-px wide strip (lane = one aligned 4-px word) and
+// marches down GB_ROWS rows. Per row every lane loads ONE coalesced 32-bit word, gets its left/right neighbour words by
+// warp shuffle, forms the 7-tap horizontal sums with two dp4a per pixel, and keeps the last 7 rows of sums in registers
+// (statically indexed ring); the vertical pass is 4 IMAD + 3 IADD per pixel on that ring. HBM traffic = 1 read + 1 write
+// per pixel plus the 6-row halo (19 %).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int GT_W = 64, GT_H = 32, G_R = 3;
+constexpr int GB_ROWS = 36;              // output rows per warp; GB_ROWS + 6 is a multiple of the 7-row ring
+constexpr int GB_WARPS = 4;
 
 __device__ __forceinline__ int reflect101(int p, int len) {
     if (len == 1) return 0;
@@ -113,66 +120,116 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-struct BlurTiles {  // prefix of tile counts per level so that blockIdx.x -> (level, tile)
-    int first_tile[MAX_LEVELS + 1];
-    int tiles_x[MAX_LEVELS];
-};
-
-__global__ void __launch_bounds__(256) k_gauss7(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Plan P,
-                                                const __grid_constant__ BlurTiles T) {
-    __shared__ uint8_t s_in[GT_H + 2 * G_R][GT_W + 2 * G_R + 2];
-    __shared__ uint16_t s_h[GT_H + 2 * G_R][GT_W];
-    const int img = blockIdx.y;
+__global__ void __launch_bounds__(32 * GB_WARPS) k_gauss7(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+                                                           const __grid_constant__ Plan P, const __grid_constant__ StripTable T) {
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const int sid = blockIdx.x * GB_WARPS + (threadIdx.x >> 5);
+    if (sid >= T.first[P.n_levels]) return;
     int level = 0;
-    while (level + 1 < P.n_levels && (int)blockIdx.x >= T.first_tile[level + 1]) ++level;
+    while (level + 1 < P.n_levels && sid >= T.first[level + 1]) ++level;
     const LevelGeom& g = P.lv[level];
-    const int t = blockIdx.x - T.first_tile[level];
-    const int tx0 = (t % T.tiles_x[level]) * GT_W, ty0 = (t / T.tiles_x[level]) * GT_H;
+    const int t = sid - T.first[level];
+    const int x0 = (t % T.strips_x[level]) * 128 + lane * 4, y0 = (t / T.strips_x[level]) * GB_ROWS;
+    const int w = g.w, h = g.h, pitch = g.pitch;
     const uint8_t* src = pyr + (size_t)img * P.pyr_bytes + g.img_off;
-    uint8_t* dst = blur + (size_t)img * P.pyr_bytes + g.img_off;
-    const int tid = threadIdx.x;
-    // load tile + halo with reflect-101 at the level border
-    for (int i = tid; i < (GT_H + 2 * G_R) * (GT_W + 2 * G_R); i += 256) {
-        const int ly = i / (GT_W + 2 * G_R), lx = i % (GT_W + 2 * G_R);
-        const int gy = reflect101(ty0 + ly - G_R, g.h), gx = reflect101(tx0 + lx - G_R, g.w);
-        s_in[ly][lx] = src[(size_t)gy * g.pitch + gx];
-    }
-    __syncthreads();
-    for (int i = tid; i < (GT_H + 2 * G_R) * GT_W; i += 256) {
-        const int ly = i / GT_W, lx = i % GT_W;
-        const uint8_t* r = &s_in[ly][lx];
-        s_h[ly][lx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
-    }
-    __syncthreads();
-    // vertical pass: each thread produces 4 horizontally adjacent pixels of 2 rows
-    for (int i = tid; i < GT_H * (GT_W / 4); i += 256) {
-        const int ly = i / (GT_W / 4), lx = (i % (GT_W / 4)) * 4;
-        const int gy = ty0 + ly, gx = tx0 + lx;
-        if (gy >= g.h || gx >= g.w) continue;
-        uint32_t packed = 0;
+    uint8_t* dst = blur + (size_t)img * P.pyr_bytes + g.img_off + x0;
+    const bool active = x0 < w;
+    const int n_valid = min(4, w - x0);                     // pixels of this lane's word inside the image (<= 0: none)
+    // lanes 0 / 31 fetch the strip's outer neighbour words themselves (one predicated load per row)
+    const int ex = lane == 0 ? x0 - 4 : x0 + 4;
+    const bool edge = (lane == 0 && x0 > 0) || (lane == 31 && x0 + 4 < pitch);
+    const uint32_t TA = 18u | (34u << 8) | (48u << 16) | (56u << 24), TB = 48u | (34u << 8) | (18u << 16);
+    // BORDER_REFLECT_101 in x without branches in the row loop: per-lane byte-permute selectors, built once.
+    // Window bytes b[-4..7] = (w0, w1, w2). Left edge (x0 == 0): b[-i] = b[i]. Right edge at e = w - 1 - x0: b[i] = b[2e - i], i > e.
+    const int e = w - 1 - x0;
+    uint32_t sel0 = x0 == 0 ? 0x5670u : 0x3210u, sel1 = 0x7654u, sel2 = 0x7654u;   // identity on (w0,w1) -> w0 / w1, on (w1,w2) -> w2
+    const bool w2_from_w0w1 = e <= 2;                       // sources of the reflected w2 bytes then lie in (w0, w1)
+    if (active && e < 7) {
+        sel1 = 0; sel2 = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = 18u * (s_h[ly][lx + k] + s_h[ly + 6][lx + k]) + 34u * (s_h[ly + 1][lx + k] + s_h[ly + 5][lx + k]) +
-                                 48u * (s_h[ly + 2][lx + k] + s_h[ly + 4][lx + k]) + 56u * s_h[ly + 3][lx + k];
-            packed |= ((acc + 32768u) >> 16) << (8 * k);
+        for (int i = 0; i < 4; ++i) {
+            const int s1 = i > e ? 2 * e - i : i;           // source pixel index (window coordinates) of b'[i]
+            sel1 |= (uint32_t)((s1 + 4) & 7) << (4 * i);
+            const int i2 = i + 4, s2 = i2 > e ? 2 * e - i2 : i2;
+            sel2 |= (uint32_t)((w2_from_w0w1 ? s2 + 4 : s2) & 7) << (4 * i);
         }
-        uint8_t* d = dst + (size_t)gy * g.pitch + gx;
-        if (gx + 4 <= g.w) *reinterpret_cast<uint32_t*>(d) = packed;
-        else for (int k = 0; gx + k < g.w; ++k) d[k] = (uint8_t)(packed >> (8 * k));
+    }
+    const int dec = (t / T.strips_x[level]) * GB_ROWS;      // == y0, kept separate so that row offsets stay 32-bit
+    (void)dec;
+
+    auto row_ptr = [&](int r) {                             // reflected input row y0 - 3 + r, clamped for rows that feed nothing
+        int y = y0 - 3 + r;
+        y = y < 0 ? -y : y;
+        y = y >= h ? 2 * h - 2 - y : y;
+        return src + min(max(y, 0), h - 1) * pitch;
+    };
+    // 7-deep software prefetch of the row words (statically indexed, like the ring)
+    uint32_t pw[7], pe[7];
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+        const uint8_t* row = row_ptr(d);
+        pw[d] = active ? __ldg(reinterpret_cast<const uint32_t*>(row + x0)) : 0u;
+        pe[d] = edge ? __ldg(reinterpret_cast<const uint32_t*>(row + ex)) : 0u;
+    }
+    uint32_t ring[7][4];
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ring[j][k] = 0;
+
+#pragma unroll 1
+    for (int rb = 0; rb < GB_ROWS + 6; rb += 7) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const int r = rb + j;                           // input row y0 - 3 + r
+            const uint32_t w1r = pw[j], we = pe[j];
+            {
+                const uint8_t* row = row_ptr(r + 7);
+                pw[j] = active ? __ldg(reinterpret_cast<const uint32_t*>(row + x0)) : 0u;
+                pe[j] = edge ? __ldg(reinterpret_cast<const uint32_t*>(row + ex)) : 0u;
+            }
+            uint32_t w0r = __shfl_up_sync(0xffffffffu, w1r, 1), w2r = __shfl_down_sync(0xffffffffu, w1r, 1);
+            w0r = lane == 0 ? we : w0r;
+            w2r = lane == 31 ? we : w2r;
+            const uint32_t w0 = __byte_perm(w0r, w1r, sel0), w1 = __byte_perm(w0r, w1r, sel1);
+            const uint32_t w2 = __byte_perm(w2_from_w0w1 ? w0r : w1r, w2_from_w0w1 ? w1r : w2r, sel2);
+            // horizontal 7-tap: px k uses bytes [k-3, k] of (w0:w1) and [k+1, k+4] of (w1:w2)
+            ring[j][0] = __dp4a(__funnelshift_r(w0, w1, 8), TA, __dp4a(__funnelshift_r(w1, w2, 8), TB, 0u));
+            ring[j][1] = __dp4a(__funnelshift_r(w0, w1, 16), TA, __dp4a(__funnelshift_r(w1, w2, 16), TB, 0u));
+            ring[j][2] = __dp4a(__funnelshift_r(w0, w1, 24), TA, __dp4a(__funnelshift_r(w1, w2, 24), TB, 0u));
+            ring[j][3] = __dp4a(w1, TA, __dp4a(w2, TB, 0u));
+            const int y = y0 + r - 6;                       // output row whose window ends at input row r
+            if (r >= 6 && y < h) {
+                uint32_t acc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc[k] = 18u * (ring[(j + 1) % 7][k] + ring[j][k]) + 34u * (ring[(j + 2) % 7][k] + ring[(j + 6) % 7][k]) +
+                             48u * (ring[(j + 3) % 7][k] + ring[(j + 5) % 7][k]) + 56u * ring[(j + 4) % 7][k] + 32768u;
+                // byte 2 of each accumulator -> one word
+                const uint32_t o = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+                uint8_t* d = dst + y * pitch;
+                if (n_valid == 4) *reinterpret_cast<uint32_t*>(d) = o;
+                else if (n_valid > 0) {
+                    d[0] = (uint8_t)o;
+                    if (n_valid > 1) d[1] = (uint8_t)(o >> 8);
+                    if (n_valid > 2) d[2] = (uint8_t)(o >> 16);
+                }
+            }
+        }
     }
 }
 
 int launch_blur(const Plan& P, const uint8_t* d_pyr, uint8_t* d_blur, int n_images, cudaStream_t s) {
-    BlurTiles T{};
+    StripTable T{};
     int n = 0;
     for (int l = 0; l < P.n_levels; ++l) {
-        T.first_tile[l] = n;
-        T.tiles_x[l] = (P.lv[l].w + GT_W - 1) / GT_W;
-        n += T.tiles_x[l] * ((P.lv[l].h + GT_H - 1) / GT_H);
+        T.first[l] = n;
+        T.strips_x[l] = (P.lv[l].w + 127) / 128;
+        n += T.strips_x[l] * ((P.lv[l].h + GB_ROWS - 1) / GB_ROWS);
     }
-    for (int l = P.n_levels; l <= MAX_LEVELS; ++l) T.first_tile[l] = n;
-    dim3 grid(n, n_images);
-    k_gauss7<<<grid, 256, 0, s>>>(d_pyr, d_blur, P, T);
+    for (int l = P.n_levels; l <= MAX_LEVELS; ++l) T.first[l] = n;
+    dim3 grid((n + GB_WARPS - 1) / GB_WARPS, n_images);
+    k_gauss7<<<grid, 32 * GB_WARPS, 0, s>>>(d_pyr, d_blur, P, T);
     return 1;
 }
 
