@@ -70,7 +70,7 @@ struct mcv_orb {
     bool have_plan = false;
     int cap_images = 0;     // workspace capacity (images)
     int last_images = 0;    // images processed by the last extract
-    DevBuf tabs, src, pyr, blur, score, cell_pts, cell_cnt, arena_a, arena_b, out_pts, out_cnt, kps, desc, counts, seeds, misc;
+    DevBuf tabs, src, pyr, blur, score, nz_list, nz_cnt, cell_raw, cell_pts, cell_cnt, arena_a, arena_b, out_pts, out_cnt, kps, desc, counts, seeds, misc;
     HostBuf h_stage;
     int last_cap = 0;       // per-image keypoint slots of the last extract (layout of kps/desc)
     int last_launches = 0;
@@ -117,7 +117,7 @@ static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs)
     memset(&P, 0, sizeof(P));
     P.n_levels = h->prm.nlevels; P.w = w; P.h = hgt; P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     tabs.clear();
-    int img_off = 0, cell_base = 0, cand_off = 0, out_off = 0;
+    int img_off = 0, cell_base = 0, cand_off = 0, out_off = 0, nz_off = 0;
     for (int l = 0; l < P.n_levels; ++l) {
         LevelGeom& g = P.lv[l];
         g.scale = h->scale[l]; g.inv_scale = h->inv_scale[l];
@@ -139,6 +139,9 @@ static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs)
         g.cand_off = cand_off;
         g.cand_cap = g.n_cols * g.n_rows * g.cell_cap;
         cand_off += g.cand_cap;
+        g.nz_off = nz_off;
+        g.nz_cap = std::max(0, g.w - 2 * EDGE_THRESHOLD) * std::max(0, g.h - 2 * EDGE_THRESHOLD);
+        nz_off += (g.nz_cap + 63) & ~63;
         g.quota = h->quota[l];
         // quadtree roots — ORBextractor.cc:527-529
         g.n_ini = (int)roundf(width / (float)(max_by - BORDER));
@@ -177,6 +180,16 @@ static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs)
                 yb0[dy] = (short)cv_round_host((1.f - fy) * 2048.f);
                 yb1[dy] = (short)cv_round_host(fy * 2048.f);
             }
+            // k_resize_march preconditions: S[sx], S[sx+1] of 4 consecutive output px inside one 8-byte window, non-negative
+            // coefficients, source rows strictly increasing, source wide enough for three aligned word loads per row
+            bool ok = !g.area_fast && s.pitch >= 16;
+            for (int dx = 0; dx < g.w && ok; dx += 4) {
+                const int last = std::min(dx + 3, g.w - 1);
+                ok = std::min(xofs[last] + 1, s.w - 1) - xofs[dx] <= 7 && xofs[last] >= xofs[dx];
+                for (int k = dx; k <= last && ok; ++k) ok = xofs[k] >= xofs[dx] && xa0[k] >= 0 && xa1[k] >= 0;
+            }
+            for (int dy = 0; dy < g.h && ok; ++dy) ok = yb0[dy] >= 0 && yb1[dy] >= 0 && (dy == 0 || yofs[dy] > yofs[dy - 1]);
+            g.march_ok = ok ? 1 : 0;
             for (auto* v : {&xofs, &xa0, &xa1, &yofs, &yb0, &yb1}) tabs.insert(tabs.end(), v->begin(), v->end());
         }
     }
@@ -184,6 +197,7 @@ static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs)
     P.cells_per_image = cell_base;
     P.cand_per_image = cand_off;
     P.out_per_image = out_off;
+    P.nz_per_image = nz_off;
     P.max_quad_kp = out_off;
     return MCV_OK;
 }
@@ -208,6 +222,9 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
         if ((st = h->blur.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->score.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->cell_pts.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
+        if ((st = h->cell_raw.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
+        if ((st = h->nz_list.reserve((size_t)P.nz_per_image * n_images * 4))) return st;
+        if ((st = h->nz_cnt.reserve((size_t)P.n_levels * n_images * 4))) return st;
         if ((st = h->arena_a.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->arena_b.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->cell_cnt.reserve((size_t)P.cells_per_image * n_images * 4))) return st;
@@ -232,7 +249,8 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     prof_mark(h, 1);
     n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
     prof_mark(h, 2);
-    n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
+    n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->nz_list.as<unsigned>(), h->nz_cnt.as<int>(), h->cell_raw.as<uint32_t>(),
+                           h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
     prof_mark(h, 3);
     const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
                                 h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
@@ -280,7 +298,7 @@ void mcv_orb_destroy(mcv_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->score, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->out_pts, &h->out_cnt,
+    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->score, &h->nz_list, &h->nz_cnt, &h->cell_raw, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->out_pts, &h->out_cnt,
                       &h->kps, &h->desc, &h->counts, &h->seeds, &h->misc})
         b->release();
     h->h_stage.release();
@@ -711,7 +729,7 @@ constexpr int RIG_SLOTS = 3;
 
 struct RigSlot {
     mcv_orb* orb = nullptr;
-    DevBuf imgs, kps, desc, counts, u_right, depth, best_dist;
+    DevBuf imgs, kps, desc, counts, u_right, depth, best_dist, st_scratch;
     cudaEvent_t done = nullptr;
 };
 
@@ -734,12 +752,13 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
     if (st) return st;
     if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints()"); return MCV_ERR_CAPACITY; }
     if ((st = sl.best_dist.reserve((size_t)n_frames * cap * 4))) return st;
+    if ((st = sl.st_scratch.reserve(stereo_scratch_bytes(h->plan, n_frames, cap)))) return st;
     st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap);
     if (st) return st;
     int n = h->last_launches;
     cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 6] : nullptr;
     n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
-                       d_depth, sl.best_dist.as<int>(), nullptr, h->stream, mid);
+                       d_depth, sl.best_dist.as<int>(), nullptr, sl.st_scratch.p, h->stream, mid);
     prof_mark(h, 7);
     if (h->profile && h->prof_calls < PROF_RING) ++h->prof_calls;
     MCV_CUDA(cudaGetLastError());
@@ -780,7 +799,7 @@ void mcv_rig_destroy(mcv_rig* r) {
     cudaStreamSynchronize(r->stream);
     for (RigSlot& sl : r->slot) {
         cudaStreamSynchronize(sl.orb->stream);
-        for (DevBuf* b : {&sl.imgs, &sl.kps, &sl.desc, &sl.counts, &sl.u_right, &sl.depth, &sl.best_dist}) b->release();
+        for (DevBuf* b : {&sl.imgs, &sl.kps, &sl.desc, &sl.counts, &sl.u_right, &sl.depth, &sl.best_dist, &sl.st_scratch}) b->release();
         if (sl.done) cudaEventDestroy(sl.done);
         mcv_orb_destroy(sl.orb);
     }
@@ -933,6 +952,7 @@ mcv_status mcv_stereo_match(mcv_orb* left, mcv_orb* right, const mcv_keypoint* k
     const size_t kb = sizeof(mcv_keypoint);
     const size_t need = (size_t)n_l * (kb + 32 + 16) + (size_t)std::max(n_r, 1) * (kb + 32) + 256;
     if ((st = left->misc.reserve(need))) return st;
+    if ((st = left->seeds.reserve(stereo_scratch_bytes(left->plan, 1, std::max(n_r, 1))))) return st;  // seeds buffer is idle between extracts
     uint8_t* base = left->misc.as<uint8_t>();
     float* d_ur = reinterpret_cast<float*>(base); float* d_dp = d_ur + n_l; int* d_bd = reinterpret_cast<int*>(d_dp + n_l); int* d_br = d_bd + n_l;
     uint8_t* d_dl = reinterpret_cast<uint8_t*>(d_br + n_l); uint8_t* d_dr = d_dl + (size_t)n_l * 32;
@@ -944,7 +964,7 @@ mcv_status mcv_stereo_match(mcv_orb* left, mcv_orb* right, const mcv_keypoint* k
         MCV_CUDA(cudaMemcpyAsync(d_dr, desc_r, (size_t)n_r * 32, cudaMemcpyHostToDevice, s));
     }
     launch_stereo_pair(left->plan, left->pyr.as<uint8_t>(), right->pyr.as<uint8_t>(), d_kl, d_dl, n_l, d_kr, d_dr, n_r, bf, baseline, d_ur, d_dp, d_bd,
-                       d_br, s);
+                       d_br, left->seeds.p, s);
     MCV_CUDA(cudaGetLastError());
     MCV_CUDA(cudaMemcpyAsync(u_right, d_ur, (size_t)n_l * 4, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaMemcpyAsync(depth_left, d_dp, (size_t)n_l * 4, cudaMemcpyDeviceToHost, s));

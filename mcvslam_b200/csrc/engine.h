@@ -31,6 +31,7 @@ struct LevelGeom {
     int cell_cap;          // candidate slots per cell (upper bound of NMS survivors)
     int cand_off;          // entry offset of this level inside one image's candidate block
     int cand_cap;          // n_cells * cell_cap
+    int nz_off, nz_cap;    // this level's slice of one image's non-zero-score list (entries): worst case one per detection pixel
     int quota;             // mnFeaturesPerLevel[level]
     int n_ini;             // quadtree roots
     float h_x;             // root width
@@ -39,13 +40,14 @@ struct LevelGeom {
     int kp_size;           // (int)(31 * scale)
     int tab_off;           // int offset into the resize tables (level >= 1)
     int area_fast;         // exact 2x decimation -> 2x2 box path
+    int march_ok;          // geometry fits k_resize_march (8-byte source window per 4 output px, increasing source rows)
 };
 
 struct Plan {
     int n_levels, w, h;
     int ini_th, min_th;
     int pyr_bytes;         // per image, multiple of 256
-    int cells_per_image, cand_per_image, out_per_image;
+    int cells_per_image, cand_per_image, out_per_image, nz_per_image;
     int max_quad_kp;       // sum of out_cap
     int max_cell_w, max_cell_h, max_quota;
     LevelGeom lv[MAX_LEVELS];
@@ -76,8 +78,8 @@ void set_error(const std::string& s);
 int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, uint8_t* d_pyr,
                    const int* d_tabs, int n_images, cudaStream_t s);
 int launch_blur(const Plan& P, const uint8_t* d_pyr, uint8_t* d_blur, int n_images, cudaStream_t s);
-int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, uint32_t* d_cell_pts, int* d_cell_cnt, int n_images,
-                      cudaStream_t s);
+int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
+                      uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s);
 int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
                   uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s);
 int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blur, const uint32_t* d_out_pts, const int* d_out_cnt,
@@ -85,11 +87,13 @@ int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blu
                        cudaStream_t s);
 int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps, const uint8_t* d_desc, const int* d_counts, int cap,
                   int n_frames, int left_cam, int right_cam, int cams_per_frame, float bf, float baseline, float* d_u_right,
-                  float* d_depth, int* d_best_dist, int* d_best_r, cudaStream_t s, cudaEvent_t mid = nullptr);
+                  float* d_depth, int* d_best_dist, int* d_best_r, void* d_scratch, cudaStream_t s, cudaEvent_t mid = nullptr);
+// bytes of d_scratch (row tables + sorted right-keypoint records) for launch_stereo / launch_stereo_pair
+size_t stereo_scratch_bytes(const Plan& P, int n_frames, int max_right);
 // stereo across two separate pyramids (mcv_stereo_match on two handles): one "frame", explicit pointers
 int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_pyr_r, const mcv_keypoint* d_kl, const uint8_t* d_dl, int nl,
                        const mcv_keypoint* d_kr, const uint8_t* d_dr, int nr, float bf, float baseline, float* d_u_right, float* d_depth,
-                       int* d_best_dist, int* d_best_r, cudaStream_t s);
+                       int* d_best_dist, int* d_best_r, void* d_scratch, cudaStream_t s);
 int launch_octree_standalone(const uint32_t* d_pts, int n, int w_box, int h_box, int n_target, uint32_t* d_arena_a, uint32_t* d_arena_b,
                              uint32_t* d_out, int* d_out_cnt, int out_cap, cudaStream_t s);
 

@@ -82,6 +82,107 @@ __global__ void __launch_bounds__(256) k_resize_level(uint8_t* __restrict__ pyr,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// bilinear resize, register-marching form for the pyramid's usual geometry (1 < scale <= 2, strictly increasing source
+// rows; the host checks both on the tables and otherwise uses k_resize_level).
+//
+// A warp owns a 128-px wide strip of the destination (lane = 4 output pixels) and marches down RS_ROWS output rows. All
+// x-geometry is row-invariant, so each lane builds it ONCE: the 8-byte source window that holds S[sx], S[sx+1] of its four
+// pixels starts at byte sx(px0); it is assembled from three aligned 32-bit loads with two funnel shifts, and two
+// byte-permutes put (S0, S1) pairs where DP2A wants them — the horizontal pass H = S0*a0 + S1*a1 is one DP2A per pixel.
+// The horizontal result of a source row is kept in registers and reused by the next output row (each source row feeds
+// ~1.7 output rows at scale 1.2). Vertical pass per pixel: 2 IMAD.HI + IADD3 + SHF, i.e. exactly
+// (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2 of cv::resize's 11-bit fixed-point path.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RS_ROWS = 32;
+constexpr int RS_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
+                                                                 int sw, int sh, int spitch, int soff, int dw, int dh, int dpitch, int doff,
+                                                                 int strips_x, int n_strips) {
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const int sid = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    if (sid >= n_strips) return;
+    const int dx0 = (sid % strips_x) * 128 + lane * 4, dy0 = (sid / strips_x) * RS_ROWS;
+    const uint8_t* S = pyr + (size_t)img * pyr_bytes + soff;
+    uint8_t* D = pyr + (size_t)img * pyr_bytes + doff;
+    const int* xofs = tab;
+    const int* xa0 = tab + dw;
+    const int* xa1 = tab + 2 * dw;
+    const int* yofs = tab + 3 * dw;
+    const int* yb0 = yofs + dh;
+    const int* yb1 = yofs + 2 * dh;
+    const bool active = dx0 < dw;
+    // row-invariant x geometry of this lane
+    unsigned coef[4], sel01 = 0, sel23 = 0;
+    int wb = 0, shift = 0;
+    {
+        int sx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dx = min(dx0 + k, dw - 1);
+            sx[k] = active ? xofs[dx] : 0;
+            coef[k] = active ? ((unsigned)xa0[dx] | ((unsigned)xa1[dx] << 16)) : 0u;
+        }
+        wb = sx[0] & ~3; shift = (sx[0] & 3) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned o0 = (unsigned)(sx[k] - sx[0]), o1 = (unsigned)(min(sx[k] + 1, sw - 1) - sx[0]);
+            const unsigned pair = (o0 & 7u) | ((o1 & 7u) << 4);
+            if (k < 2) sel01 |= pair << (8 * k); else sel23 |= pair << (8 * (k - 2));
+        }
+    }
+    const int wo0 = wb, wo1 = min(wb + 4, spitch - 4), wo2 = min(wb + 8, spitch - 4);   // never read past the row pitch
+    // per-row coefficients of this strip: lane j holds output row dy0 + j
+    int my_sy = 0;
+    unsigned my_b0 = 0, my_b1 = 0;
+    if (dy0 + lane < dh) { my_sy = yofs[dy0 + lane]; my_b0 = (unsigned)yb0[dy0 + lane] << 16; my_b1 = (unsigned)yb1[dy0 + lane] << 16; }
+
+    auto hrow = [&](int r, unsigned h[4]) {             // horizontal pass of source row r (>> 4 applied)
+        const uint8_t* row = S + (size_t)r * spitch;
+        unsigned w0 = 0, w1 = 0, w2 = 0;
+        if (active) {
+            w0 = *reinterpret_cast<const unsigned*>(row + wo0);
+            w1 = *reinterpret_cast<const unsigned*>(row + wo1);
+            w2 = *reinterpret_cast<const unsigned*>(row + wo2);
+        }
+        const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+        const unsigned p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);
+        h[0] = __dp2a_lo(coef[0], p01, 0u) >> 4; h[1] = __dp2a_hi(coef[1], p01, 0u) >> 4;
+        h[2] = __dp2a_lo(coef[2], p23, 0u) >> 4; h[3] = __dp2a_hi(coef[3], p23, 0u) >> 4;
+    };
+
+    unsigned h0[4] = {0, 0, 0, 0}, h1[4] = {0, 0, 0, 0};
+    int held0 = -1, held1 = -1;
+    const int rows = min(RS_ROWS, dh - dy0);
+    for (int j = 0; j < rows; ++j) {
+        const int sy = __shfl_sync(0xffffffffu, my_sy, j);
+        const unsigned b0 = __shfl_sync(0xffffffffu, my_b0, j), b1 = __shfl_sync(0xffffffffu, my_b1, j);
+        const int ra = min(max(sy, 0), sh - 1), rb = min(max(sy + 1, 0), sh - 1);
+        if (ra != held0) {
+            if (ra == held1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h0[k] = h1[k];
+            } else hrow(ra, h0);
+            held0 = ra;
+        }
+        if (rb != held1) {
+            if (rb == held0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h1[k] = h0[k];
+            } else hrow(rb, h1);
+            held1 = rb;
+        }
+        unsigned v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b0, h0[k]) + __umulhi(b1, h1[k]) + 2u) >> 2;
+        const unsigned packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        uint8_t* d = D + (size_t)(dy0 + j) * dpitch + dx0;
+        if (dx0 + 4 <= dw) *reinterpret_cast<unsigned*>(d) = packed;
+        else if (active) for (int k = 0; dx0 + k < dw; ++k) d[k] = (uint8_t)(packed >> (8 * k));
+    }
+}
+
 int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, uint8_t* d_pyr, const int* d_tabs,
                    int n_images, cudaStream_t s) {
     int launches = 0;
@@ -94,9 +195,15 @@ int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t
     for (int l = 1; l < P.n_levels; ++l) {
         const LevelGeom& a = P.lv[l - 1];
         const LevelGeom& g = P.lv[l];
-        dim3 b(32, 8), grid((g.w + 4 * 32 - 1) / (4 * 32), (g.h + 7) / 8, n_images);
-        k_resize_level<<<grid, b, 0, s>>>(d_pyr, P.pyr_bytes, d_tabs + g.tab_off, a.w, a.h, a.pitch, a.img_off, g.w, g.h, g.pitch,
-                                          g.img_off, g.area_fast);
+        if (g.march_ok) {
+            const int strips_x = (g.w + 127) / 128, n_strips = strips_x * ((g.h + RS_ROWS - 1) / RS_ROWS);
+            k_resize_march<<<dim3((n_strips + RS_WARPS - 1) / RS_WARPS, n_images), 32 * RS_WARPS, 0, s>>>(
+                d_pyr, P.pyr_bytes, d_tabs + g.tab_off, a.w, a.h, a.pitch, a.img_off, g.w, g.h, g.pitch, g.img_off, strips_x, n_strips);
+        } else {
+            dim3 b(32, 8), grid((g.w + 4 * 32 - 1) / (4 * 32), (g.h + 7) / 8, n_images);
+            k_resize_level<<<grid, b, 0, s>>>(d_pyr, P.pyr_bytes, d_tabs + g.tab_off, a.w, a.h, a.pitch, a.img_off, g.w, g.h, g.pitch,
+                                              g.img_off, g.area_fast);
+        }
         ++launches;
     }
     return launches;

@@ -158,8 +158,10 @@ __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int 
     }
     heap_size = __shfl_sync(0xffffffffu, heap_size, 0);
     __syncwarp();
-    // split loop (ORBextractor.cc:557-565)
-    while (heap_size < N) {
+    // split loop (ORBextractor.cc:557-565). Every iteration grows the heap or halves a box, so 16 * N + 256 iterations are
+    // never reached on valid input (unique integer points); the guard only keeps corrupt input from spinning forever, which
+    // is what the reference would do.
+    for (int guard = 16 * N + 256; heap_size < N && guard > 0; --guard) {
         unsigned long long top = 0;
         if (lane == 0) {
             top = heap[0];

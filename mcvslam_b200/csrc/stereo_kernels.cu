@@ -1,9 +1,14 @@
 // Left/right stereo matching for a batch of frames (sm_100a). Replaces Frame::ComputeStereoMatch (src/Frame.cpp:150-328).
 //
+// k_stereo_rows: one CTA per frame. Counting sort of the right keypoints by image row floor(yR) into a compact record
+//     array (uR, row band [minr, maxr], octave, iR) + row_start[] — the device form of vRowIndices (src/Frame.cpp:154-168).
+//     A right keypoint can only be a candidate of left row `row` if |floor(yR) - row| <= ceil(10 * scale[last]) + 1, so the
+//     match kernel scans one contiguous slice of the sorted records (~16 % of them) instead of all right keypoints.
 // k_stereo_match: one warp per left keypoint.
-//   * candidate gate, evaluated for all right keypoints in ascending index order (== the order vRowIndices[row] lists them):
+//   * candidate gate, evaluated exactly as the reference does on every record of that slice:
 //     row band floor(yR - r) <= (int)vL <= ceil(yR + r) with r = 10 * scale[octR]  (src/Frame.cpp:160-168),
 //     |octR - octL| <= 1, uL - maxD <= uR <= uL - 1                                 (src/Frame.cpp:199-215);
+//     the 2-NN key carries iR, so the result does not depend on the order the slice is scanned in;
 //   * Hamming 2-NN over the candidates with strict '<' streaming semantics == lexicographic (distance, index) top-2
 //     (Matcher::KnnMatch + LoopBody, src/Matcher.cpp:245-302), sentinel distance 999;
 //   * FilterRatio(0.70) and FilterThreshold(int(46 * 0.75) = 34)                    (src/Frame.cpp:225);
@@ -29,16 +34,60 @@ struct StereoArgs {
     float bf, baseline;
     float* u_right; float* depth; int* best_dist; int* best_r;
     size_t out_stride;
+    int* row_start;                                // [frame][h + 2]: first sorted record of each image row (+ end)
+    uint4* recs;                                   // [frame][rec_stride] records sorted by row
+    size_t rec_stride;
+    int band;                                      // ceil(10 * scale[last level]) + 2
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// row table of the right keypoints: record = (uR bits, minr | maxr << 16, iR | octave << 24, row)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ StereoArgs A, const __grid_constant__ Plan P) {
+    extern __shared__ int s_row[];                 // h + 1 counters, then reused as running offsets
+    const int f = blockIdx.x, tid = threadIdx.x, h = P.h;
+    const int nr = A.nr ? A.nr[(size_t)f * A.count_stride] : A.nr_fixed;
+    const mcv_keypoint* kr = A.kr + (size_t)f * A.frame_kp_stride;
+    int* row_start = A.row_start + (size_t)f * (h + 2);
+    uint4* recs = A.recs + (size_t)f * A.rec_stride;
+    for (int i = tid; i <= h; i += 256) s_row[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nr; i += 256) atomicAdd(&s_row[min(max((int)floorf(kr[i].y), 0), h - 1)], 1);
+    __syncthreads();
+    // exclusive scan over h rows: 256 threads x ceil(h / 256) consecutive rows each, warp shuffles + one smem hop
+    __shared__ int s_warp[8];
+    const int per = (h + 255) / 256, r0 = tid * per;
+    int sum = 0;
+    for (int r = r0; r < min(r0 + per, h); ++r) sum += s_row[r];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
+    for (int r = r0; r < min(r0 + per, h); ++r) { const int c = s_row[r]; s_row[r] = base; row_start[r] = base; base += c; }
+    if (tid == 255) { row_start[h] = nr; row_start[h + 1] = nr; }
+    __syncthreads();
+    for (int i = tid; i < nr; i += 256) {
+        const float uR = kr[i].x, yR = kr[i].y;
+        const int oct = kr[i].octave;
+        const float r = __fmul_rn(10.f, P.lv[oct].scale);
+        const int maxr = (int)ceilf(__fadd_rn(yR, r)), minr = (int)floorf(__fsub_rn(yR, r));
+        const int row = min(max((int)floorf(yR), 0), h - 1);
+        const int pos = atomicAdd(&s_row[row], 1);
+        // rows are clamped to 16 bits: |minr|, |maxr| < 32768 for any supported image (<= 4128 rows)
+        recs[pos] = make_uint4(__float_as_uint(uR), (unsigned)(minr & 0xffff) | ((unsigned)maxr << 16), (unsigned)i | ((unsigned)oct << 24), (unsigned)row);
+    }
+}
 
 __global__ void __launch_bounds__(32 * ST_WARPS) k_stereo_match(const __grid_constant__ StereoArgs A, const __grid_constant__ Plan P) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int iL = blockIdx.x * ST_WARPS + (threadIdx.x >> 5);
     const int nl = A.nl ? A.nl[(size_t)f * A.count_stride] : A.nl_fixed;
-    const int nr = A.nr ? A.nr[(size_t)f * A.count_stride] : A.nr_fixed;
     if (iL >= nl) return;
     const mcv_keypoint* kl = A.kl + (size_t)f * A.frame_kp_stride;
-    const mcv_keypoint* kr = A.kr + (size_t)f * A.frame_kp_stride;
+    const mcv_keypoint* kr = A.kr + (size_t)f * A.frame_kp_stride;   // .x of the matched keypoint only
     const uint8_t* dl = A.dl + (size_t)f * A.frame_kp_stride * 32;
     const uint8_t* dr = A.dr + (size_t)f * A.frame_kp_stride * 32;
     float* o_ur = A.u_right + (size_t)f * A.out_stride;
@@ -59,13 +108,15 @@ __global__ void __launch_bounds__(32 * ST_WARPS) k_stereo_match(const __grid_con
     // per-lane streaming top-2 over this lane's candidates (ascending iR), keys = dist << 20 | iR
     const unsigned SENT = 999u << 20;
     unsigned k0 = SENT, k1 = SENT;
-    for (int i0 = 0; i0 < nr; i0 += 32) {
-        const int iR = i0 + lane;
-        if (iR < nr) {
-            const float uR = kr[iR].x, yR = kr[iR].y;
-            const int octR = kr[iR].octave;
-            const float r = __fmul_rn(10.f, P.lv[octR].scale);
-            const int maxr = (int)ceilf(__fadd_rn(yR, r)), minr = (int)floorf(__fsub_rn(yR, r));
+    {
+        const int* row_start = A.row_start + (size_t)f * (n_rows + 2);
+        const uint4* recs = A.recs + (size_t)f * A.rec_stride;
+        const int p_end = row_start[min(row + A.band + 1, n_rows)];
+        for (int p = row_start[max(row - A.band, 0)] + lane; p < p_end; p += 32) {
+            const uint4 rec = __ldg(recs + p);
+            const float uR = __uint_as_float(rec.x);
+            const int minr = (int)(short)(rec.y & 0xffffu), maxr = (int)rec.y >> 16;
+            const int octR = (int)(rec.z >> 24), iR = (int)(rec.z & 0xffffffu);
             if (row >= minr && row <= maxr && octR >= levelL - 1 && octR <= levelL + 1 && uR >= minU && uR <= maxU) {
                 const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(dr + (size_t)iR * 32));
                 const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(dr + (size_t)iR * 32 + 16));
@@ -179,17 +230,29 @@ __global__ void __launch_bounds__(256) k_stereo_median(const __grid_constant__ S
     }
 }
 
-static int run_stereo(const StereoArgs& A, const Plan& P, int n_frames, int max_left, cudaStream_t s, cudaEvent_t mid = nullptr) {
+size_t stereo_scratch_bytes(const Plan& P, int n_frames, int max_right) {
+    return (size_t)n_frames * ((size_t)(P.h + 2) * sizeof(int) + (size_t)max_right * sizeof(uint4)) + 256;
+}
+
+static int run_stereo(StereoArgs A, const Plan& P, int n_frames, int max_left, int max_right, void* scratch, cudaStream_t s, cudaEvent_t mid = nullptr) {
+    // scratch layout: records first (16-byte aligned), then the row tables
+    A.recs = reinterpret_cast<uint4*>(scratch);
+    A.rec_stride = (size_t)max_right;
+    A.row_start = reinterpret_cast<int*>(A.recs + (size_t)n_frames * max_right);
+    A.band = (int)ceilf(10.f * P.lv[P.n_levels - 1].scale) + 2;
+    const size_t smem = (size_t)(P.h + 1) * sizeof(int);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_stereo_rows<<<n_frames, 256, smem, s>>>(A, P);
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, n_frames);
     k_stereo_match<<<grid, 32 * ST_WARPS, 0, s>>>(A, P);
     if (mid) cudaEventRecord(mid, s);
     k_stereo_median<<<n_frames, 256, 0, s>>>(A);
-    return 2;
+    return 3;
 }
 
 int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps, const uint8_t* d_desc, const int* d_counts, int cap,
                   int n_frames, int left_cam, int right_cam, int cams_per_frame, float bf, float baseline, float* d_u_right, float* d_depth,
-                  int* d_best_dist, int* d_best_r, cudaStream_t s, cudaEvent_t mid) {
+                  int* d_best_dist, int* d_best_r, void* d_scratch, cudaStream_t s, cudaEvent_t mid) {
     StereoArgs A{};
     A.pyr_l = d_pyr + (size_t)left_cam * P.pyr_bytes; A.pyr_r = d_pyr + (size_t)right_cam * P.pyr_bytes;
     A.frame_pyr_stride = (size_t)cams_per_frame * P.pyr_bytes;
@@ -199,12 +262,12 @@ int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps
     A.frame_kp_stride = (size_t)cams_per_frame * cap;
     A.bf = bf; A.baseline = baseline;
     A.u_right = d_u_right; A.depth = d_depth; A.best_dist = d_best_dist; A.best_r = d_best_r; A.out_stride = cap;
-    return run_stereo(A, P, n_frames, cap, s, mid);
+    return run_stereo(A, P, n_frames, cap, cap, d_scratch, s, mid);
 }
 
 int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_pyr_r, const mcv_keypoint* d_kl, const uint8_t* d_dl, int nl,
                        const mcv_keypoint* d_kr, const uint8_t* d_dr, int nr, float bf, float baseline, float* d_u_right, float* d_depth,
-                       int* d_best_dist, int* d_best_r, cudaStream_t s) {
+                       int* d_best_dist, int* d_best_r, void* d_scratch, cudaStream_t s) {
     StereoArgs A{};
     A.pyr_l = d_pyr_l; A.pyr_r = d_pyr_r; A.frame_pyr_stride = 0;
     A.kl = d_kl; A.kr = d_kr; A.dl = d_dl; A.dr = d_dr;
@@ -212,7 +275,7 @@ int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_p
     A.bf = bf; A.baseline = baseline;
     A.u_right = d_u_right; A.depth = d_depth; A.best_dist = d_best_dist; A.best_r = d_best_r; A.out_stride = 0;
     if (nl <= 0) return 0;
-    return run_stereo(A, P, 1, nl, s);
+    return run_stereo(A, P, 1, nl, std::max(nr, 1), d_scratch, s);
 }
 
 }  // namespace mcv
