@@ -117,7 +117,7 @@ static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs)
     memset(&P, 0, sizeof(P));
     P.n_levels = h->prm.nlevels; P.w = w; P.h = hgt; P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     tabs.clear();
-    int img_off = 0, cell_base = 0, cand_off = 0, out_off = 0, nz_off = 0;
+    int img_off = 0, cell_base = 0, cand_off = 0, out_off = 0;
     for (int l = 0; l < P.n_levels; ++l) {
         LevelGeom& g = P.lv[l];
         g.scale = h->scale[l]; g.inv_scale = h->inv_scale[l];
@@ -139,9 +139,6 @@ static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs)
         g.cand_off = cand_off;
         g.cand_cap = g.n_cols * g.n_rows * g.cell_cap;
         cand_off += g.cand_cap;
-        g.nz_off = nz_off;
-        g.nz_cap = std::max(0, g.w - 2 * EDGE_THRESHOLD) * std::max(0, g.h - 2 * EDGE_THRESHOLD);
-        nz_off += (g.nz_cap + 63) & ~63;
         g.quota = h->quota[l];
         // quadtree roots — ORBextractor.cc:527-529
         g.n_ini = (int)roundf(width / (float)(max_by - BORDER));
@@ -197,7 +194,7 @@ static mcv_status build_plan(mcv_orb* h, int w, int hgt, std::vector<int>& tabs)
     P.cells_per_image = cell_base;
     P.cand_per_image = cand_off;
     P.out_per_image = out_off;
-    P.nz_per_image = nz_off;
+    { StripTable T{}; P.n_fast_strips = fast_strip_table(P, T); }
     P.max_quad_kp = out_off;
     return MCV_OK;
 }
@@ -223,8 +220,8 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
         if ((st = h->score.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->cell_pts.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->cell_raw.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
-        if ((st = h->nz_list.reserve((size_t)P.nz_per_image * n_images * 4))) return st;
-        if ((st = h->nz_cnt.reserve((size_t)P.n_levels * n_images * 4))) return st;
+        if ((st = h->nz_list.reserve((size_t)P.n_fast_strips * FS_SEG * n_images * 4))) return st;
+        if ((st = h->nz_cnt.reserve((size_t)std::max(1, P.n_fast_strips) * n_images * 4))) return st;
         if ((st = h->arena_a.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->arena_b.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->cell_cnt.reserve((size_t)P.cells_per_image * n_images * 4))) return st;
@@ -823,8 +820,9 @@ mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames
     if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
     if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
     MCV_CUDA(cudaSetDevice(r->device));
-    // device-resident batches are throughput-bound: one chunk per call unless the batch is several chunks of 64+ frames
-    const int chunk = std::max(rig_chunk_size(r, n_frames), std::min(n_frames, 128));
+    // chunks round-robin over the slots' streams: the latency-bound quadtree kernel of one chunk overlaps the issue-bound
+    // stencils of the others
+    const int chunk = rig_chunk_size(r, n_frames);
     const size_t img3 = (size_t)3 * w * hgt;
     int launches = 0, used = 0;
     MCV_CUDA(cudaEventRecord(r->fork, r->stream));

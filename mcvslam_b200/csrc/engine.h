@@ -15,6 +15,8 @@ constexpr int EDGE_THRESHOLD = 19;   // ORBextractor.cc:73
 constexpr int BORDER = 16;           // EDGE_THRESHOLD - 3: origin of FAST candidate coordinates (ORBextractor.cc:588)
 constexpr int MAX_DIM = 4096 + 2 * BORDER;  // candidate coordinates are packed in 12 bits
 constexpr int NUM_SMS = 148;
+constexpr int FS_ROWS = 36;            // rows per FAST strip; FS_ROWS + 6 is a multiple of the kernel's 7-row register ring
+constexpr int FS_SEG = 128 * FS_ROWS;  // list entries a strip owns: worst case every pixel of the strip scores
 
 // Candidate / quadtree point: x (12 bits) | y (12 bits) << 12 | response (8 bits) << 24, coordinates relative to BORDER.
 __host__ __device__ inline uint32_t pack_pt(int x, int y, int r) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)r << 24); }
@@ -31,7 +33,6 @@ struct LevelGeom {
     int cell_cap;          // candidate slots per cell (upper bound of NMS survivors)
     int cand_off;          // entry offset of this level inside one image's candidate block
     int cand_cap;          // n_cells * cell_cap
-    int nz_off, nz_cap;    // this level's slice of one image's non-zero-score list (entries): worst case one per detection pixel
     int quota;             // mnFeaturesPerLevel[level]
     int n_ini;             // quadtree roots
     float h_x;             // root width
@@ -47,7 +48,8 @@ struct Plan {
     int n_levels, w, h;
     int ini_th, min_th;
     int pyr_bytes;         // per image, multiple of 256
-    int cells_per_image, cand_per_image, out_per_image, nz_per_image;
+    int cells_per_image, cand_per_image, out_per_image;
+    int n_fast_strips;     // FAST strips (128 px x FS_ROWS rows) over all levels; each owns FS_SEG list entries
     int max_quad_kp;       // sum of out_cap
     int max_cell_w, max_cell_h, max_quota;
     LevelGeom lv[MAX_LEVELS];
@@ -57,6 +59,8 @@ struct StripTable {         // prefix of per-level strip counts: linear strip id
     int first[MAX_LEVELS + 1];
     int strips_x[MAX_LEVELS];
 };
+
+int fast_strip_table(const Plan& P, StripTable& T);
 
 struct SeedInfo {          // single-image path only
     const mcv_keypoint* d_seeds;  // device copy, original order

@@ -13,12 +13,13 @@
 //    pushed to a per-warp queue and scored 32 at a time (one lane per pixel) so the expensive arc min/max network never runs
 //    divergent.
 //
-//    Every pixel with S >= minThFAST (6-7 % of the pixels) is also appended to a per-(image, level) list, one atomicAdd per
-//    32 scored pixels, so that nothing downstream has to scan the dense map again.
+//    Every pixel with S >= minThFAST (6-7 % of the pixels) is also appended to the strip's own list segment (the warp owns
+//    the strip, so the fill count is a register: no atomics), so that nothing downstream has to scan the dense map again.
 //
-//  k_nms_sparse — one thread per listed pixel: strict 8-neighbour maximum test against the dense map, where neighbours
-//    outside the pixel's own cell (detection rims of adjacent cells tile the level without overlap) count as 0 — exactly
-//    what the per-cell cv::FAST sees. Survivors are appended (atomicAdd, unordered) to their cell's slot array.
+//  k_nms_sparse — one warp per strip: stages the strip's window of the dense map (+1 px ring) in shared memory with
+//    coalesced word loads, then runs one lane per listed pixel: strict 8-neighbour maximum test, where neighbours outside
+//    the pixel's own cell (detection rims of adjacent cells tile the level without overlap) count as 0 — exactly what the
+//    per-cell cv::FAST sees. Survivors are appended (atomicAdd, unordered) to their cell's slot array.
 //
 //  k_cell_order — one warp per cell: applies the ini -> min threshold fallback ("any maximum with S >= ini ? S >= ini :
 //    S >= min" — equivalent to re-running FAST at minThFAST) and sorts the survivors by (y, x), i.e. the
@@ -30,7 +31,6 @@
 
 namespace mcv {
 
-constexpr int FS_ROWS = 36;   // output rows per warp; FS_ROWS + 6 is a multiple of the 7-row ring, so no step is wasted
 constexpr int FS_WARPS = 4;
 constexpr int FS_QCAP = 32 + 128;
 
@@ -72,10 +72,11 @@ __device__ __forceinline__ unsigned gt4(unsigned a, unsigned add_lo7, bool add_h
     return add_hi ? (a | s) : (a & s);                  // carry out of bit 7 of a + add, add's bit 7 being a constant
 }
 
-// Scores queued pixels 32 at a time (one lane each) while at least `keep_below` + 1 are queued; returns the new fill.
-// Pixels with score >= Tm go to the dense map and, packed x | y << 12 | score << 24 (level coordinates), to the list.
+// Scores queued pixels 32 at a time (one lane each) while at least `keep_below` + 1 are queued. Pixels with score >= Tm go
+// to the dense map and, packed x | y << 12 | score << 24 (level coordinates), to the strip's list. Returns
+// (list fill << 8) | queue fill.
 __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_below, const uint8_t* src, uint8_t* dst, int pitch, int Tm,
-                                        unsigned* __restrict__ list, int* __restrict__ list_cnt) {
+                                        unsigned* __restrict__ list, int ln) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     __syncwarp();
@@ -90,16 +91,12 @@ __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_belo
             if (sc >= Tm) { dst[y * pitch + x] = (uint8_t)sc; hit = true; packed = pack_pt(x, y, sc); }
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(list_cnt, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (hit) list[base + __popc(m & lt)] = packed;
-        }
+        if (hit) list[ln + __popc(m & lt)] = packed;
+        ln += __popc(m);
         qn -= n;
     }
     __syncwarp();
-    return qn;
+    return (ln << 8) | qn;
 }
 
 __global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
@@ -118,8 +115,8 @@ __global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __r
     const int w = g.w, h = g.h, pitch = g.pitch;
     const uint8_t* src = pyr + (size_t)img * P.pyr_bytes + g.img_off;
     uint8_t* dst = score + (size_t)img * P.pyr_bytes + g.img_off;
-    unsigned* list = nz_list + (size_t)img * P.nz_per_image + g.nz_off;
-    int* list_cnt = nz_cnt + (size_t)img * P.n_levels + level;
+    unsigned* list = nz_list + ((size_t)img * P.n_fast_strips + sid) * FS_SEG;   // this strip's own segment
+    int ln = 0;                                             // its fill (warp-uniform)
     const int x_lo = EDGE_THRESHOLD, x_hi = w - EDGE_THRESHOLD, y_hi = h - EDGE_THRESHOLD;   // detection region [19, n-19)
     const bool in_row = x0 < pitch;                         // word exists in memory
     const int ex = lane == 0 ? x0 - 4 : x0 + 4;             // lanes 0 / 31 fetch the strip's outer neighbour words
@@ -177,39 +174,69 @@ __global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __r
                     base += __popc(m);
                 }
                 qn = base;
-                if (qn >= 32) qn = drain_queue(q, qn, 31, src, dst, pitch, Tm, list, list_cnt);
+                if (qn >= 32) { const int r2 = drain_queue(q, qn, 31, src, dst, pitch, Tm, list, ln); qn = r2 & 0xff; ln = r2 >> 8; }
             }
         }
     }
-    drain_queue(q, qn, 0, src, dst, pitch, Tm, list, list_cnt);
+    ln = drain_queue(q, qn, 0, src, dst, pitch, Tm, list, ln) >> 8;
+    if (lane == 0) nz_cnt[(size_t)img * P.n_fast_strips + sid] = ln;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// sparse NMS: one thread per listed pixel. grid = (chunks of all levels, images); a level's chunks stride over its list.
+// sparse NMS: one warp per strip (same strip table as k_fast_score).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int NMS_THREADS = 256;
+constexpr int NMS_WARPS = 8;
+constexpr int NMS_TW = 34;                      // tile words per row: the strip's 32 words + one word left and right
+constexpr int NMS_TR = FS_ROWS + 2;             // tile rows: the strip's rows + one above and below
 
-struct ChunkTable {           // linear chunk id -> level
-    int first[MAX_LEVELS + 1];
-};
-
-__global__ void __launch_bounds__(NMS_THREADS) k_nms_sparse(const uint8_t* __restrict__ score, const unsigned* __restrict__ nz_list,
-                                                            const int* __restrict__ nz_cnt, uint32_t* __restrict__ cell_raw,
-                                                            int* __restrict__ cell_cnt, const __grid_constant__ Plan P,
-                                                            const __grid_constant__ ChunkTable T) {
-    const int img = blockIdx.y;
+__global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __restrict__ score, const unsigned* __restrict__ nz_list,
+                                                               const int* __restrict__ nz_cnt, uint32_t* __restrict__ cell_raw,
+                                                               int* __restrict__ cell_cnt, const __grid_constant__ Plan P,
+                                                               const __grid_constant__ StripTable T) {
+    __shared__ unsigned s_tile[NMS_WARPS][NMS_TR * NMS_TW];
+    const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sid = blockIdx.x * NMS_WARPS + warp;
+    if (sid >= P.n_fast_strips) return;
+    const int count = nz_cnt[(size_t)img * P.n_fast_strips + sid];
+    if (count == 0) return;
     int level = 0;
-    while (level + 1 < P.n_levels && (int)blockIdx.x >= T.first[level + 1]) ++level;
+    while (level + 1 < P.n_levels && sid >= T.first[level + 1]) ++level;
     const LevelGeom& g = P.lv[level];
-    const int chunk = blockIdx.x - T.first[level], n_chunks = T.first[level + 1] - T.first[level];
-    const int count = nz_cnt[(size_t)img * P.n_levels + level];
-    const unsigned* list = nz_list + (size_t)img * P.nz_per_image + g.nz_off;
+    const int t = sid - T.first[level];
+    const int tx0 = BORDER + (t % T.strips_x[level]) * 128 - 4;           // level x of tile byte 0 (a multiple of 4)
+    const int ty0 = EDGE_THRESHOLD + (t / T.strips_x[level]) * FS_ROWS - 1;   // level y of tile row 0
+    const int pitch = g.pitch;
     const uint8_t* S = score + (size_t)img * P.pyr_bytes + g.img_off;
+    unsigned* tile = s_tile[warp];
+    // stage the window: rows ty0 .. ty0 + NMS_TR - 1, words tx0/4 .. tx0/4 + 33. Bytes outside the level's detection region
+    // may hold anything (the dense map is only written inside it); the test below never reads them.
+    // (fully unrolled: all loads of a batch are in flight before the first store needs its data)
+    constexpr int TILE_ITERS = (NMS_TR * NMS_TW + 31) / 32;
+#pragma unroll
+    for (int k0 = 0; k0 < TILE_ITERS; k0 += 8) {
+        unsigned v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = (k0 + k) * 32 + lane;
+            const int r = i / NMS_TW, w = i - r * NMS_TW;
+            const int y = ty0 + r, x = tx0 + 4 * w;
+            v[k] = (k0 + k < TILE_ITERS && i < NMS_TR * NMS_TW && y < g.h && x + 4 <= pitch) ? __ldg(reinterpret_cast<const unsigned*>(S + (size_t)y * pitch + x)) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = (k0 + k) * 32 + lane;
+            if (k0 + k < TILE_ITERS && i < NMS_TR * NMS_TW) tile[i] = v[k];
+        }
+    }
+    __syncwarp();
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+    const unsigned* list = nz_list + ((size_t)img * P.n_fast_strips + sid) * FS_SEG;
     int* cnts = cell_cnt + (size_t)img * P.cells_per_image + g.cell_base;
     uint32_t* cells = cell_raw + (size_t)img * P.cand_per_image + g.cand_off;
     const float inv_wc = 1.0f / (float)g.w_cell, inv_hc = 1.0f / (float)g.h_cell;
-    const int x_hi = g.w - EDGE_THRESHOLD, y_hi = g.h - EDGE_THRESHOLD, pitch = g.pitch;
-    for (int i = chunk * NMS_THREADS + threadIdx.x; i < count; i += n_chunks * NMS_THREADS) {
+    const int x_hi = g.w - EDGE_THRESHOLD, y_hi = g.h - EDGE_THRESHOLD;
+    constexpr int TP = NMS_TW * 4;                                        // tile pitch in bytes
+    for (int i = lane; i < count; i += 32) {
         const unsigned e = __ldg(list + i);
         const int x = pt_x(e), y = pt_y(e), s = pt_r(e);
         // cell of the pixel: detection region of cell (cy, cx) = rows [19 + cy*h_cell, ...), cols [19 + cx*w_cell, ...)
@@ -217,12 +244,12 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_sparse(const uint8_t* __res
         const int cx = (int)(((float)ux + 0.5f) * inv_wc), cy = (int)(((float)uy + 0.5f) * inv_hc);
         const int rx = ux - cx * g.w_cell, ry = uy - cy * g.h_cell;
         const bool lf = rx > 0, rt = rx < g.w_cell - 1 && x + 1 < x_hi, up = ry > 0, dn = ry < g.h_cell - 1 && y + 1 < y_hi;
-        const uint8_t* c = S + y * pitch + x;
-        int m = 0;                                   // neighbours outside the cell's detection region count as 0
-        if (lf) m = c[-1];
-        if (rt) m = max(m, (int)c[1]);
-        if (up) { m = max(m, (int)c[-pitch]); if (lf) m = max(m, (int)c[-pitch - 1]); if (rt) m = max(m, (int)c[-pitch + 1]); }
-        if (dn) { m = max(m, (int)c[pitch]); if (lf) m = max(m, (int)c[pitch - 1]); if (rt) m = max(m, (int)c[pitch + 1]); }
+        const uint8_t* c = tb + (y - ty0) * TP + (x - tx0);
+        // neighbours outside the cell's detection region count as 0
+        const int l0 = lf ? 1 : 0, r0 = rt ? 1 : 0;
+        int m = max(lf ? (int)c[-1] : 0, rt ? (int)c[1] : 0);
+        if (up) m = max(m, max((int)c[-TP], max((int)c[-TP - l0], (int)c[-TP + r0])));
+        if (dn) m = max(m, max((int)c[TP], max((int)c[TP - l0], (int)c[TP + r0])));
         if (s > m) {
             const int cell = cy * g.n_cols + cx;
             const int slot = atomicAdd(&cnts[cell], 1);
@@ -286,9 +313,9 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) k_cell_order(const uint32_t* _
     if (lane == 0) *cnt_p = kept;
 }
 
-int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
-                      uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s) {
-    StripTable T{};
+// strip table shared by k_fast_score and k_nms_sparse; its total is Plan::n_fast_strips (fast_strip_table is also what
+// build_plan uses to size the list segments)
+int fast_strip_table(const Plan& P, StripTable& T) {
     int n = 0;
     for (int l = 0; l < P.n_levels; ++l) {
         T.first[l] = n;
@@ -297,18 +324,18 @@ int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, uns
         n += T.strips_x[l] * std::max(0, (rh + FS_ROWS - 1) / FS_ROWS);
     }
     for (int l = P.n_levels; l <= MAX_LEVELS; ++l) T.first[l] = n;
-    cudaMemsetAsync(d_nz_cnt, 0, (size_t)n_images * P.n_levels * sizeof(int), s);
+    return n;
+}
+
+int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
+                      uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s) {
+    StripTable T{};
+    const int n = fast_strip_table(P, T);
     cudaMemsetAsync(d_cell_cnt, 0, (size_t)n_images * P.cells_per_image * sizeof(int), s);
-    if (n > 0) k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_score, d_nz_list, d_nz_cnt, P, T);
-    // sparse NMS: size the grid for a 1/8 fill of every level's list (typical scenes: 6-7 %); denser lists are strided over
-    ChunkTable C{};
-    int chunks = 0;
-    for (int l = 0; l < P.n_levels; ++l) {
-        C.first[l] = chunks;
-        chunks += std::max(1, (P.lv[l].nz_cap / 8 + NMS_THREADS - 1) / NMS_THREADS);
+    if (n > 0) {
+        k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_score, d_nz_list, d_nz_cnt, P, T);
+        k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(d_score, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
     }
-    for (int l = P.n_levels; l <= MAX_LEVELS; ++l) C.first[l] = chunks;
-    k_nms_sparse<<<dim3(chunks, n_images), NMS_THREADS, 0, s>>>(d_score, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, C);
     k_cell_order<<<dim3((P.cells_per_image + ORD_WARPS - 1) / ORD_WARPS, n_images), 32 * ORD_WARPS, 0, s>>>(d_cell_raw, d_cell_pts, d_cell_cnt, P);
     return 3;
 }

@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(256) k_resize_level(uint8_t* __restrict__ pyr,
 // ~1.7 output rows at scale 1.2). Vertical pass per pixel: 2 IMAD.HI + IADD3 + SHF, i.e. exactly
 // (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2 of cv::resize's 11-bit fixed-point path.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int RS_ROWS = 32;
+constexpr int RS_ROWS = 16;   // output rows per warp (<= 32: lane j holds row j's coefficients)
 constexpr int RS_WARPS = 4;
+constexpr int RS_PREF = 4;    // source rows in flight per lane
 
 __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
                                                                  int sw, int sh, int spitch, int soff, int dw, int dh, int dpitch, int doff,
@@ -138,48 +139,56 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restr
     unsigned my_b0 = 0, my_b1 = 0;
     if (dy0 + lane < dh) { my_sy = yofs[dy0 + lane]; my_b0 = (unsigned)yb0[dy0 + lane] << 16; my_b1 = (unsigned)yb1[dy0 + lane] << 16; }
 
-    auto hrow = [&](int r, unsigned h[4]) {             // horizontal pass of source row r (>> 4 applied)
-        const uint8_t* row = S + (size_t)r * spitch;
-        unsigned w0 = 0, w1 = 0, w2 = 0;
-        if (active) {
-            w0 = *reinterpret_cast<const unsigned*>(row + wo0);
-            w1 = *reinterpret_cast<const unsigned*>(row + wo1);
-            w2 = *reinterpret_cast<const unsigned*>(row + wo2);
-        }
-        const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+    auto load_row = [&](int r, unsigned w[3]) {         // the three aligned source words of row r (clamped to the image)
+        const uint8_t* row = S + (size_t)min(r, sh - 1) * spitch;
+        w[0] = active ? *reinterpret_cast<const unsigned*>(row + wo0) : 0u;
+        w[1] = active ? *reinterpret_cast<const unsigned*>(row + wo1) : 0u;
+        w[2] = active ? *reinterpret_cast<const unsigned*>(row + wo2) : 0u;
+    };
+    auto hpass = [&](const unsigned w[3], unsigned h[4]) {   // horizontal pass (>> 4 applied)
+        const unsigned lo = __funnelshift_r(w[0], w[1], shift), hi = __funnelshift_r(w[1], w[2], shift);
         const unsigned p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);
         h[0] = __dp2a_lo(coef[0], p01, 0u) >> 4; h[1] = __dp2a_hi(coef[1], p01, 0u) >> 4;
         h[2] = __dp2a_lo(coef[2], p23, 0u) >> 4; h[3] = __dp2a_hi(coef[3], p23, 0u) >> 4;
     };
 
-    unsigned h0[4] = {0, 0, 0, 0}, h1[4] = {0, 0, 0, 0};
-    int held0 = -1, held1 = -1;
+    // The strip's source rows are consecutive: walk them once, RS_PREF rows prefetched ahead (statically indexed ring), and
+    // emit every output row as soon as its lower source row (rb) has been filtered.
     const int rows = min(RS_ROWS, dh - dy0);
-    for (int j = 0; j < rows; ++j) {
-        const int sy = __shfl_sync(0xffffffffu, my_sy, j);
-        const unsigned b0 = __shfl_sync(0xffffffffu, my_b0, j), b1 = __shfl_sync(0xffffffffu, my_b1, j);
-        const int ra = min(max(sy, 0), sh - 1), rb = min(max(sy + 1, 0), sh - 1);
-        if (ra != held0) {
-            if (ra == held1) {
+    const int r_begin = min(max(__shfl_sync(0xffffffffu, my_sy, 0), 0), sh - 1);
+    const int r_end = min(max(__shfl_sync(0xffffffffu, my_sy, rows - 1) + 1, 0), sh - 1);
+    unsigned raw[RS_PREF][3];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) h0[k] = h1[k];
-            } else hrow(ra, h0);
-            held0 = ra;
+    for (int u = 0; u < RS_PREF; ++u) load_row(r_begin + u, raw[u]);
+    unsigned hprev[4] = {0, 0, 0, 0}, hcur[4] = {0, 0, 0, 0};
+    int j = 0;
+#pragma unroll 1
+    for (int r = r_begin; r <= r_end; r += RS_PREF) {
+#pragma unroll
+        for (int u = 0; u < RS_PREF; ++u) {
+            const int rr = r + u;
+            if (rr <= r_end) {
+                unsigned cur[3] = {raw[u][0], raw[u][1], raw[u][2]};
+                load_row(rr + RS_PREF, raw[u]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hprev[k] = hcur[k];
+                hpass(cur, hcur);
+                while (j < rows) {
+                    const int sy = __shfl_sync(0xffffffffu, my_sy, j);
+                    const int ra = min(max(sy, 0), sh - 1), rb = min(max(sy + 1, 0), sh - 1);
+                    if (rb != rr) break;
+                    const unsigned b0 = __shfl_sync(0xffffffffu, my_b0, j), b1 = __shfl_sync(0xffffffffu, my_b1, j);
+                    unsigned v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b0, ra == rb ? hcur[k] : hprev[k]) + __umulhi(b1, hcur[k]) + 2u) >> 2;
+                    const unsigned packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                    uint8_t* d = D + (size_t)(dy0 + j) * dpitch + dx0;
+                    if (dx0 + 4 <= dw) *reinterpret_cast<unsigned*>(d) = packed;
+                    else if (active) for (int k = 0; dx0 + k < dw; ++k) d[k] = (uint8_t)(packed >> (8 * k));
+                    ++j;
+                }
+            }
         }
-        if (rb != held1) {
-            if (rb == held0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) h1[k] = h0[k];
-            } else hrow(rb, h1);
-            held1 = rb;
-        }
-        unsigned v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b0, h0[k]) + __umulhi(b1, h1[k]) + 2u) >> 2;
-        const unsigned packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-        uint8_t* d = D + (size_t)(dy0 + j) * dpitch + dx0;
-        if (dx0 + 4 <= dw) *reinterpret_cast<unsigned*>(d) = packed;
-        else if (active) for (int k = 0; dx0 + k < dw; ++k) d[k] = (uint8_t)(packed >> (8 * k));
     }
 }
 

@@ -9,8 +9,10 @@
 // One warp owns one (image, level) task. Lane 0 drives the heap in shared memory; the whole warp does the data-parallel
 // parts: the scan over the level's cell counts, the gather of the cell lists into reference order, the stable 4-way
 // partition of a node's points (warp ballots), and the final first-max-response search. Point lists ping-pong between two
-// global arenas: a node occupies the same [start, start+count) range in either arena and its children are written to the
-// other one, so no allocation is needed.
+// arenas: a node occupies the same [start, start+count) range in either arena and its children are written to the other
+// one, so no allocation is needed. The arenas live in SHARED memory whenever the level's candidates fit (pts_cap, sized
+// at 5 x quota — several times what textured scenes produce); the ~150 dependent partition passes of a level then run at
+// shared-memory latency. Levels with more candidates than that use the global arenas: same code, same result.
 #include "engine.h"
 
 namespace mcv {
@@ -226,7 +228,7 @@ __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int 
 __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
                                                                uint32_t* __restrict__ arena_a, uint32_t* __restrict__ arena_b,
                                                                uint32_t* __restrict__ out_pts, int* __restrict__ out_cnt,
-                                                               const __grid_constant__ Plan P, int n_images, int heap_cap) {
+                                                               const __grid_constant__ Plan P, int n_images, int heap_cap, int pts_cap) {
     extern __shared__ unsigned long long oct_smem[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task = blockIdx.x * warps + warp;
@@ -234,27 +236,37 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
     // level-major task order so that the long level-0 tasks start first
     const int level = task / n_images, img = task - level * n_images;
     const LevelGeom& g = P.lv[level];
-    unsigned long long* heap = oct_smem + (size_t)warp * heap_cap;
-    NodeRec* nodes = reinterpret_cast<NodeRec*>(oct_smem + (size_t)warps * heap_cap) + (size_t)warp * heap_cap;
+    // per-warp shared memory: heap (8 B) | nodes (16 B) | arena A | arena B (4 B each)
+    const size_t per_warp = (size_t)heap_cap * 3 + (size_t)pts_cap;     // in 8-byte units; pts_cap is even
+    unsigned long long* heap = oct_smem + (size_t)warp * per_warp;
+    NodeRec* nodes = reinterpret_cast<NodeRec*>(heap + heap_cap);
+    uint32_t* sA = reinterpret_cast<uint32_t*>(heap + (size_t)heap_cap * 3);
+    uint32_t* sB = sA + pts_cap;
 
     const int* cnts = cell_cnt + (size_t)img * P.cells_per_image + g.cell_base;
     const uint32_t* cells = cell_pts + (size_t)img * P.cand_per_image + g.cand_off;
-    uint32_t* A = arena_a + (size_t)img * P.cand_per_image + g.cand_off;
-    uint32_t* B = arena_b + (size_t)img * P.cand_per_image + g.cand_off;
     const int n_cells = g.n_cols * g.n_rows;
+    // total first: decides where the arenas live
+    int M = 0;
+    for (int c = lane; c < n_cells; c += 32) M += cnts[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M += __shfl_xor_sync(0xffffffffu, M, o);
+    const bool in_smem = M <= pts_cap;
+    uint32_t* A = in_smem ? sA : arena_a + (size_t)img * P.cand_per_image + g.cand_off;
+    uint32_t* B = in_smem ? sB : arena_b + (size_t)img * P.cand_per_image + g.cand_off;
 
     // gather the per-cell lists into reference order (cell-row-major): 32 cells per round, one lane per cell
-    int M = 0;
+    int base = 0;
     for (int c0 = 0; c0 < n_cells; c0 += 32) {
         const int c = c0 + lane;
         const int k = c < n_cells ? cnts[c] : 0;
         int incl = k;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        const int dst0 = M + incl - k;
+        const int dst0 = base + incl - k;
         const uint32_t* src = cells + (size_t)c * g.cell_cap;
-        for (int j = 0; j < k; ++j) A[dst0 + j] = src[j];
-        M += __shfl_sync(0xffffffffu, incl, 31);
+        for (int j = 0; j < k; ++j) A[dst0 + j] = __ldg(src + j);
+        base += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
     const int box_w = g.w - 2 * BORDER, box_h = g.h - 2 * BORDER;
@@ -263,20 +275,27 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
     if (lane == 0) out_cnt[(size_t)img * P.n_levels + level] = min(n, g.out_cap);
 }
 
-static int oct_config(int max_quota_plus, int& warps, size_t& smem) {
-    // heap (8 B) + node (16 B) per entry; keep a CTA under ~200 KB and use up to 4 warps
-    const size_t per_warp = (size_t)max_quota_plus * (sizeof(unsigned long long) + sizeof(NodeRec));
-    warps = (int)std::min<size_t>(OCT_WARPS_MAX, std::max<size_t>(1, (200 * 1024) / per_warp));
+// Shared memory per warp: heap + nodes for `heap_cap` entries and two point arenas of pts_cap entries; as many warps per CTA
+// (<= 4) as keep a CTA under ~56 KB so that several CTAs stay resident per SM.
+static int oct_config(int heap_cap, int& pts_cap, int& warps, size_t& smem) {
+    const size_t hn = (size_t)heap_cap * (sizeof(unsigned long long) + sizeof(NodeRec));
+    if (hn > 200 * 1024) return -1;
+    pts_cap = std::min(pts_cap, (int)((200 * 1024 - hn) / 8)) & ~1;
+    const size_t per_warp = hn + (size_t)pts_cap * 8;
+    warps = (int)std::min<size_t>(OCT_WARPS_MAX, std::max<size_t>(1, (56 * 1024) / per_warp));
     smem = per_warp * warps;
-    return per_warp <= 220 * 1024 ? 0 : -1;
+    return 0;
 }
 
 int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
                   uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s) {
-    int heap_cap = 8;
-    for (int l = 0; l < P.n_levels; ++l) heap_cap = std::max(heap_cap, P.lv[l].out_cap + 2);
+    int heap_cap = 8, pts_cap = 64;
+    for (int l = 0; l < P.n_levels; ++l) {
+        heap_cap = std::max(heap_cap, P.lv[l].out_cap + 2);
+        pts_cap = std::max(pts_cap, std::min(P.lv[l].cand_cap, 5 * P.lv[l].quota + 256));
+    }
     int warps; size_t smem;
-    if (oct_config(heap_cap, warps, smem)) return -1;
+    if (oct_config(heap_cap, pts_cap, warps, smem)) return -1;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -284,7 +303,7 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     }
     const int tasks = n_images * P.n_levels;
     k_octree<<<(tasks + warps - 1) / warps, 32 * warps, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, P,
-                                                                   n_images, heap_cap);
+                                                                   n_images, heap_cap, pts_cap);
     return 1;
 }
 
