@@ -191,6 +191,9 @@ def main():
 
     def step_device():
         rig.process_async(d_imgs.data_ptr(), B, W, H, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), d_ur.data_ptr(), d_dp.data_ptr())
+
+    def finish_device():
+        rig.join()     # order the timing stream after every step's results
         if world > 1:  # the only collective: gather of the per-image keypoint counts (result directory)
             dist.all_gather_into_tensor(gathered, d_cnt)
 
@@ -208,12 +211,14 @@ def main():
             sampler.start()
         for _ in range(args.warmup):
             step_device()
+        finish_device()
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
         for _ in range(args.steps):
             step_device()
+        finish_device()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -222,6 +227,7 @@ def main():
         rig.set_profiling(True)
         for _ in range(max(3, min(10, args.steps))):
             step_device()
+        finish_device()
         barrier()
         stage_ms, n_calls = rig.stage_ms()
         rig.set_profiling(False)

@@ -182,9 +182,15 @@ mcv_status mcv_rig_set_chunk_frames(mcv_rig* r, int chunk_frames);
 mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, int imgs_on_device,
                            mcv_keypoint* kps_out, uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left,
                            int cap, int out_on_device);
-/* As mcv_rig_process with device-resident inputs and outputs, but only enqueues work on the rig's stream (async). */
+/* As mcv_rig_process with device-resident inputs and outputs, but only ENQUEUES the work (async): it runs on the rig's
+ * internal streams, ordered after everything already on the rig's stream, and consecutive calls overlap (the latency-bound
+ * quadtree stage of one call runs beside the stencils of the next). The results are complete after mcv_rig_sync() (host
+ * wait) or, for work queued on the rig's stream afterwards, after mcv_rig_join(). Do not reuse the output buffers of a call
+ * before one of the two. */
 mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
                                  uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth_left, int cap);
+/* Orders the rig's stream after all work enqueued so far by mcv_rig_process_async (no host wait). */
+mcv_status mcv_rig_join(mcv_rig* r);
 mcv_status mcv_rig_sync(mcv_rig* r);
 /* Number of engine kernels launched by the last process call on this rig (for bench.py's gpu_launches). */
 int mcv_rig_last_launches(const mcv_rig* r);
@@ -224,6 +230,9 @@ mcv_status mcv_debug_fast_atan2(const float* y, const float* x, int n, float* ou
 mcv_status mcv_debug_level_keypoints(mcv_orb* h, int image_index, int level, int which, mcv_keypoint* out, int cap, int* n_out);
 /* Blurred level (GaussianBlur 7x7 sigma 2, ORBextractor.cc:874-875) of the last extract call. */
 mcv_status mcv_debug_download_blurred(mcv_orb* h, int image_index, int level, uint8_t* dst, size_t dst_stride);
+/* SM clock stamps of the quadtree kernel's phases for level 0 of image 0 of the last launch (start, candidates gathered,
+ * roots, split loop done, heap drained, keypoints selected, 0, 0) — where the latency of that kernel goes. */
+mcv_status mcv_debug_octree_clocks(long long* out8);
 /* Integer-pipe microbenchmark: runs `iters` dependent-free rounds of (xor+popc) x8 per thread on the whole GPU and
  * returns achieved popc32/s and the kernel time; the matching roofline denominator. */
 mcv_status mcv_debug_popc_peak(int iters, double* popc_per_s, double* ms);

@@ -29,10 +29,10 @@ EXPORTS = [
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
-    "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
+    "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
     "mcv_project_match", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
-    "mcv_debug_download_blurred", "mcv_debug_popc_peak",
+    "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
         L.mcv_rig_process.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, vp, i, i]
         L.mcv_rig_process_async.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, i]
         L.mcv_rig_sync.argtypes = [vp]
+        L.mcv_rig_join.argtypes = [vp]
         L.mcv_rig_last_launches.argtypes = [vp]
         L.mcv_rig_set_chunk_frames.argtypes = [vp, i]
         L.mcv_rig_set_profiling.argtypes = [vp, i]
@@ -102,6 +103,7 @@ def lib():
         L.mcv_debug_fast_atan2.argtypes = [vp, vp, i, vp]
         L.mcv_debug_level_keypoints.argtypes = [vp, i, i, i, vp, i, C.POINTER(i)]
         L.mcv_debug_download_blurred.argtypes = [vp, i, i, vp, sz]
+        L.mcv_debug_octree_clocks.argtypes = [vp]
         L.mcv_debug_popc_peak.argtypes = [i, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -397,6 +399,10 @@ class Rig:
     def process_async(self, imgs_ptr, n_frames, w, h, kps_ptr, desc_ptr, counts_ptr, ur_ptr, dp_ptr):
         _check(lib().mcv_rig_process_async(self._r, imgs_ptr, n_frames, w, h, kps_ptr, desc_ptr, counts_ptr, ur_ptr, dp_ptr, self.cap))
 
+    def join(self):
+        """Orders the rig's stream after everything process_async has enqueued (no host wait)."""
+        _check(lib().mcv_rig_join(self._r))
+
     def sync(self):
         _check(lib().mcv_rig_sync(self._r))
 
@@ -431,6 +437,12 @@ def debug_fast_atan2(y, x):
     o = np.empty_like(y)
     _check(lib().mcv_debug_fast_atan2(_p(y), _p(x), y.size, _p(o)))
     return o
+
+
+def octree_clocks():
+    c = np.zeros(8, np.int64)
+    _check(lib().mcv_debug_octree_clocks(_p(c)))
+    return c
 
 
 def popc_peak(iters=4096):

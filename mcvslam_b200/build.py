@@ -62,25 +62,5 @@ def build(force=False, verbose=False):
     return SO
 
 
-HOST_TEST_SRC = os.path.join(HERE, "..", "tests", "cpp", "host_mirror_test.cpp")
-HOST_TEST_BIN = os.path.join(HERE, "..", "tests", "cpp", "_build", "host_mirror_test")
-
-
-def build_host_test(force=False):
-    """Compiles the C++ host mirror (host/mcvslam_b200.hpp) into tests/cpp/_build/host_mirror_test with g++, linked against
-    the engine and — as the checker — the CPU oracle. Proves the header-only mirror builds as plain C++17 without nvcc."""
-    ora = os.path.join(HERE, "..", "oracle", "_build")
-    deps = [HOST_TEST_SRC, os.path.join(HERE, "host", "mcvslam_b200.hpp"), os.path.join(HERE, "host", "cv_shim.hpp"),
-            os.path.join(HERE, "..", "include", "mcv_b200.h"), SO, os.path.join(ora, "liborb_oracle.so")]
-    os.makedirs(os.path.dirname(HOST_TEST_BIN), exist_ok=True)
-    if force or _stale(HOST_TEST_BIN, deps):
-        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-pthread", HOST_TEST_SRC, "-o", HOST_TEST_BIN, "-L" + HERE, "-lmcv_b200",
-               "-L" + ora, "-lorb_oracle", "-Wl,-rpath,$ORIGIN/../../../mcvslam_b200", "-Wl,-rpath,$ORIGIN/../../../oracle/_build"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("host mirror test failed to compile:\n%s\n%s" % (r.stdout, r.stderr))
-    return HOST_TEST_BIN
-
-
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

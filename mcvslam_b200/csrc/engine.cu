@@ -215,7 +215,7 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
     const Plan& P = h->plan;
     if (n_images > h->cap_images) {
         mcv_status st;
-        if ((st = h->pyr.reserve((size_t)P.pyr_bytes * n_images))) return st;
+        if ((st = h->pyr.reserve((size_t)P.pyr_bytes * n_images + 256))) return st;   // + spare bytes: k_resize_march reads whole words past a row end
         if ((st = h->blur.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->score.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->cell_pts.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
@@ -237,10 +237,15 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
 }
 
 // Enqueue the whole extraction of n_images device-resident images. d_kps/d_desc/d_counts: device outputs, `cap` slots/image.
+// `wait_front` / `signal_front` (optional) stagger concurrent chunks: the issue-bound front half (pyramid .. per-cell lists)
+// of a chunk starts when the previous chunk's front half is done, so that it runs beside that chunk's latency-bound
+// quadtree kernel instead of beside its front half.
 static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_pitch, size_t src_image_stride, int n_images,
-                                  const SeedInfo* seeds, mcv_keypoint* d_kps, uint8_t* d_desc, int* d_counts, int cap) {
+                                  const SeedInfo* seeds, mcv_keypoint* d_kps, uint8_t* d_desc, int* d_counts, int cap,
+                                  cudaEvent_t wait_front = nullptr, cudaEvent_t signal_front = nullptr) {
     const Plan& P = h->plan;
     int n = 0;
+    if (wait_front) MCV_CUDA(cudaStreamWaitEvent(h->stream, wait_front, 0));
     prof_mark(h, 0);
     n += launch_pyramid(P, d_imgs, src_pitch, src_image_stride, h->pyr.as<uint8_t>(), h->tabs.as<int>(), n_images, h->stream);
     prof_mark(h, 1);
@@ -248,6 +253,7 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     prof_mark(h, 2);
     n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->nz_list.as<unsigned>(), h->nz_cnt.as<int>(), h->cell_raw.as<uint32_t>(),
                            h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
+    if (signal_front) MCV_CUDA(cudaEventRecord(signal_front, h->stream));
     prof_mark(h, 3);
     const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
                                 h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
@@ -689,6 +695,12 @@ mcv_status mcv_debug_fast_atan2(const float* y, const float* x, int n, float* ou
     return MCV_OK;
 }
 
+mcv_status mcv_debug_octree_clocks(long long* out8) {
+    if (!out8) return MCV_ERR_BAD_ARG;
+    if (octree_debug_clocks(out8)) { set_error("cudaMemcpyFromSymbol failed"); return MCV_ERR_CUDA; }
+    return MCV_OK;
+}
+
 mcv_status mcv_debug_popc_peak(int iters, double* popc_per_s, double* ms_out) {
     if (iters <= 0) return MCV_ERR_BAD_ARG;
     cudaStream_t s;
@@ -727,7 +739,7 @@ constexpr int RIG_SLOTS = 3;
 struct RigSlot {
     mcv_orb* orb = nullptr;
     DevBuf imgs, kps, desc, counts, u_right, depth, best_dist, st_scratch;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr, front = nullptr;   // all work of the last chunk / its front half
 };
 
 struct mcv_rig {
@@ -737,21 +749,31 @@ struct mcv_rig {
     bool own_stream = false;
     RigSlot slot[RIG_SLOTS];
     cudaEvent_t fork = nullptr;
-    int chunk_frames = 32;
+    int chunk_frames = 32;          // host path: chunks pipeline H2D / kernels / D2H
+    int chunk_frames_dev = 128;     // device-resident path: consecutive calls overlap instead (see mcv_rig_process_async)
+    int next_slot = 0;              // chunks rotate over the slots across calls
+    int use_slots = RIG_SLOTS;      // host path: slots in rotation (env MCV_RIG_SLOTS)
+    int use_slots_dev = 1;          // device-resident path (env MCV_RIG_SLOTS_DEV): measured on B200, running whole batches
+                                    // back to back on ONE stream beats overlapping them (28.8k vs 25.0k frames/s, profiles/)
+    cudaEvent_t last_front = nullptr;   // front-half event of the most recently enqueued chunk
+    bool pending_join = false;
     int last_launches = 0;
 };
 
 // ORBE + SMatch of n_frames device-resident triplets on one slot (its stream); all pointers are device pointers.
 static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
-                            uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth, int cap, int* launches) {
+                            uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth, int cap, int* launches,
+                            bool stagger = true) {
     mcv_orb* h = sl.orb;
     mcv_status st = ensure_workspace(h, w, hgt, 3 * n_frames, 1);
     if (st) return st;
     if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints()"); return MCV_ERR_CAPACITY; }
     if ((st = sl.best_dist.reserve((size_t)n_frames * cap * 4))) return st;
     if ((st = sl.st_scratch.reserve(stereo_scratch_bytes(h->plan, n_frames, cap)))) return st;
-    st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap);
+    st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap,
+                         stagger && r->last_front != sl.front ? r->last_front : nullptr, sl.front);
     if (st) return st;
+    r->last_front = sl.front;
     int n = h->last_launches;
     cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 6] : nullptr;
     n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
@@ -781,11 +803,15 @@ mcv_status mcv_rig_create(const mcv_rig_params* p, int device, void* stream, mcv
         mcv_status st = mcv_orb_create(&p->orb, device, nullptr, &r->slot[i].orb);
         if (st) { for (int k = 0; k < i; ++k) mcv_orb_destroy(r->slot[k].orb); delete r; return st; }
         cudaEventCreateWithFlags(&r->slot[i].done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&r->slot[i].front, cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&r->fork, cudaEventDisableTiming);
     if (stream) r->stream = (cudaStream_t)stream;
     else { cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking); r->own_stream = true; }
     if (const char* e = getenv("MCV_RIG_CHUNK")) r->chunk_frames = atoi(e);
+    if (const char* e = getenv("MCV_RIG_CHUNK_DEV")) r->chunk_frames_dev = atoi(e);
+    if (const char* e = getenv("MCV_RIG_SLOTS")) r->use_slots = std::max(1, std::min(RIG_SLOTS, atoi(e)));
+    if (const char* e = getenv("MCV_RIG_SLOTS_DEV")) r->use_slots_dev = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     *out = r;
     return MCV_OK;
 }
@@ -798,6 +824,7 @@ void mcv_rig_destroy(mcv_rig* r) {
         cudaStreamSynchronize(sl.orb->stream);
         for (DevBuf* b : {&sl.imgs, &sl.kps, &sl.desc, &sl.counts, &sl.u_right, &sl.depth, &sl.best_dist, &sl.st_scratch}) b->release();
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.front) cudaEventDestroy(sl.front);
         mcv_orb_destroy(sl.orb);
     }
     if (r->fork) cudaEventDestroy(r->fork);
@@ -820,25 +847,36 @@ mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames
     if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
     if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
     MCV_CUDA(cudaSetDevice(r->device));
-    // chunks round-robin over the slots' streams: the latency-bound quadtree kernel of one chunk overlaps the issue-bound
-    // stencils of the others
-    const int chunk = rig_chunk_size(r, n_frames);
+    // Chunks rotate over the slots' streams ACROSS calls and are staggered by their front-half events, so the latency-bound
+    // quadtree kernel of one chunk (or call) runs beside the issue-bound stencils of the next. The work is ordered after
+    // what is already on the rig's stream (fork); the rig's stream is ordered after the results only by mcv_rig_join.
+    const bool profiling = r->slot[0].orb->profile;
+    const int chunk = profiling || r->chunk_frames_dev <= 0 ? n_frames : std::min(n_frames, r->chunk_frames_dev);
     const size_t img3 = (size_t)3 * w * hgt;
-    int launches = 0, used = 0;
+    int launches = 0;
     MCV_CUDA(cudaEventRecord(r->fork, r->stream));
-    for (int f0 = 0, c = 0; f0 < n_frames; f0 += chunk, ++c) {
-        RigSlot& sl = r->slot[c % RIG_SLOTS];
-        if (c < RIG_SLOTS) { MCV_CUDA(cudaStreamWaitEvent(sl.orb->stream, r->fork, 0)); ++used; }
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        RigSlot& sl = r->slot[profiling ? 0 : r->next_slot % r->use_slots_dev];
+        if (!profiling) r->next_slot = (r->next_slot + 1) % r->use_slots_dev;
+        MCV_CUDA(cudaStreamWaitEvent(sl.orb->stream, r->fork, 0));
         const int nf = std::min(chunk, n_frames - f0);
         mcv_status st = rig_chunk(r, sl, d_imgs + f0 * img3, nf, w, hgt, d_kps + (size_t)3 * f0 * cap, d_desc + (size_t)3 * f0 * cap * 32,
-                                  d_counts + 3 * f0, d_u_right + (size_t)f0 * cap, d_depth + (size_t)f0 * cap, cap, &launches);
+                                  d_counts + 3 * f0, d_u_right + (size_t)f0 * cap, d_depth + (size_t)f0 * cap, cap, &launches, !profiling);
         if (st) return st;
     }
-    for (int i = 0; i < used; ++i) {
-        MCV_CUDA(cudaEventRecord(r->slot[i].done, r->slot[i].orb->stream));
-        MCV_CUDA(cudaStreamWaitEvent(r->stream, r->slot[i].done, 0));
-    }
+    r->pending_join = true;
     r->last_launches = launches;
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_join(mcv_rig* r) {
+    if (!r) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaSetDevice(r->device));
+    for (RigSlot& sl : r->slot) {
+        MCV_CUDA(cudaEventRecord(sl.done, sl.orb->stream));
+        MCV_CUDA(cudaStreamWaitEvent(r->stream, sl.done, 0));
+    }
+    r->pending_join = false;
     return MCV_OK;
 }
 
@@ -895,8 +933,9 @@ mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w,
     const size_t img3 = (size_t)3 * w * hgt, kb = sizeof(mcv_keypoint);
     int launches = 0;
     MCV_CUDA(cudaStreamSynchronize(r->stream));
-    for (int f0 = 0, c = 0; f0 < n_frames; f0 += chunk, ++c) {
-        RigSlot& sl = r->slot[c % RIG_SLOTS];
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        RigSlot& sl = r->slot[r->next_slot % r->use_slots];
+        r->next_slot = (r->next_slot + 1) % r->use_slots;
         cudaStream_t s = sl.orb->stream;
         const int nf = std::min(chunk, n_frames - f0);
         const size_t n_img = (size_t)3 * nf;

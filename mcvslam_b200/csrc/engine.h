@@ -101,6 +101,8 @@ int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_p
 int launch_octree_standalone(const uint32_t* d_pts, int n, int w_box, int h_box, int n_target, uint32_t* d_arena_a, uint32_t* d_arena_b,
                              uint32_t* d_out, int* d_out_cnt, int out_cap, cudaStream_t s);
 
+int octree_debug_clocks(long long out[8]);
+
 // matching
 int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, cudaStream_t s);
 int launch_knn2_candidates(const uint8_t* d_q, int nq, const uint8_t* d_t, const int32_t* d_off, const int32_t* d_cidx, int32_t* d_idx,

@@ -236,24 +236,31 @@ __global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __
     const float inv_wc = 1.0f / (float)g.w_cell, inv_hc = 1.0f / (float)g.h_cell;
     const int x_hi = g.w - EDGE_THRESHOLD, y_hi = g.h - EDGE_THRESHOLD;
     constexpr int TP = NMS_TW * 4;                                        // tile pitch in bytes
-    for (int i = lane; i < count; i += 32) {
-        const unsigned e = __ldg(list + i);
-        const int x = pt_x(e), y = pt_y(e), s = pt_r(e);
-        // cell of the pixel: detection region of cell (cy, cx) = rows [19 + cy*h_cell, ...), cols [19 + cx*w_cell, ...)
-        const int ux = x - EDGE_THRESHOLD, uy = y - EDGE_THRESHOLD;
-        const int cx = (int)(((float)ux + 0.5f) * inv_wc), cy = (int)(((float)uy + 0.5f) * inv_hc);
-        const int rx = ux - cx * g.w_cell, ry = uy - cy * g.h_cell;
-        const bool lf = rx > 0, rt = rx < g.w_cell - 1 && x + 1 < x_hi, up = ry > 0, dn = ry < g.h_cell - 1 && y + 1 < y_hi;
-        const uint8_t* c = tb + (y - ty0) * TP + (x - tx0);
-        // neighbours outside the cell's detection region count as 0
-        const int l0 = lf ? 1 : 0, r0 = rt ? 1 : 0;
-        int m = max(lf ? (int)c[-1] : 0, rt ? (int)c[1] : 0);
-        if (up) m = max(m, max((int)c[-TP], max((int)c[-TP - l0], (int)c[-TP + r0])));
-        if (dn) m = max(m, max((int)c[TP], max((int)c[TP - l0], (int)c[TP + r0])));
-        if (s > m) {
-            const int cell = cy * g.n_cols + cx;
-            const int slot = atomicAdd(&cnts[cell], 1);
-            cells[(size_t)cell * g.cell_cap + slot] = pack_pt(x - BORDER, y - BORDER, s);   // reference coordinates: level - BORDER
+    for (int i0 = lane; i0 < count; i0 += 128) {
+        unsigned ent[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ent[u] = i0 + 32 * u < count ? __ldg(list + i0 + 32 * u) : 0u;   // four list loads in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + 32 * u >= count) break;
+            const unsigned e = ent[u];
+            const int x = pt_x(e), y = pt_y(e), s = pt_r(e);
+            // cell of the pixel: detection region of cell (cy, cx) = rows [19 + cy*h_cell, ...), cols [19 + cx*w_cell, ...)
+            const int ux = x - EDGE_THRESHOLD, uy = y - EDGE_THRESHOLD;
+            const int cx = (int)(((float)ux + 0.5f) * inv_wc), cy = (int)(((float)uy + 0.5f) * inv_hc);
+            const int rx = ux - cx * g.w_cell, ry = uy - cy * g.h_cell;
+            const bool lf = rx > 0, rt = rx < g.w_cell - 1 && x + 1 < x_hi, up = ry > 0, dn = ry < g.h_cell - 1 && y + 1 < y_hi;
+            const uint8_t* c = tb + (y - ty0) * TP + (x - tx0);
+            // neighbours outside the cell's detection region count as 0
+            const int l0 = lf ? 1 : 0, r0 = rt ? 1 : 0;
+            int m = max(lf ? (int)c[-1] : 0, rt ? (int)c[1] : 0);
+            if (up) m = max(m, max((int)c[-TP], max((int)c[-TP - l0], (int)c[-TP + r0])));
+            if (dn) m = max(m, max((int)c[TP], max((int)c[TP - l0], (int)c[TP + r0])));
+            if (s > m) {
+                const int cell = cy * g.n_cols + cx;
+                const int slot = atomicAdd(&cnts[cell], 1);
+                cells[(size_t)cell * g.cell_cap + slot] = pack_pt(x - BORDER, y - BORDER, s);   // reference coordinates: level - BORDER
+            }
         }
     }
 }

@@ -133,60 +133,71 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restr
             if (k < 2) sel01 |= pair << (8 * k); else sel23 |= pair << (8 * (k - 2));
         }
     }
-    const int wo0 = wb, wo1 = min(wb + 4, spitch - 4), wo2 = min(wb + 8, spitch - 4);   // never read past the row pitch
     // per-row coefficients of this strip: lane j holds output row dy0 + j
-    int my_sy = 0;
+    int my_rb = -1, my_same = 0, my_sy = 0;
     unsigned my_b0 = 0, my_b1 = 0;
-    if (dy0 + lane < dh) { my_sy = yofs[dy0 + lane]; my_b0 = (unsigned)yb0[dy0 + lane] << 16; my_b1 = (unsigned)yb1[dy0 + lane] << 16; }
-
-    auto load_row = [&](int r, unsigned w[3]) {         // the three aligned source words of row r (clamped to the image)
-        const uint8_t* row = S + (size_t)min(r, sh - 1) * spitch;
-        w[0] = active ? *reinterpret_cast<const unsigned*>(row + wo0) : 0u;
-        w[1] = active ? *reinterpret_cast<const unsigned*>(row + wo1) : 0u;
-        w[2] = active ? *reinterpret_cast<const unsigned*>(row + wo2) : 0u;
-    };
-    auto hpass = [&](const unsigned w[3], unsigned h[4]) {   // horizontal pass (>> 4 applied)
+    if (dy0 + lane < dh) {
+        my_sy = yofs[dy0 + lane]; my_b0 = (unsigned)yb0[dy0 + lane] << 16; my_b1 = (unsigned)yb1[dy0 + lane] << 16;
+        const int ra = min(max(my_sy, 0), sh - 1);
+        my_rb = min(max(my_sy + 1, 0), sh - 1);
+        my_same = ra == my_rb;                                      // both source rows clamp to the same row (image edge)
+    }
+    auto hpass = [&](const unsigned w[3], unsigned h[4]) {         // horizontal pass (>> 4 applied)
         const unsigned lo = __funnelshift_r(w[0], w[1], shift), hi = __funnelshift_r(w[1], w[2], shift);
         const unsigned p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);
         h[0] = __dp2a_lo(coef[0], p01, 0u) >> 4; h[1] = __dp2a_hi(coef[1], p01, 0u) >> 4;
         h[2] = __dp2a_lo(coef[2], p23, 0u) >> 4; h[3] = __dp2a_hi(coef[3], p23, 0u) >> 4;
     };
 
-    // The strip's source rows are consecutive: walk them once, RS_PREF rows prefetched ahead (statically indexed ring), and
-    // emit every output row as soon as its lower source row (rb) has been filtered.
+    // The strip's source rows are consecutive: walk them once with RS_PREF rows in flight (statically indexed ring, no
+    // register rotation: the two horizontal results alternate between hA and hB), and emit every output row as soon as its
+    // lower source row (rb) has been filtered. The three loads of a row are p[0], p[4], p[8] off one running pointer; words
+    // past the row end are never selected (the pyramid allocation carries 256 spare bytes for the very last row).
     const int rows = min(RS_ROWS, dh - dy0);
     const int r_begin = min(max(__shfl_sync(0xffffffffu, my_sy, 0), 0), sh - 1);
-    const int r_end = min(max(__shfl_sync(0xffffffffu, my_sy, rows - 1) + 1, 0), sh - 1);
+    const int r_end = __shfl_sync(0xffffffffu, my_rb, rows - 1);
+    const uint8_t* sp = S + (size_t)r_begin * spitch + wb;          // row r_begin; advanced by RS_PREF rows per round
+    uint8_t* dp = D + (size_t)dy0 * dpitch + dx0;
     unsigned raw[RS_PREF][3];
 #pragma unroll
-    for (int u = 0; u < RS_PREF; ++u) load_row(r_begin + u, raw[u]);
-    unsigned hprev[4] = {0, 0, 0, 0}, hcur[4] = {0, 0, 0, 0};
-    int j = 0;
+    for (int u = 0; u < RS_PREF; ++u) {
+        const bool ld = active && r_begin + u <= r_end;
+        const uint8_t* p = sp + u * spitch;
+        raw[u][0] = ld ? *reinterpret_cast<const unsigned*>(p) : 0u;
+        raw[u][1] = ld ? *reinterpret_cast<const unsigned*>(p + 4) : 0u;
+        raw[u][2] = ld ? *reinterpret_cast<const unsigned*>(p + 8) : 0u;
+    }
+    unsigned hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+    int j = 0, rb_next = __shfl_sync(0xffffffffu, my_rb, 0);
 #pragma unroll 1
     for (int r = r_begin; r <= r_end; r += RS_PREF) {
+        sp += RS_PREF * spitch;
 #pragma unroll
         for (int u = 0; u < RS_PREF; ++u) {
             const int rr = r + u;
-            if (rr <= r_end) {
-                unsigned cur[3] = {raw[u][0], raw[u][1], raw[u][2]};
-                load_row(rr + RS_PREF, raw[u]);
+            const unsigned cur[3] = {raw[u][0], raw[u][1], raw[u][2]};
+            {
+                const bool ld = active && rr + RS_PREF <= r_end;
+                const uint8_t* p = sp + u * spitch;
+                raw[u][0] = ld ? *reinterpret_cast<const unsigned*>(p) : 0u;
+                raw[u][1] = ld ? *reinterpret_cast<const unsigned*>(p + 4) : 0u;
+                raw[u][2] = ld ? *reinterpret_cast<const unsigned*>(p + 8) : 0u;
+            }
+            unsigned* hc = (u & 1) ? hB : hA;                       // resolved at compile time
+            unsigned* hp = (u & 1) ? hA : hB;
+            hpass(cur, hc);
+            while (rb_next == rr) {
+                const unsigned b0 = __shfl_sync(0xffffffffu, my_b0, j), b1 = __shfl_sync(0xffffffffu, my_b1, j);
+                const bool same = __shfl_sync(0xffffffffu, my_same, j) != 0;
+                unsigned v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) hprev[k] = hcur[k];
-                hpass(cur, hcur);
-                while (j < rows) {
-                    const int sy = __shfl_sync(0xffffffffu, my_sy, j);
-                    const int ra = min(max(sy, 0), sh - 1), rb = min(max(sy + 1, 0), sh - 1);
-                    if (rb != rr) break;
-                    const unsigned b0 = __shfl_sync(0xffffffffu, my_b0, j), b1 = __shfl_sync(0xffffffffu, my_b1, j);
-                    unsigned v[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b0, ra == rb ? hcur[k] : hprev[k]) + __umulhi(b1, hcur[k]) + 2u) >> 2;
-                    const unsigned packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-                    uint8_t* d = D + (size_t)(dy0 + j) * dpitch + dx0;
-                    if (dx0 + 4 <= dw) *reinterpret_cast<unsigned*>(d) = packed;
-                    else if (active) for (int k = 0; dx0 + k < dw; ++k) d[k] = (uint8_t)(packed >> (8 * k));
-                    ++j;
-                }
+                for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b0, same ? hc[k] : hp[k]) + __umulhi(b1, hc[k]) + 2u) >> 2;
+                const unsigned packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                if (dx0 + 4 <= dw) *reinterpret_cast<unsigned*>(dp) = packed;
+                else if (active) for (int k = 0; dx0 + k < dw; ++k) dp[k] = (uint8_t)(packed >> (8 * k));
+                dp += dpitch;
+                ++j;
+                rb_next = j < rows ? __shfl_sync(0xffffffffu, my_rb, j) : -1;
             }
         }
     }

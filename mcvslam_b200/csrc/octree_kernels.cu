@@ -54,8 +54,12 @@ __device__ __forceinline__ unsigned long long heap_pop(unsigned long long* h, in
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            if (hcnt(h[child]) < hcnt(h[child - 1])) child--;
-            h[hole] = h[child];
+            // both children in ONE 16-byte load: h points at slot 1 of a 16-byte aligned array, so the pair (child - 1, child) =
+            // (odd, even) index is 16-byte aligned and the sift-down has a single shared-memory latency per level
+            const ulonglong2 pair = *reinterpret_cast<const ulonglong2*>(h + child - 1);
+            unsigned long long v = pair.y;
+            if (hcnt(pair.y) < hcnt(pair.x)) { child--; v = pair.x; }
+            h[hole] = v;
             hole = child;
         }
         if ((len & 1) == 0 && child == (len - 2) / 2) {
@@ -121,10 +125,14 @@ __device__ __forceinline__ void split_points(const uint32_t* __restrict__ src, u
     }
 }
 
+// Phase clocks of task 0 (level 0 of image 0) of the last k_octree launch: start, gathered, roots, split loop, drain, selection.
+__device__ long long g_oct_clk[8];
+#define OCT_CLK(i) do { if (clk && lane == 0) clk[i] = clock64(); } while (0)
+
 // The distribution proper, on points already laid out in arena A [0, M) in reference order.
 // Writes the selected points (heap-pop order) to out[0..n) and returns n in every lane.
 __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int box_w, int box_h, int n_ini, float h_x, int N, int out_cap,
-                               unsigned long long* heap, NodeRec* nodes, uint32_t* out, int lane) {
+                               unsigned long long* heap, NodeRec* nodes, uint32_t* out, int lane, long long* clk = nullptr) {
     if (M == 0) return 0;
     int heap_size = 0, n_nodes = 0;
     // roots (ORBextractor.cc:533-555): bucket by (int)(x / hX), drop empty roots
@@ -160,6 +168,7 @@ __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int 
     }
     heap_size = __shfl_sync(0xffffffffu, heap_size, 0);
     __syncwarp();
+    OCT_CLK(2);
     // split loop (ORBextractor.cc:557-565). Every iteration grows the heap or halves a box, so 16 * N + 256 iterations are
     // never reached on valid input (unique integer points); the guard only keeps corrupt input from spinning forever, which
     // is what the reference would do.
@@ -203,6 +212,7 @@ __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int 
         n_nodes = __shfl_sync(0xffffffffu, n_nodes, 0);
         __syncwarp();
     }
+    OCT_CLK(3);
     // drain (ORBextractor.cc:568-578): pop everything; popped entries pile up at the tail in reverse pop order
     const int total = heap_size;
     if (lane == 0) {
@@ -210,6 +220,7 @@ __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int 
         while (hs > 0) heap_pop(heap, hs);
     }
     __syncwarp();
+    OCT_CLK(4);
     const int n_out = min(total, out_cap);
     for (int i = lane; i < n_out; i += 32) {
         const NodeRec nd = nodes[(uint32_t)heap[total - 1 - i]];
@@ -222,6 +233,7 @@ __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int 
         }
         out[i] = best;
     }
+    OCT_CLK(5);
     return total;
 }
 
@@ -229,23 +241,27 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
                                                                uint32_t* __restrict__ arena_a, uint32_t* __restrict__ arena_b,
                                                                uint32_t* __restrict__ out_pts, int* __restrict__ out_cnt,
                                                                const __grid_constant__ Plan P, int n_images, int heap_cap, int pts_cap) {
-    extern __shared__ unsigned long long oct_smem[];
+    extern __shared__ __align__(16) unsigned long long oct_smem[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task = blockIdx.x * warps + warp;
     if (task >= n_images * P.n_levels) return;
     // level-major task order so that the long level-0 tasks start first
     const int level = task / n_images, img = task - level * n_images;
     const LevelGeom& g = P.lv[level];
-    // per-warp shared memory: heap (8 B) | nodes (16 B) | arena A | arena B (4 B each)
-    const size_t per_warp = (size_t)heap_cap * 3 + (size_t)pts_cap;     // in 8-byte units; pts_cap is even
-    unsigned long long* heap = oct_smem + (size_t)warp * per_warp;
-    NodeRec* nodes = reinterpret_cast<NodeRec*>(heap + heap_cap);
-    uint32_t* sA = reinterpret_cast<uint32_t*>(heap + (size_t)heap_cap * 3);
+    // per-warp shared memory: heap (8 B) | nodes (16 B) | arena A | arena B (4 B each). heap_cap and pts_cap are even, so every
+    // warp's block is 16-byte aligned; the heap proper starts at slot 1 (see heap_pop).
+    const size_t per_warp = (size_t)heap_cap * 3 + (size_t)pts_cap;     // in 8-byte units
+    unsigned long long* hbase = oct_smem + (size_t)warp * per_warp;
+    unsigned long long* heap = hbase + 1;
+    NodeRec* nodes = reinterpret_cast<NodeRec*>(hbase + heap_cap);
+    uint32_t* sA = reinterpret_cast<uint32_t*>(hbase + (size_t)heap_cap * 3);
     uint32_t* sB = sA + pts_cap;
 
     const int* cnts = cell_cnt + (size_t)img * P.cells_per_image + g.cell_base;
     const uint32_t* cells = cell_pts + (size_t)img * P.cand_per_image + g.cand_off;
     const int n_cells = g.n_cols * g.n_rows;
+    long long* clk = task == 0 ? g_oct_clk : nullptr;
+    OCT_CLK(0);
     // total first: decides where the arenas live
     int M = 0;
     for (int c = lane; c < n_cells; c += 32) M += cnts[c];
@@ -269,9 +285,10 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
         base += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
+    OCT_CLK(1);
     const int box_w = g.w - 2 * BORDER, box_h = g.h - 2 * BORDER;
     uint32_t* out = out_pts + (size_t)img * P.out_per_image + g.out_off;
-    const int n = distribute_warp(A, B, M, box_w, box_h, g.n_ini, g.h_x, g.quota, g.out_cap, heap, nodes, out, lane);
+    const int n = distribute_warp(A, B, M, box_w, box_h, g.n_ini, g.h_x, g.quota, g.out_cap, heap, nodes, out, lane, clk);
     if (lane == 0) out_cnt[(size_t)img * P.n_levels + level] = min(n, g.out_cap);
 }
 
@@ -291,7 +308,7 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
                   uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s) {
     int heap_cap = 8, pts_cap = 64;
     for (int l = 0; l < P.n_levels; ++l) {
-        heap_cap = std::max(heap_cap, P.lv[l].out_cap + 2);
+        heap_cap = std::max(heap_cap, (P.lv[l].out_cap + 4 + 1) & ~1);   // + slot 0 offset, even
         pts_cap = std::max(pts_cap, std::min(P.lv[l].cand_cap, 5 * P.lv[l].quota + 256));
     }
     int warps; size_t smem;
@@ -307,12 +324,14 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     return 1;
 }
 
+int octree_debug_clocks(long long out[8]) { return cudaMemcpyFromSymbol(out, g_oct_clk, sizeof(long long) * 8) == cudaSuccess ? 0 : -1; }
+
 // Static DistributeOctTree on caller points (mcv_orb_distribute_octree): one warp, points already in arena A.
 __global__ void __launch_bounds__(32) k_octree_one(uint32_t* arena_a, uint32_t* arena_b, int M, int box_w, int box_h, int n_ini, float h_x,
                                                    int N, uint32_t* out, int* out_cnt, int out_cap, int heap_cap) {
-    extern __shared__ unsigned long long oct_smem[];
+    extern __shared__ __align__(16) unsigned long long oct_smem[];
     NodeRec* nodes = reinterpret_cast<NodeRec*>(oct_smem + heap_cap);
-    const int n = distribute_warp(arena_a, arena_b, M, box_w, box_h, n_ini, h_x, N, out_cap, oct_smem, nodes, out, threadIdx.x);
+    const int n = distribute_warp(arena_a, arena_b, M, box_w, box_h, n_ini, h_x, N, out_cap, oct_smem + 1, nodes, out, threadIdx.x);
     if (threadIdx.x == 0) *out_cnt = min(n, out_cap);
 }
 
@@ -322,7 +341,7 @@ int launch_octree_standalone(const uint32_t* d_pts, int n, int w_box, int h_box,
     const int n_ini = (int)roundf((float)w_box / (float)h_box);
     if (n_ini < 1) return -1;
     const float h_x = (float)w_box / (float)n_ini;
-    const int heap_cap = std::max(n_target + 4, n_ini + 4);
+    const int heap_cap = (std::max(n_target + 4, n_ini + 4) + 4 + 1) & ~1;
     const size_t smem = (size_t)heap_cap * (sizeof(unsigned long long) + sizeof(NodeRec));
     if (smem > 220 * 1024) return -1;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_octree_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -7,9 +7,12 @@ import pytest
 
 
 def _bin(oracle):
+    import sys
     from mcvslam_b200 import build as B
     B.build()
-    return B.build_host_test()
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp"))
+    import build_host_test
+    return build_host_test.build()
 
 
 def test_host_mirror_builds_and_fails_loudly_without_gpu(oracle, tmp_path):
