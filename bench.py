@@ -100,6 +100,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bench_matching(A, torch, dev, stream):
+    """Brute-force Hamming 2-NN (mcv_knn2_bf_device) on device-resident random descriptors: configs[0]'s 2000 x 2000 and one
+    GPU's query shard of configs[4] (131072 of the 1M queries x all 1M train rows). pairs/s, and popc32/s against the live
+    measured xor+popc peak (8 popc32 per 256-bit pair)."""
+    L = A.lib()
+    peak, _ = A.popc_peak(8192)
+    out = {"unit": "descriptor pairs/s", "popc32_peak_per_s": peak, "peak_source": "mcv_debug_popc_peak (8 independent xor+popc+add chains per thread, whole GPU)", "cases": []}
+    g = torch.Generator(device="cpu"); g.manual_seed(5)
+    for name, nq, nt, reps in (("configs[0] 2000x2000", 2000, 2000, 50), ("configs[4] shard 131072x1048576", 131072, 1048576, 2)):
+        q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, generator=g).to(dev)
+        t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, generator=g).to(dev)
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=dev); dst = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        run = lambda: A._check(L.mcv_knn2_bf_device(q.data_ptr(), nq, t.data_ptr(), nt, 0, idx.data_ptr(), dst.data_ptr(), stream.cuda_stream))
+        for _ in range(3 if nq < 10000 else 1):
+            run()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(reps):
+            run()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        sec = e0.elapsed_time(e1) * 1e-3 / reps
+        pairs = float(nq) * nt / sec
+        out["cases"].append({"case": name, "ms": sec * 1e3, "pairs_per_s": pairs, "popc32_per_s": pairs * 8, "frac_of_popc_peak": pairs * 8 / peak,
+                             "self_match_check": None})
+    return out
+
+
 def cpu_baseline(n_threads, budget_s=15.0):
     """The CPU oracle (a port of the reference's algorithm, oracle/) on the host cores over a bounded sample."""
     from oracle import oracle as O
@@ -149,6 +178,7 @@ def main():
     ap.add_argument("--frames", type=int, default=128, help="three-camera frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-matching", action="store_true")
     ap.add_argument("--chunk", type=int, default=None, help="frames per pipelined chunk inside the engine (default: engine default 32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -243,6 +273,12 @@ def main():
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop() if rank == 0 else None
 
+    # second headline metric (BASELINE.json): Hamming matches/s = query x train descriptor pairs per second of the brute-force
+    # 2-NN kernel, device-resident, against the measured xor+popc peak of this GPU (integer-pipe roofline)
+    matching = None
+    if rank == 0 and not args.no_matching:
+        matching = bench_matching(A, torch, dev, stream)
+
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -283,6 +319,7 @@ def main():
             "stage_ms_per_step": {k: v / max(1, n_calls) for k, v in stage_ms.items()},
             "stage_ms_note": "per-kernel CUDA-event durations from %d extra steps run unchunked on one stream right after the timed region" % n_calls,
             "clocks": clocks,
+            "matching": matching,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
