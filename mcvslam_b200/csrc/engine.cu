@@ -70,7 +70,7 @@ struct mcv_orb {
     bool have_plan = false;
     int cap_images = 0;     // workspace capacity (images)
     int last_images = 0;    // images processed by the last extract
-    DevBuf tabs, src, pyr, blur, score, nz_list, nz_cnt, cell_raw, cell_pts, cell_cnt, arena_a, arena_b, out_pts, out_cnt, kps, desc, counts, seeds, misc;
+    DevBuf tabs, src, pyr, blur, score, nz_list, nz_cnt, cell_raw, cell_pts, cell_cnt, arena_a, arena_b, oct_idx, out_pts, out_cnt, kps, desc, counts, seeds, misc;
     HostBuf h_stage;
     int last_cap = 0;       // per-image keypoint slots of the last extract (layout of kps/desc)
     int last_launches = 0;
@@ -224,9 +224,10 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
         if ((st = h->nz_cnt.reserve((size_t)std::max(1, P.n_fast_strips) * n_images * 4))) return st;
         if ((st = h->arena_a.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->arena_b.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
+        if ((st = h->oct_idx.reserve((size_t)P.cand_per_image * n_images * 2))) return st;
         if ((st = h->cell_cnt.reserve((size_t)P.cells_per_image * n_images * 4))) return st;
         if ((st = h->out_pts.reserve((size_t)P.out_per_image * n_images * 4))) return st;
-        if ((st = h->out_cnt.reserve((size_t)P.n_levels * n_images * 4))) return st;
+        if ((st = h->out_cnt.reserve((size_t)P.n_levels * n_images * 4 * 2))) return st;   // counts | per-task overflow flags (launch_octree)
         h->cap_images = n_images;
     }
     mcv_status st;
@@ -256,7 +257,7 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     if (signal_front) MCV_CUDA(cudaEventRecord(signal_front, h->stream));
     prof_mark(h, 3);
     const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
-                                h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
+                                h->oct_idx.as<uint16_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
     if (r < 0) { set_error("nfeatures too large for the quadtree kernel's shared-memory heap"); return MCV_ERR_CAPACITY; }
     n += r;
     prof_mark(h, 4);
@@ -301,7 +302,7 @@ void mcv_orb_destroy(mcv_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->score, &h->nz_list, &h->nz_cnt, &h->cell_raw, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->out_pts, &h->out_cnt,
+    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->score, &h->nz_list, &h->nz_cnt, &h->cell_raw, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->oct_idx, &h->out_pts, &h->out_cnt,
                       &h->kps, &h->desc, &h->counts, &h->seeds, &h->misc})
         b->release();
     h->h_stage.release();

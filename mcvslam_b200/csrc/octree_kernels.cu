@@ -14,6 +14,9 @@
 // at 5 x quota — several times what textured scenes produce); the ~150 dependent partition passes of a level then run at
 // shared-memory latency. Levels with more candidates than that use the global arenas: same code, same result.
 #include "engine.h"
+#include <stdlib.h>
+
+#include "octree_core.cuh"
 
 namespace mcv {
 
@@ -240,11 +243,13 @@ __device__ int distribute_warp(uint32_t* arena_a, uint32_t* arena_b, int M, int 
 __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
                                                                uint32_t* __restrict__ arena_a, uint32_t* __restrict__ arena_b,
                                                                uint32_t* __restrict__ out_pts, int* __restrict__ out_cnt,
-                                                               const __grid_constant__ Plan P, int n_images, int heap_cap, int pts_cap) {
+                                                               const __grid_constant__ Plan P, int n_images, int heap_cap, int pts_cap,
+                                                               const int* __restrict__ only) {
     extern __shared__ __align__(16) unsigned long long oct_smem[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task = blockIdx.x * warps + warp;
     if (task >= n_images * P.n_levels) return;
+    if (only && !only[task]) return;   // fallback launch: only the tasks k_octree_sorted could not hold in shared memory
     // level-major task order so that the long level-0 tasks start first
     const int level = task / n_images, img = task - level * n_images;
     const LevelGeom& g = P.lv[level];
@@ -292,6 +297,162 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
     if (lane == 0) out_cnt[(size_t)img * P.n_levels + level] = min(n, g.out_cap);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_octree_sorted: one CTA per (image, level). Data-parallel phases on all threads (gather in reference order, path codes,
+// counting sort by depth-T bucket, per-bucket sort), then thread 0 replays the heap on counts alone (octree_core.cuh), then
+// all threads pick each surviving node's first-maximum-response point. Everything lives in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int OC_THREADS = 64;
+
+__device__ __forceinline__ int block_excl_scan(int v, int* s_part, int& total) {   // OC_THREADS threads; s_part: OC_THREADS / 32 ints
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();                      // s_part may still be read from a previous scan
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < OC_THREADS / 32; ++w) { const int t = s_part[w]; if (w < warp) base += t; tot += t; }
+    total = tot;
+    return base + incl - v;
+}
+
+// Sorts up to 8 (code, index) pairs held in registers (odd-even transposition, static indexing only).
+__device__ __forceinline__ void sort8(uint32_t (&c)[8], uint16_t (&x)[8]) {
+#pragma unroll
+    for (int round = 0; round < 8; ++round) {
+#pragma unroll
+        for (int i = round & 1; i + 1 < 8; i += 2) {
+            const bool sw = c[i + 1] < c[i];
+            const uint32_t c0 = sw ? c[i + 1] : c[i], c1 = sw ? c[i] : c[i + 1];
+            const uint16_t x0 = sw ? x[i + 1] : x[i], x1 = sw ? x[i] : x[i + 1];
+            c[i] = c0; c[i + 1] = c1; x[i] = x0; x[i + 1] = x1;
+        }
+    }
+}
+
+// One CTA per (image, level). Shared memory holds only what the serial replay touches: R0 = histogram / scatter cursors
+// (nb u32), afterwards heap | node table; S (u16 x nb_pad). Per-point arrays live in global memory (L2-resident): `arena` =
+// candidates in reference order, `scode` / `sidx` = path codes and original indices sorted by code. With ~7 KB per CTA every
+// task of a 128-frame batch is resident at once: the kernel lasts as long as its longest heap replay.
+__global__ void __launch_bounds__(OC_THREADS) k_octree_sorted(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
+                                                              uint32_t* __restrict__ arena, uint32_t* __restrict__ scode_all,
+                                                              uint16_t* __restrict__ sidx_all, uint32_t* __restrict__ out_pts,
+                                                              int* __restrict__ out_cnt, int* __restrict__ overflow,
+                                                              const __grid_constant__ Plan P, int n_images, int nb_pad, int r0_words, int heap_alloc) {
+    extern __shared__ __align__(16) unsigned char oc_smem[];
+    __shared__ int s_part[OC_THREADS / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const int task = blockIdx.x;                       // level-major: the long level-0 tasks start first
+    const int level = task / n_images, img = task - level * n_images;
+    const LevelGeom& lg = P.lv[level];
+    uint32_t* cur = reinterpret_cast<uint32_t*>(oc_smem);
+    uint32_t* heap = cur + 1;                                  // heap - 1 is 16-byte aligned (oct::load2 / load4)
+    uint32_t* nodes = cur + heap_alloc;
+    uint16_t* S = reinterpret_cast<uint16_t*>(cur + r0_words);
+    const size_t task_off = (size_t)img * P.cand_per_image + lg.cand_off;
+    uint32_t* pts = arena + task_off;                  // candidates in reference order
+    uint32_t* scode = scode_all + task_off;
+    uint16_t* sidx = sidx_all + task_off;
+
+    oct::Geom g;
+    g.n_ini = lg.n_ini; g.h_x = lg.h_x; g.box_h = lg.h - 2 * BORDER; g.N = lg.quota; g.T = oct::tier_for(lg.n_ini);
+    const int nb = lg.n_ini << (2 * g.T);
+    const int bsh = 2 * (oct::DIGITS - g.T);
+    long long* clk = task == 0 ? g_oct_clk : nullptr;
+    if (clk && tid == 0) clk[0] = clock64();
+
+    // -- gather: each thread owns a contiguous run of cells (reference order = cell-row-major, row-major inside a cell)
+    const int* cnts = cell_cnt + (size_t)img * P.cells_per_image + lg.cell_base;
+    const uint32_t* cells = cell_pts + task_off;
+    const int n_cells = lg.n_cols * lg.n_rows;
+    const int cpt = (n_cells + OC_THREADS - 1) / OC_THREADS;
+    const int c_lo = min(tid * cpt, n_cells), c_hi = min(c_lo + cpt, n_cells);
+    int mine = 0;
+    for (int c = c_lo; c < c_hi; ++c) mine += cnts[c];
+    for (int b = tid; b < nb; b += OC_THREADS) cur[b] = 0u;
+    int M;
+    int off = block_excl_scan(mine, s_part, M);        // (its barriers also publish the zeroed histogram)
+    if (M > 65535) {                                   // 16-bit indices: the legacy kernel takes this task
+        if (tid == 0) overflow[task] = 1;
+        return;
+    }
+    if (tid == 0) overflow[task] = 0;
+    for (int c = c_lo; c < c_hi; ++c) {
+        const int k = cnts[c];
+        const uint32_t* src = cells + (size_t)c * lg.cell_cap;
+        for (int j = 0; j < k; ++j) {
+            const uint32_t p = __ldg(src + j);
+            pts[off + j] = p;
+            atomicAdd(&cur[min(oct::bucket_direct(p, g), nb - 1)], 1u);   // bucket histogram
+        }
+        off += k;
+    }
+    __syncthreads();
+    if (clk && tid == 0) clk[1] = clock64();
+    // -- exclusive scan of the histogram: S (kept) and cur (scatter cursors)
+    {
+        const int bpt = (nb + OC_THREADS - 1) / OC_THREADS;
+        const int b_lo = min(tid * bpt, nb), b_hi = min(b_lo + bpt, nb);
+        int sum = 0;
+        for (int b = b_lo; b < b_hi; ++b) sum += (int)cur[b];
+        int tot;
+        int run = block_excl_scan(sum, s_part, tot);
+        for (int b = b_lo; b < b_hi; ++b) { const int k = (int)cur[b]; S[b] = (uint16_t)run; cur[b] = (uint32_t)run; run += k; }
+        if (tid == 0) S[nb] = (uint16_t)M;
+    }
+    __syncthreads();
+    // -- scatter (code, index) into bucket order; arrival order inside a bucket is arbitrary, the per-bucket sort fixes it
+#pragma unroll 4
+    for (int i = tid; i < M; i += OC_THREADS) {
+        const uint32_t pc = oct::path_code(__ldcg(pts + i), g);
+        const uint32_t pos = atomicAdd(&cur[min((int)(pc >> bsh), nb - 1)], 1u);
+        scode[pos] = pc;
+        sidx[pos] = (uint16_t)i;
+    }
+    __syncthreads();
+    // -- per-bucket sort by code (codes of distinct points are distinct): every tree node is now a contiguous range
+    for (int b = tid; b < nb; b += OC_THREADS) {
+        const uint32_t lo = S[b], n = S[b + 1] - lo;
+        if (n < 2) continue;
+        if (n <= 8) {
+            uint32_t c[8]; uint16_t x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { c[k] = k < (int)n ? __ldcg(scode + lo + k) : 0xffffffffu; x[k] = k < (int)n ? __ldcg(sidx + lo + k) : (uint16_t)0; }
+            sort8(c, x);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k < (int)n) { scode[lo + k] = c[k]; sidx[lo + k] = x[k]; }
+        } else {                                       // crowded bucket: plain insertion sort in global memory
+            for (uint32_t i = lo + 1; i < lo + n; ++i) {
+                const uint32_t c = __ldcg(scode + i);
+                const uint16_t x = __ldcg(sidx + i);
+                uint32_t j = i;
+                while (j > lo && __ldcg(scode + j - 1) > c) { scode[j] = __ldcg(scode + j - 1); sidx[j] = __ldcg(sidx + j - 1); --j; }
+                scode[j] = c; sidx[j] = x;
+            }
+        }
+    }
+    __syncthreads();
+    if (clk && tid == 0) clk[2] = clock64();
+    // -- serial heap replay on counts
+    if (tid == 0) {
+        s_total = oct::replay(scode, S, g, heap, nodes, clk ? clk + 3 : nullptr);
+        if (clk) clk[4] = clock64();
+    }
+    __syncthreads();
+    const int total = s_total;
+    const int n_out = min(total, lg.out_cap);
+    uint32_t* out = out_pts + (size_t)img * P.out_per_image + lg.out_off;
+    for (int i = tid; i < n_out; i += OC_THREADS) out[i] = oct::select_best(heap[total - 1 - i], nodes, S, g.T, pts, sidx);
+    if (tid == 0) {
+        out_cnt[(size_t)img * P.n_levels + level] = n_out;
+        if (clk) clk[5] = clock64();
+    }
+}
+
 // Shared memory per warp: heap + nodes for `heap_cap` entries and two point arenas of pts_cap entries; as many warps per CTA
 // (<= 4) as keep a CTA under ~56 KB so that several CTAs stay resident per SM.
 static int oct_config(int heap_cap, int& pts_cap, int& warps, size_t& smem) {
@@ -304,8 +465,8 @@ static int oct_config(int heap_cap, int& pts_cap, int& warps, size_t& smem) {
     return 0;
 }
 
-int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
-                  uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s) {
+static int launch_octree_legacy(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
+                                uint32_t* d_out_pts, int* d_out_cnt, int n_images, const int* d_only, cudaStream_t s) {
     int heap_cap = 8, pts_cap = 64;
     for (int l = 0; l < P.n_levels; ++l) {
         heap_cap = std::max(heap_cap, (P.lv[l].out_cap + 4 + 1) & ~1);   // + slot 0 offset, even
@@ -320,8 +481,46 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     }
     const int tasks = n_images * P.n_levels;
     k_octree<<<(tasks + warps - 1) / warps, 32 * warps, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, P,
-                                                                   n_images, heap_cap, pts_cap);
+                                                                   n_images, heap_cap, pts_cap, d_only);
     return 1;
+}
+
+int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
+                  uint16_t* d_oct_idx, uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s) {
+    // profiling aid (what does the stage cost inside the pipelined step?): MCV_DEBUG_SKIP_OCTREE_AFTER=n stops launching the
+    // quadtree after n calls — downstream then consumes the previous call's selection, so results are only valid for repeated input
+    static const char* skip_env = getenv("MCV_DEBUG_SKIP_OCTREE_AFTER");
+    static long skip_calls = 0;
+    if (skip_env && ++skip_calls > atol(skip_env)) return 0;
+    // shared-memory plan of k_octree_sorted: R0 = cursors, later heap | nodes (r0_words u32) | S (nb_pad u16)
+    int nb = 1, max_ini = 1, max_heap = 8;
+    bool can_overflow = false;
+    for (int l = 0; l < P.n_levels; ++l) {
+        const LevelGeom& g = P.lv[l];
+        max_ini = std::max(max_ini, g.n_ini);
+        max_heap = std::max(max_heap, std::max(g.quota + 3, g.n_ini));
+        nb = std::max(nb, g.n_ini << (2 * oct::tier_for(g.n_ini)));
+        can_overflow |= g.cand_cap > 65535;
+    }
+    const int heap_alloc = (2 * (max_heap + 1) + 8 + 3) & ~3;              // oct::heap_pop's speculative reach (+ the slot before the heap)
+    const int r0_words = (std::max(nb, heap_alloc + max_heap + 4) + 3) & ~3;
+    const int nb_pad = (nb + 1 + 7) & ~7;
+    const size_t smem = (size_t)r0_words * 4 + (size_t)nb_pad * 2;
+    if (max_ini > oct::MAX_ROOTS || max_heap > 65000 || smem > 200 * 1024)   // panoramas / huge quotas: legacy kernel for everything
+        return launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, nullptr, s);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_octree_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // many small CTAs that live as long as one thread's heap replay: ask for the largest shared-memory carve-out
+        cudaFuncSetAttribute(k_octree_sorted, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = smem;
+    }
+    const int tasks = n_images * P.n_levels;
+    int* d_overflow = d_out_cnt + tasks;
+    k_octree_sorted<<<tasks, OC_THREADS, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_out_pts, d_out_cnt, d_overflow, P,
+                                                    n_images, nb_pad, r0_words, heap_alloc);
+    if (!can_overflow) return 1;
+    return 1 + launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, d_overflow, s);
 }
 
 int octree_debug_clocks(long long out[8]) { return cudaMemcpyFromSymbol(out, g_oct_clk, sizeof(long long) * 8) == cudaSuccess ? 0 : -1; }

@@ -1,0 +1,38 @@
+// Test infrastructure: runs the quadtree core that the sm_100a kernel uses (mcvslam_b200/csrc/octree_core.cuh) on the CPU,
+// with the kernel's data-parallel phases replayed sequentially (and the bucket scatter deliberately in REVERSE arrival order,
+// since the kernel's atomics give no order), so tests/test_octree_core.py can check it against the oracle without a GPU.
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../mcvslam_b200/csrc/octree_core.cuh"
+
+using namespace mcv::oct;
+using std::max;
+
+extern "C" int octcore_distribute(const uint32_t* pts, int M, int box_w, int box_h, int N, uint32_t* out, int out_cap) {
+    const int n_ini = (int)roundf((float)box_w / (float)box_h);   // ORBextractor.cc:527
+    if (n_ini < 1 || n_ini > MAX_ROOTS || M > 65535) return -1;
+    Geom g{n_ini, (float)box_w / (float)n_ini, box_h, N, tier_for(n_ini)};
+    const int nb = n_ini << (2 * g.T);
+    std::vector<uint32_t> code(M), S(nb + 1, 0), cur(nb, 0), scode(M);
+    std::vector<uint16_t> sidx(M);
+    for (int i = 0; i < M; ++i) { code[i] = path_code(pts[i], g); if (bucket_of(code[i], g.T) >= nb || bucket_direct(pts[i], g) != bucket_of(code[i], g.T)) return -2; ++cur[bucket_of(code[i], g.T)]; }
+    for (int b = 0; b < nb; ++b) { S[b + 1] = S[b] + cur[b]; cur[b] = S[b]; }
+    for (int i = M - 1; i >= 0; --i) { const uint32_t pos = cur[bucket_of(code[i], g.T)]++; scode[pos] = code[i]; sidx[pos] = (uint16_t)i; }
+    for (int b = 0; b < nb; ++b)   // per-bucket insertion sort, as the kernel does
+        for (uint32_t i = S[b] + 1; i < S[b + 1]; ++i) {
+            const uint32_t c = scode[i]; const uint16_t x = sidx[i];
+            uint32_t j = i;
+            while (j > S[b] && scode[j - 1] > c) { scode[j] = scode[j - 1]; sidx[j] = sidx[j - 1]; --j; }
+            scode[j] = c; sidx[j] = x;
+        }
+    std::vector<uint32_t> heap_store(2 * (std::max(N + 3, n_ini) + 1) + 8 + 2), nodes(std::max(N + 3, n_ini) + 4);
+    uint32_t* heap = heap_store.data() + 1;
+    std::vector<uint16_t> S16(S.begin(), S.end());   // the kernel keeps the table in 16 bits
+    const int total = replay(scode.data(), S16.data(), g, heap, nodes.data());
+    for (int i = 0; i < total && i < out_cap; ++i) out[i] = select_best(heap[total - 1 - i], nodes.data(), S16.data(), g.T, pts, sidx.data());
+    return total;
+}
