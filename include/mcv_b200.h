@@ -189,6 +189,15 @@ mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w,
  * before one of the two. */
 mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
                                  uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth_left, int cap);
+/* As mcv_rig_process with HOST inputs and outputs (pinned memory, or the copies degrade to synchronous ones), but only ENQUEUES
+ * the step — host->device copy of the images, kernels, device->host copy of every result — on the rig's internal streams and
+ * returns a ticket; consecutive submits overlap (copies of one step beside the kernels of another; this replaces the reference's
+ * capture thread running ahead of Frame construction, src/System.cpp:60-66). The outputs of a submit are complete after
+ * mcv_rig_wait(ticket) (or mcv_rig_sync). The caller keeps the buffers alive and untouched until then; at most 8 tickets may be
+ * outstanding. Chunk size: env MCV_RIG_SUBMIT_CHUNK (default 64 frames). */
+mcv_status mcv_rig_submit(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, mcv_keypoint* kps_out, uint8_t* desc_out,
+                          int32_t* counts, float* u_right, float* depth_left, int cap, long long* ticket);
+mcv_status mcv_rig_wait(mcv_rig* r, long long ticket);
 /* Orders the rig's stream after all work enqueued so far by mcv_rig_process_async (no host wait). */
 mcv_status mcv_rig_join(mcv_rig* r);
 mcv_status mcv_rig_sync(mcv_rig* r);

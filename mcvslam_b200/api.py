@@ -29,7 +29,7 @@ EXPORTS = [
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
-    "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
+    "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
     "mcv_project_match", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
@@ -91,6 +91,8 @@ def lib():
         L.mcv_rig_extractor.restype = vp
         L.mcv_rig_process.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, vp, i, i]
         L.mcv_rig_process_async.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, i]
+        L.mcv_rig_submit.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, i, C.POINTER(C.c_longlong)]
+        L.mcv_rig_wait.argtypes = [vp, C.c_longlong]
         L.mcv_rig_sync.argtypes = [vp]
         L.mcv_rig_join.argtypes = [vp]
         L.mcv_rig_last_launches.argtypes = [vp]
@@ -398,6 +400,15 @@ class Rig:
 
     def process_async(self, imgs_ptr, n_frames, w, h, kps_ptr, desc_ptr, counts_ptr, ur_ptr, dp_ptr):
         _check(lib().mcv_rig_process_async(self._r, imgs_ptr, n_frames, w, h, kps_ptr, desc_ptr, counts_ptr, ur_ptr, dp_ptr, self.cap))
+
+    def submit(self, imgs_ptr, n_frames, w, h, kps_ptr, desc_ptr, counts_ptr, ur_ptr, dp_ptr):
+        """Enqueues one step on HOST (pinned) buffers — H2D, kernels, D2H — and returns a ticket for wait()."""
+        t = C.c_longlong(0)
+        _check(lib().mcv_rig_submit(self._r, imgs_ptr, n_frames, w, h, kps_ptr, desc_ptr, counts_ptr, ur_ptr, dp_ptr, self.cap, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        _check(lib().mcv_rig_wait(self._r, ticket))
 
     def join(self):
         """Orders the rig's stream after everything process_async has enqueued (no host wait)."""

@@ -736,6 +736,7 @@ mcv_status mcv_debug_popc_peak(int iters, double* popc_per_s, double* ms_out) {
 // the throughput-bound stencils of another (CUDA streams replace the reference's ThreadPool(3), src/Frame.cpp:22).
 // =========================================================================================================
 constexpr int RIG_SLOTS = 3;
+constexpr int RIG_TICKETS = 8;
 
 struct RigSlot {
     mcv_orb* orb = nullptr;
@@ -757,6 +758,9 @@ struct mcv_rig {
     int use_slots_dev = 1;          // device-resident path (env MCV_RIG_SLOTS_DEV): measured on B200, running whole batches
                                     // back to back on ONE stream beats overlapping them (28.8k vs 25.0k frames/s, profiles/)
     cudaEvent_t last_front = nullptr;   // front-half event of the most recently enqueued chunk
+    cudaEvent_t ticket[RIG_TICKETS] = {};   // completion of the last RIG_TICKETS mcv_rig_submit calls
+    long long submitted = 0;                // number of mcv_rig_submit calls so far (ticket ids start at 1)
+    int submit_chunk = 64;                  // frames per chunk of mcv_rig_submit (env MCV_RIG_SUBMIT_CHUNK)
     bool pending_join = false;
     int last_launches = 0;
 };
@@ -786,6 +790,49 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
     return MCV_OK;
 }
 
+// Host-buffer path: per chunk H2D -> kernels -> D2H on the slot's stream (all asynchronous), chunks rotating over the slots.
+static mcv_status rig_enqueue_host(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, int imgs_on_device, mcv_keypoint* kps_out,
+                                   uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device, int chunk) {
+    const size_t img3 = (size_t)3 * w * hgt, kb = sizeof(mcv_keypoint);
+    int launches = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        RigSlot& sl = r->slot[r->next_slot % r->use_slots];
+        r->next_slot = (r->next_slot + 1) % r->use_slots;
+        cudaStream_t s = sl.orb->stream;
+        const int nf = std::min(chunk, n_frames - f0);
+        const size_t n_img = (size_t)3 * nf;
+        mcv_status st;
+        const uint8_t* d_imgs = imgs + f0 * img3;
+        if (!imgs_on_device) {
+            if ((st = sl.imgs.reserve(img3 * nf))) return st;
+            MCV_CUDA(cudaMemcpyAsync(sl.imgs.p, imgs + f0 * img3, img3 * nf, cudaMemcpyHostToDevice, s));
+            d_imgs = sl.imgs.as<uint8_t>();
+        }
+        mcv_keypoint* d_kps = kps_out + (size_t)3 * f0 * cap; uint8_t* d_desc = desc_out + (size_t)3 * f0 * cap * 32;
+        int* d_counts = counts + 3 * f0; float* d_ur = u_right + (size_t)f0 * cap; float* d_dp = depth_left + (size_t)f0 * cap;
+        if (!out_on_device) {
+            if ((st = sl.kps.reserve(n_img * cap * kb))) return st;
+            if ((st = sl.desc.reserve(n_img * cap * 32))) return st;
+            if ((st = sl.counts.reserve(n_img * 4))) return st;
+            if ((st = sl.u_right.reserve((size_t)nf * cap * 4))) return st;
+            if ((st = sl.depth.reserve((size_t)nf * cap * 4))) return st;
+            d_kps = sl.kps.as<mcv_keypoint>(); d_desc = sl.desc.as<uint8_t>(); d_counts = sl.counts.as<int>();
+            d_ur = sl.u_right.as<float>(); d_dp = sl.depth.as<float>();
+        }
+        st = rig_chunk(r, sl, d_imgs, nf, w, hgt, d_kps, d_desc, d_counts, d_ur, d_dp, cap, &launches);
+        if (st) return st;
+        if (!out_on_device) {
+            MCV_CUDA(cudaMemcpyAsync(kps_out + (size_t)3 * f0 * cap, d_kps, n_img * cap * kb, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(desc_out + (size_t)3 * f0 * cap * 32, d_desc, n_img * cap * 32, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(counts + 3 * f0, d_counts, n_img * 4, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(u_right + (size_t)f0 * cap, d_ur, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
+            MCV_CUDA(cudaMemcpyAsync(depth_left + (size_t)f0 * cap, d_dp, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    r->last_launches = launches;
+    return MCV_OK;
+}
+
 static inline int rig_chunk_size(const mcv_rig* r, int n_frames) {
     // profiling measures whole-batch kernels on one stream; otherwise chunk so that all slots get work
     if (r->slot[0].orb->profile || r->chunk_frames <= 0) return n_frames;
@@ -811,6 +858,7 @@ mcv_status mcv_rig_create(const mcv_rig_params* p, int device, void* stream, mcv
     else { cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking); r->own_stream = true; }
     if (const char* e = getenv("MCV_RIG_CHUNK")) r->chunk_frames = atoi(e);
     if (const char* e = getenv("MCV_RIG_CHUNK_DEV")) r->chunk_frames_dev = atoi(e);
+    if (const char* e = getenv("MCV_RIG_SUBMIT_CHUNK")) r->submit_chunk = atoi(e);
     if (const char* e = getenv("MCV_RIG_SLOTS")) r->use_slots = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     if (const char* e = getenv("MCV_RIG_SLOTS_DEV")) r->use_slots_dev = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     *out = r;
@@ -829,6 +877,7 @@ void mcv_rig_destroy(mcv_rig* r) {
         mcv_orb_destroy(sl.orb);
     }
     if (r->fork) cudaEventDestroy(r->fork);
+    for (cudaEvent_t e : r->ticket) if (e) cudaEventDestroy(e);
     if (r->own_stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -930,46 +979,41 @@ mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w,
         return mcv_rig_sync(r);
     }
     // host side involved: per-chunk H2D -> kernels -> D2H on the slot's stream, chunks overlapping across slots
-    const int chunk = rig_chunk_size(r, n_frames);
-    const size_t img3 = (size_t)3 * w * hgt, kb = sizeof(mcv_keypoint);
-    int launches = 0;
     MCV_CUDA(cudaStreamSynchronize(r->stream));
-    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
-        RigSlot& sl = r->slot[r->next_slot % r->use_slots];
-        r->next_slot = (r->next_slot + 1) % r->use_slots;
-        cudaStream_t s = sl.orb->stream;
-        const int nf = std::min(chunk, n_frames - f0);
-        const size_t n_img = (size_t)3 * nf;
-        mcv_status st;
-        const uint8_t* d_imgs = imgs + f0 * img3;
-        if (!imgs_on_device) {
-            if ((st = sl.imgs.reserve(img3 * nf))) return st;
-            MCV_CUDA(cudaMemcpyAsync(sl.imgs.p, imgs + f0 * img3, img3 * nf, cudaMemcpyHostToDevice, s));
-            d_imgs = sl.imgs.as<uint8_t>();
-        }
-        mcv_keypoint* d_kps = kps_out + (size_t)3 * f0 * cap; uint8_t* d_desc = desc_out + (size_t)3 * f0 * cap * 32;
-        int* d_counts = counts + 3 * f0; float* d_ur = u_right + (size_t)f0 * cap; float* d_dp = depth_left + (size_t)f0 * cap;
-        if (!out_on_device) {
-            if ((st = sl.kps.reserve(n_img * cap * kb))) return st;
-            if ((st = sl.desc.reserve(n_img * cap * 32))) return st;
-            if ((st = sl.counts.reserve(n_img * 4))) return st;
-            if ((st = sl.u_right.reserve((size_t)nf * cap * 4))) return st;
-            if ((st = sl.depth.reserve((size_t)nf * cap * 4))) return st;
-            d_kps = sl.kps.as<mcv_keypoint>(); d_desc = sl.desc.as<uint8_t>(); d_counts = sl.counts.as<int>();
-            d_ur = sl.u_right.as<float>(); d_dp = sl.depth.as<float>();
-        }
-        st = rig_chunk(r, sl, d_imgs, nf, w, hgt, d_kps, d_desc, d_counts, d_ur, d_dp, cap, &launches);
-        if (st) return st;
-        if (!out_on_device) {
-            MCV_CUDA(cudaMemcpyAsync(kps_out + (size_t)3 * f0 * cap, d_kps, n_img * cap * kb, cudaMemcpyDeviceToHost, s));
-            MCV_CUDA(cudaMemcpyAsync(desc_out + (size_t)3 * f0 * cap * 32, d_desc, n_img * cap * 32, cudaMemcpyDeviceToHost, s));
-            MCV_CUDA(cudaMemcpyAsync(counts + 3 * f0, d_counts, n_img * 4, cudaMemcpyDeviceToHost, s));
-            MCV_CUDA(cudaMemcpyAsync(u_right + (size_t)f0 * cap, d_ur, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
-            MCV_CUDA(cudaMemcpyAsync(depth_left + (size_t)f0 * cap, d_dp, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
-        }
-    }
+    mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, imgs_on_device, kps_out, desc_out, counts, u_right, depth_left, cap,
+                                     out_on_device, rig_chunk_size(r, n_frames));
+    if (st) return st;
     for (RigSlot& sl : r->slot) MCV_CUDA(cudaStreamSynchronize(sl.orb->stream));
-    r->last_launches = launches;
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_submit(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, mcv_keypoint* kps_out, uint8_t* desc_out,
+                          int32_t* counts, float* u_right, float* depth_left, int cap, long long* ticket) {
+    if (!r || !imgs || n_frames <= 0 || !kps_out || !desc_out || !counts || !u_right || !depth_left) return MCV_ERR_BAD_ARG;
+    if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
+    if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
+    MCV_CUDA(cudaSetDevice(r->device));
+    const int chunk = r->slot[0].orb->profile || r->submit_chunk <= 0 ? n_frames : std::min(n_frames, r->submit_chunk);
+    mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, 0, kps_out, desc_out, counts, u_right, depth_left, cap, 0, chunk);
+    if (st) return st;
+    // completion = every slot's stream has drained what this call put on it
+    const long long id = ++r->submitted;
+    cudaEvent_t& ev = r->ticket[id % RIG_TICKETS];
+    if (!ev) MCV_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (RigSlot& sl : r->slot) {
+        MCV_CUDA(cudaEventRecord(sl.done, sl.orb->stream));
+        MCV_CUDA(cudaStreamWaitEvent(r->stream, sl.done, 0));
+    }
+    MCV_CUDA(cudaEventRecord(ev, r->stream));
+    if (ticket) *ticket = id;
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_wait(mcv_rig* r, long long ticket) {
+    if (!r || ticket <= 0 || ticket > r->submitted) return MCV_ERR_BAD_ARG;
+    if (r->submitted - ticket >= RIG_TICKETS) return MCV_OK;   // older than the ring: completed before a later ticket was recorded over it
+    MCV_CUDA(cudaSetDevice(r->device));
+    MCV_CUDA(cudaEventSynchronize(r->ticket[ticket % RIG_TICKETS]));
     return MCV_OK;
 }
 

@@ -125,3 +125,39 @@ def test_c5_one_million_by_one_million(api, oracle):
     tn = t_cpu.numpy()
     ref, k = oracle.knn2_bf(tn[rows], tn)
     assert np.array_equal(idx[rows], ref["trainIdx"]) and np.array_equal(dst[rows], ref["distance"].astype(np.int32))
+
+
+@pytest.mark.gpu
+def test_rig_submit_wait_matches_sync_call(api):
+    """mcv_rig_submit / mcv_rig_wait (asynchronous host-buffer steps, several in flight) returns what the synchronous
+    mcv_rig_process returns for the same triplets."""
+    import torch
+    from mcvslam_b200 import synth
+    frames = np.stack([synth.triplet(300 + s) for s in range(6)])
+    rig = api.Rig(device=0)
+    ref = rig.process(frames)
+    cap = rig.cap
+    n = len(frames)
+    h_img = torch.from_numpy(frames).pin_memory()
+    outs, tickets = [], []
+    for k in range(5):   # more submits than slots, each on its own result buffers, all in flight at once
+        o = dict(kps=torch.zeros(n * 3 * cap * 28, dtype=torch.uint8).pin_memory(), desc=torch.zeros(n * 3 * cap * 32, dtype=torch.uint8).pin_memory(),
+                 cnt=torch.zeros(n * 3, dtype=torch.int32).pin_memory(), ur=torch.zeros(n * cap, dtype=torch.float32).pin_memory(),
+                 dp=torch.zeros(n * cap, dtype=torch.float32).pin_memory())
+        outs.append(o)
+        tickets.append(rig.submit(h_img.data_ptr(), n, 640, 480, o["kps"].data_ptr(), o["desc"].data_ptr(), o["cnt"].data_ptr(), o["ur"].data_ptr(),
+                                  o["dp"].data_ptr()))
+    for k in reversed(range(5)):
+        rig.wait(tickets[k])
+        o = outs[k]
+        cnt = o["cnt"].numpy().reshape(n, 3)
+        assert np.array_equal(cnt, ref["counts"])
+        kps = o["kps"].numpy().reshape(n, 3, cap, 28); desc = o["desc"].numpy().reshape(n, 3, cap, 32)
+        for f in range(n):
+            for c in range(3):
+                m = cnt[f, c]
+                assert kps[f, c, :m].tobytes() == ref["kps"][f, c, :m].tobytes()
+                assert desc[f, c, :m].tobytes() == ref["desc"][f, c, :m].tobytes()
+            m = cnt[f, 0]
+            assert np.array_equal(o["ur"].numpy().reshape(n, cap)[f, :m].view(np.uint32), ref["u_right"][f, :m].view(np.uint32))
+    rig.close()
