@@ -42,7 +42,8 @@ PYR_BYTES_PER_IMAGE = 950532          # all 8 levels
 STAGE_BYTES_PER_IMAGE = {
     "pyramid": 307200 + 950532,                 # read input, write 8 levels
     "blur": 2 * 950532,                         # read pyramid, write smoothed pyramid
-    "fast_cells": 950532 + 4 * 6500,            # read pyramid, write ~6.5k packed candidates
+    "fast_score": 2 * 950532,                   # read pyramid, write the score map
+    "nms_cells": 950532 + 4 * 6500,             # read score map, write ~6.5k packed candidates
     "quadtree": 2 * 4 * 6500 + 4 * 2000,        # read candidates, write them ordered, write 2000 selected
     "orient_desc": 2000 * (31 * 31 + 37 * 37 + 60),  # per keypoint: intensity patch + smoothed patch + 60 B out
     "stereo_match": (2 * 2000 * 60 + 2000 * 16) / 3.0,   # per frame / 3 images
@@ -329,9 +330,17 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         dom = max(stage_ms, key=stage_ms.get)
         dom_ms = stage_ms[dom] / max(1, n_calls)
-        launches_per_call = 8 if dom == "pyramid" else 1
+        launches_per_call = {"pyramid": 8, "nms_cells": 2, "quadtree": 2}.get(dom, 1)
         dom_bytes = STAGE_BYTES_PER_IMAGE[dom] * 3 * B
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes of the same kernel from the committed ncu --set full capture, scaled to this launch's images
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["per_image"][dom] * 3 * B
+        except Exception:
+            pass
+        kernel_names = {"pyramid": "k_copy_level0 + 7 x k_resize_march", "blur": "k_gauss7", "fast_score": "k_fast_score",
+                        "nms_cells": "k_nms_sparse + k_cell_order", "quadtree": "k_octree_sorted", "orient_desc": "k_orient_desc",
+                        "stereo_match": "k_stereo_rows + k_stereo_match", "stereo_median": "k_stereo_median"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -346,8 +355,8 @@ def main():
                                                 "step's H2D and D2H inside the region",
                     "sync_call_value": e2e_sync_v, "sync_call_how": "one synchronous mcv_rig_process call per step (%d steps)" % e2e_steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "launches_per_step": launches_per_call,
+            "roofline": {"bound": "hbm", "kernel": kernel_names.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, per launch)", "peak_source": peak_src, "launches_per_step": launches_per_call,
                          "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms,
                          "whole_path_frac": (ALGO_BYTES_PER_FRAME * value / world) / 1e9 / peak},
             "stage_ms_per_step": {k: v / max(1, n_calls) for k, v in stage_ms.items()},

@@ -205,8 +205,8 @@ mcv_status mcv_rig_sync(mcv_rig* r);
 int mcv_rig_last_launches(const mcv_rig* r);
 /* Per-stage device timing (the reference brackets the same stages with MyTimer "ORBE"/"SMatch", src/Frame.cpp:119,135).
  * When on, CUDA events are recorded between the stages of every process call on the rig's stream (no extra
- * synchronisation). mcv_rig_stage_ms synchronises and returns the summed milliseconds of the 7 stages — pyramid, blur,
- * fast_cells, quadtree, orient_desc, stereo_match, stereo_median — over the calls since profiling was switched on. */
+ * synchronisation). mcv_rig_stage_ms synchronises and returns the summed milliseconds of the 8 stages — pyramid, blur,
+ * fast_score, nms_cells, quadtree, orient_desc, stereo_match, stereo_median — over the calls since profiling was switched on. */
 mcv_status mcv_rig_set_profiling(mcv_rig* r, int on);
 mcv_status mcv_rig_stage_ms(mcv_rig* r, float* total_ms, int n_stages, int* n_calls);
 

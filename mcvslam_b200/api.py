@@ -423,7 +423,7 @@ class Rig:
     def last_launches(self):
         return lib().mcv_rig_last_launches(self._r)
 
-    STAGES = ("pyramid", "blur", "fast_cells", "quadtree", "orient_desc", "stereo_match", "stereo_median")
+    STAGES = ("pyramid", "blur", "fast_score", "nms_cells", "quadtree", "orient_desc", "stereo_match", "stereo_median")
 
     def set_profiling(self, on):
         _check(lib().mcv_rig_set_profiling(self._r, int(on)))

@@ -80,7 +80,7 @@ struct mcv_orb {
     int prof_calls = 0;
 };
 
-constexpr int N_STAGES = 7;   // pyramid, blur, fast_cells, quadtree, orient_desc, stereo_match, stereo_median
+constexpr int N_STAGES = 8;   // pyramid, blur, fast_score, nms_cells, quadtree, orient_desc, stereo_match, stereo_median
 constexpr int PROF_RING = 512;
 static inline void prof_mark(mcv_orb* h, int stage_boundary) {
     if (h->profile && h->prof_calls < PROF_RING) cudaEventRecord(h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + stage_boundary], h->stream);
@@ -253,17 +253,18 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
     prof_mark(h, 2);
     n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->nz_list.as<unsigned>(), h->nz_cnt.as<int>(), h->cell_raw.as<uint32_t>(),
-                           h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream);
+                           h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream,
+                           (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 3] : nullptr);
     if (signal_front) MCV_CUDA(cudaEventRecord(signal_front, h->stream));
-    prof_mark(h, 3);
+    prof_mark(h, 4);
     const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
                                 h->oct_idx.as<uint16_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
     if (r < 0) { set_error("nfeatures too large for the quadtree kernel's shared-memory heap"); return MCV_ERR_CAPACITY; }
     n += r;
-    prof_mark(h, 4);
+    prof_mark(h, 5);
     n += launch_orient_desc(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), seeds, d_kps,
                             d_desc, d_counts, cap, n_images, h->stream);
-    prof_mark(h, 5);
+    prof_mark(h, 6);
     MCV_CUDA(cudaGetLastError());
     h->last_images = n_images; h->last_cap = cap; h->last_launches = n;
     return MCV_OK;
@@ -780,10 +781,10 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
     if (st) return st;
     r->last_front = sl.front;
     int n = h->last_launches;
-    cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 6] : nullptr;
+    cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 7] : nullptr;
     n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
                        d_depth, sl.best_dist.as<int>(), nullptr, sl.st_scratch.p, h->stream, mid);
-    prof_mark(h, 7);
+    prof_mark(h, 8);
     if (h->profile && h->prof_calls < PROF_RING) ++h->prof_calls;
     MCV_CUDA(cudaGetLastError());
     *launches += n;

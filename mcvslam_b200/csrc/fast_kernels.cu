@@ -335,14 +335,15 @@ int fast_strip_table(const Plan& P, StripTable& T) {
 }
 
 int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
-                      uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s) {
+                      uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s, cudaEvent_t after_score) {
     StripTable T{};
     const int n = fast_strip_table(P, T);
     cudaMemsetAsync(d_cell_cnt, 0, (size_t)n_images * P.cells_per_image * sizeof(int), s);
-    if (n > 0) {
+    if (n > 0)
         k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_score, d_nz_list, d_nz_cnt, P, T);
+    if (after_score) cudaEventRecord(after_score, s);   // stage boundary for mcv_rig_stage_ms
+    if (n > 0)
         k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(d_score, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
-    }
     k_cell_order<<<dim3((P.cells_per_image + ORD_WARPS - 1) / ORD_WARPS, n_images), 32 * ORD_WARPS, 0, s>>>(d_cell_raw, d_cell_pts, d_cell_cnt, P);
     return 3;
 }
