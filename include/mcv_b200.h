@@ -167,6 +167,12 @@ typedef struct mcv_rig_params {
 } mcv_rig_params;
 
 mcv_status mcv_rig_create(const mcv_rig_params* params, int device, void* stream, mcv_rig** out);
+/* Input pixel format of every later extract / process / submit call on the handle: 1 = CV_8UC1 gray (default, what
+ * BaseExtractor::Extract asserts, ORBextractor.cc:837), 3 = CV_8UC3 interleaved BGR as the capture delivers it — then
+ * System::Track's cv::cvtColor(COLOR_BGR2GRAY) (src/System.cpp:60-64) runs on the device, fused into the level-0 write of the
+ * pyramid (bit-exact to OpenCV's fixed-point path), and image sizes / strides are in bytes of the 3-channel rows. */
+mcv_status mcv_rig_set_input_channels(mcv_rig* r, int channels);
+mcv_status mcv_orb_set_input_channels(mcv_orb* h, int channels);
 void mcv_rig_destroy(mcv_rig* r);
 int mcv_rig_max_keypoints(const mcv_rig* r);
 /* The extractor of slot 0 (image index = 3*frame + cam within the chunk it processed last; cam 0=L,1=R,2=W). The whole batch

@@ -29,7 +29,7 @@ EXPORTS = [
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
-    "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
+    "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_set_input_channels", "mcv_orb_set_input_channels", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
     "mcv_project_match", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
@@ -93,6 +93,8 @@ def lib():
         L.mcv_rig_process_async.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, i]
         L.mcv_rig_submit.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, i, C.POINTER(C.c_longlong)]
         L.mcv_rig_wait.argtypes = [vp, C.c_longlong]
+        L.mcv_rig_set_input_channels.argtypes = [vp, i]
+        L.mcv_orb_set_input_channels.argtypes = [vp, i]
         L.mcv_rig_sync.argtypes = [vp]
         L.mcv_rig_join.argtypes = [vp]
         L.mcv_rig_last_launches.argtypes = [vp]
@@ -179,9 +181,15 @@ class ORB:
         reference). Returns (count, kps, desps); count is -1 for an empty image (ORBextractor.cc:834)."""
         if img is None or img.size == 0:
             return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
-        assert img.dtype == np.uint8 and img.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:837)"
-        if img.strides[1] != 1:
+        if img.ndim == 3:   # CV_8UC3 BGR: System::Track's cvtColor (src/System.cpp:60-64) runs on the device
+            assert img.dtype == np.uint8 and img.shape[2] == 3
             img = np.ascontiguousarray(img)
+            _check(lib().mcv_orb_set_input_channels(self._h, 3))
+        else:
+            assert img.dtype == np.uint8 and img.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:837)"
+            _check(lib().mcv_orb_set_input_channels(self._h, 1))
+            if img.strides[1] != 1:
+                img = np.ascontiguousarray(img)
         seeds = None if kps is None or len(kps) == 0 else np.ascontiguousarray(kps, KP_DTYPE)
         ns = 0 if seeds is None else len(seeds)
         cap = self.max_keypoints(ns)
@@ -381,10 +389,15 @@ class Rig:
         except Exception:
             pass
 
+    def set_input_channels(self, channels):
+        """1 = gray (default), 3 = interleaved BGR: System::Track's cvtColor(BGR2GRAY) (src/System.cpp:60-64) runs on the device."""
+        _check(lib().mcv_rig_set_input_channels(self._r, int(channels)))
+
     def process(self, imgs):
-        """imgs: (n_frames, 3, H, W) u8 host array. Returns dict of host arrays (kps, desc, counts, u_right, depth_left)."""
+        """imgs: (n_frames, 3, H, W) u8 host array — or (n_frames, 3, H, W, 3) BGR after set_input_channels(3).
+        Returns dict of host arrays (kps, desc, counts, u_right, depth_left)."""
         imgs = _u8(imgs)
-        n, three, h, w = imgs.shape
+        n, three, h, w = imgs.shape[:4]
         assert three == 3
         cap = self.cap
         out = dict(kps=np.zeros((n, 3, cap), KP_DTYPE), desc=np.zeros((n, 3, cap, 32), np.uint8), counts=np.zeros((n, 3), np.int32),

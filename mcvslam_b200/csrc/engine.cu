@@ -73,6 +73,7 @@ struct mcv_orb {
     DevBuf tabs, src, pyr, blur, score, nz_list, nz_cnt, cell_raw, cell_pts, cell_cnt, arena_a, arena_b, oct_idx, out_pts, out_cnt, kps, desc, counts, seeds, misc;
     HostBuf h_stage;
     int last_cap = 0;       // per-image keypoint slots of the last extract (layout of kps/desc)
+    int channels = 1;       // input images: 1 = CV_8UC1 gray, 3 = CV_8UC3 BGR (cvtColor fused into the level-0 write)
     int last_launches = 0;
     // optional per-stage timing: CUDA events recorded between the stages of every call (no synchronisation added)
     bool profile = false;
@@ -248,7 +249,7 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     int n = 0;
     if (wait_front) MCV_CUDA(cudaStreamWaitEvent(h->stream, wait_front, 0));
     prof_mark(h, 0);
-    n += launch_pyramid(P, d_imgs, src_pitch, src_image_stride, h->pyr.as<uint8_t>(), h->tabs.as<int>(), n_images, h->stream);
+    n += launch_pyramid(P, d_imgs, src_pitch, src_image_stride, h->channels, h->pyr.as<uint8_t>(), h->tabs.as<int>(), n_images, h->stream);
     prof_mark(h, 1);
     n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
     prof_mark(h, 2);
@@ -336,7 +337,8 @@ mcv_status mcv_orb_extract(mcv_orb* h, const uint8_t* img, int w, int hgt, size_
     if (!h || !n_out) return MCV_ERR_BAD_ARG;
     *n_out = 0;
     if (!img || w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;  // ORBextractor.cc:834
-    if (stride < (size_t)w || n_seeds < 0 || (n_seeds > 0 && !seeds) || !kps_out || !desc_out) return MCV_ERR_BAD_ARG;
+    const size_t row_bytes = (size_t)w * h->channels;
+    if (stride < row_bytes || n_seeds < 0 || (n_seeds > 0 && !seeds) || !kps_out || !desc_out) return MCV_ERR_BAD_ARG;
     MCV_CUDA(cudaSetDevice(h->device));
     mcv_status st = ensure_workspace(h, w, hgt, 1, std::max(cap, 1));
     if (st) return st;
@@ -358,9 +360,9 @@ mcv_status mcv_orb_extract(mcv_orb* h, const uint8_t* img, int w, int hgt, size_
         MCV_CUDA(cudaMemcpyAsync(h->seeds.p, seeds, (size_t)n_seeds * sizeof(mcv_keypoint), cudaMemcpyHostToDevice, h->stream));
         si.d_seeds = h->seeds.as<mcv_keypoint>(); si.n_seeds = n_seeds;
     }
-    if ((st = h->src.reserve((size_t)w * hgt))) return st;
-    MCV_CUDA(cudaMemcpy2DAsync(h->src.p, w, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
-    st = enqueue_extract(h, h->src.as<uint8_t>(), w, (size_t)w * hgt, 1, n_seeds ? &si : nullptr, h->kps.as<mcv_keypoint>(),
+    if ((st = h->src.reserve(row_bytes * hgt))) return st;
+    MCV_CUDA(cudaMemcpy2DAsync(h->src.p, row_bytes, img, stride, row_bytes, hgt, cudaMemcpyHostToDevice, h->stream));
+    st = enqueue_extract(h, h->src.as<uint8_t>(), row_bytes, row_bytes * hgt, 1, n_seeds ? &si : nullptr, h->kps.as<mcv_keypoint>(),
                          h->desc.as<uint8_t>(), h->counts.as<int>(), cap);
     if (st) return st;
     int n = 0;
@@ -385,7 +387,7 @@ mcv_status mcv_orb_extract_batch(mcv_orb* h, const uint8_t* imgs, int n_images, 
     if (st) return st;
     if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_orb_max_keypoints()"); return MCV_ERR_CAPACITY; }
     const uint8_t* d_imgs = imgs;
-    const size_t img_bytes = (size_t)w * hgt;
+    const size_t img_bytes = (size_t)w * hgt * h->channels;
     if (!imgs_on_device) {
         if ((st = h->src.reserve(img_bytes * n_images))) return st;
         MCV_CUDA(cudaMemcpyAsync(h->src.p, imgs, img_bytes * n_images, cudaMemcpyHostToDevice, h->stream));
@@ -394,7 +396,7 @@ mcv_status mcv_orb_extract_batch(mcv_orb* h, const uint8_t* imgs, int n_images, 
     mcv_keypoint* d_kps = out_on_device ? kps_out : h->kps.as<mcv_keypoint>();
     uint8_t* d_desc = out_on_device ? desc_out : h->desc.as<uint8_t>();
     int* d_counts = out_on_device ? counts : h->counts.as<int>();
-    st = enqueue_extract(h, d_imgs, w, img_bytes, n_images, nullptr, d_kps, d_desc, d_counts, cap);
+    st = enqueue_extract(h, d_imgs, (size_t)w * h->channels, img_bytes, n_images, nullptr, d_kps, d_desc, d_counts, cap);
     if (st) return st;
     if (!out_on_device) {
         MCV_CUDA(cudaMemcpyAsync(kps_out, d_kps, (size_t)cap * n_images * sizeof(mcv_keypoint), cudaMemcpyDeviceToHost, h->stream));
@@ -776,7 +778,7 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
     if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints()"); return MCV_ERR_CAPACITY; }
     if ((st = sl.best_dist.reserve((size_t)n_frames * cap * 4))) return st;
     if ((st = sl.st_scratch.reserve(stereo_scratch_bytes(h->plan, n_frames, cap)))) return st;
-    st = enqueue_extract(h, d_imgs, w, (size_t)w * hgt, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap,
+    st = enqueue_extract(h, d_imgs, (size_t)w * h->channels, (size_t)w * hgt * h->channels, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap,
                          stagger && r->last_front != sl.front ? r->last_front : nullptr, sl.front);
     if (st) return st;
     r->last_front = sl.front;
@@ -794,7 +796,7 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
 // Host-buffer path: per chunk H2D -> kernels -> D2H on the slot's stream (all asynchronous), chunks rotating over the slots.
 static mcv_status rig_enqueue_host(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, int imgs_on_device, mcv_keypoint* kps_out,
                                    uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device, int chunk) {
-    const size_t img3 = (size_t)3 * w * hgt, kb = sizeof(mcv_keypoint);
+    const size_t img3 = (size_t)3 * w * hgt * r->slot[0].orb->channels, kb = sizeof(mcv_keypoint);
     int launches = 0;
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         RigSlot& sl = r->slot[r->next_slot % r->use_slots];
@@ -892,6 +894,20 @@ mcv_status mcv_rig_set_chunk_frames(mcv_rig* r, int chunk_frames) {
     return MCV_OK;
 }
 
+mcv_status mcv_orb_set_input_channels(mcv_orb* h, int channels) {
+    if (!h || (channels != 1 && channels != 3)) return MCV_ERR_BAD_ARG;
+    h->channels = channels;
+    return MCV_OK;
+}
+
+mcv_status mcv_rig_set_input_channels(mcv_rig* r, int channels) {
+    if (!r || (channels != 1 && channels != 3)) return MCV_ERR_BAD_ARG;
+    mcv_status st = mcv_rig_sync(r);
+    if (st) return st;
+    for (RigSlot& sl : r->slot) sl.orb->channels = channels;
+    return MCV_OK;
+}
+
 mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps, uint8_t* d_desc,
                                  int32_t* d_counts, float* d_u_right, float* d_depth, int cap) {
     if (!r || !d_imgs || n_frames <= 0 || !d_kps || !d_desc || !d_counts || !d_u_right || !d_depth) return MCV_ERR_BAD_ARG;
@@ -903,7 +919,7 @@ mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames
     // what is already on the rig's stream (fork); the rig's stream is ordered after the results only by mcv_rig_join.
     const bool profiling = r->slot[0].orb->profile;
     const int chunk = profiling || r->chunk_frames_dev <= 0 ? n_frames : std::min(n_frames, r->chunk_frames_dev);
-    const size_t img3 = (size_t)3 * w * hgt;
+    const size_t img3 = (size_t)3 * w * hgt * r->slot[0].orb->channels;
     int launches = 0;
     MCV_CUDA(cudaEventRecord(r->fork, r->stream));
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {

@@ -79,7 +79,7 @@ void set_error(const std::string& s);
     } while (0)
 
 // ---- kernel launchers (each returns the number of kernels it enqueued) ----
-int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, uint8_t* d_pyr,
+int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, int src_channels, uint8_t* d_pyr,
                    const int* d_tabs, int n_images, cudaStream_t s);
 int launch_blur(const Plan& P, const uint8_t* d_pyr, uint8_t* d_blur, int n_images, cudaStream_t s);
 int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,

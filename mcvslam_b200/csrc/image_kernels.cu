@@ -29,6 +29,36 @@ __global__ void __launch_bounds__(256) k_copy_level0(const uint8_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// level 0 from an interleaved BGR image: cv::cvtColor(COLOR_BGR2GRAY) of System::Track (src/System.cpp:60-64) fused into
+// the level-0 write. OpenCV's 8-bit path is fixed point: (B * 3735 + G * 19235 + R * 9798 + (1 << 14)) >> 15 (pinned against
+// cv2 4.13, tests/golden/bgr_golden.npz). 4 pixels per thread: three aligned 32-bit loads, one 32-bit store.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned bgr_gray(unsigned b, unsigned g, unsigned r) { return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15; }
+
+__global__ void __launch_bounds__(256) k_gray_level0(const uint8_t* __restrict__ src, size_t src_pitch, size_t src_image_stride,
+                                                     uint8_t* __restrict__ pyr, int pyr_bytes, int w, int h, int pitch) {
+    const int img = blockIdx.z;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= h) return;
+    const uint8_t* s = src + (size_t)img * src_image_stride + (size_t)y * src_pitch;
+    uint8_t* d = pyr + (size_t)img * pyr_bytes + (size_t)y * pitch;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x0 >= w) return;
+    const uint8_t* p = s + 3 * (size_t)x0;
+    if (x0 + 4 <= w && ((reinterpret_cast<uintptr_t>(p) & 3) == 0)) {
+        const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(p)), w1 = __ldg(reinterpret_cast<const unsigned*>(p + 4)),
+                       w2 = __ldg(reinterpret_cast<const unsigned*>(p + 8));   // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+        const unsigned g0 = bgr_gray(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
+        const unsigned g1 = bgr_gray(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
+        const unsigned g2 = bgr_gray((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
+        const unsigned g3 = bgr_gray((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
+        *reinterpret_cast<unsigned*>(d + x0) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);   // level rows are 16-byte aligned
+    } else {
+        for (int x = x0; x < min(x0 + 4, w); ++x) d[x] = (uint8_t)bgr_gray(s[3 * x], s[3 * x + 1], s[3 * x + 2]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // bilinear resize, 4 output pixels per thread. Tables (host-built, per level): xofs[dw], xa0[dw], xa1[dw], yofs[dh], yb0[dh], yb1[dh]
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_resize_level(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
@@ -203,13 +233,18 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restr
     }
 }
 
-int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, uint8_t* d_pyr, const int* d_tabs,
-                   int n_images, cudaStream_t s) {
+int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, int src_channels, uint8_t* d_pyr,
+                   const int* d_tabs, int n_images, cudaStream_t s) {
     int launches = 0;
     {
         const LevelGeom& g = P.lv[0];
-        dim3 b(32, 8), grid((g.w + 16 * 32 - 1) / (16 * 32), (g.h + 7) / 8, n_images);
-        k_copy_level0<<<grid, b, 0, s>>>(d_src, src_pitch, src_image_stride, d_pyr, P.pyr_bytes, g.w, g.h, g.pitch);
+        if (src_channels == 3) {
+            dim3 b(32, 8), grid((g.w + 4 * 32 - 1) / (4 * 32), (g.h + 7) / 8, n_images);
+            k_gray_level0<<<grid, b, 0, s>>>(d_src, src_pitch, src_image_stride, d_pyr, P.pyr_bytes, g.w, g.h, g.pitch);
+        } else {
+            dim3 b(32, 8), grid((g.w + 16 * 32 - 1) / (16 * 32), (g.h + 7) / 8, n_images);
+            k_copy_level0<<<grid, b, 0, s>>>(d_src, src_pitch, src_image_stride, d_pyr, P.pyr_bytes, g.w, g.h, g.pitch);
+        }
         ++launches;
     }
     for (int l = 1; l < P.n_levels; ++l) {

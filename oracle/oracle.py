@@ -48,6 +48,7 @@ def lib():
         L.ora_distribute_octree.argtypes = [vp, i, i, i, i, i, i, vp, i]
         L.ora_resize_linear_u8.argtypes = [vp, i, i, i, vp, i, i, i]
         L.ora_gauss7_u8.argtypes = [vp, i, i, i, vp, i]
+        L.ora_bgr2gray_u8.argtypes = [vp, i, i, i, vp, i]
         L.ora_fast_atan2.restype = f
         L.ora_fast_atan2.argtypes = [f, f]
         L.ora_fast_atan2_array.argtypes = [vp, vp, vp, i]
@@ -83,6 +84,16 @@ def resize_linear(img, dw, dh):
     img = _u8(img)
     out = np.empty((dh, dw), np.uint8)
     lib().ora_resize_linear_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, dw)
+    return out
+
+
+def bgr2gray(img):
+    """cv::cvtColor(COLOR_BGR2GRAY), System::Track (src/System.cpp:60-64)."""
+    img = _u8(img)
+    h, w, c = img.shape
+    assert c == 3
+    out = np.empty((h, w), np.uint8)
+    lib().ora_bgr2gray_u8(_p(img), w, h, img.strides[0], _p(out), out.strides[0])
     return out
 
 

@@ -478,6 +478,15 @@ extern "C" {
 void ora_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride) {
     resize_linear_u8(Img{src, sw, sh, (size_t)sstride}, dst, dw, dh, dstride);
 }
+// cv::cvtColor(COLOR_BGR2GRAY) on CV_8UC3 as called by System::Track (src/System.cpp:60-64). OpenCV's 8-bit path is fixed
+// point with 15 fractional bits: B2Y = 3735, G2Y = 19235, R2Y = 9798, rounded (pinned against cv2 4.13: tests/golden/bgr_golden.npz).
+void ora_bgr2gray_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* s = src + (size_t)y * sstride;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x) d[x] = (uint8_t)((s[3 * x] * 3735 + s[3 * x + 1] * 19235 + s[3 * x + 2] * 9798 + (1 << 14)) >> 15);
+    }
+}
 void ora_gauss7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
     gauss7_u8(Img{src, w, h, (size_t)sstride}, dst, dstride);
 }

@@ -118,3 +118,50 @@ def test_distribute_octree_static(api, oracle):
         b = oracle.distribute_octree(k, 16, 16 + bw, 16, 16 + bh, N)
         assert len(a) == len(b)
         assert (a["x"] == b["x"]).all() and (a["y"] == b["y"]).all() and (a["response"] == b["response"]).all()
+
+
+@pytest.mark.gpu
+def test_bgr_ingest_matches_cv2_fixture_and_gray_path(api, oracle):
+    """CV_8UC3 input: cvtColor(BGR2GRAY) fused into the level-0 write (src/System.cpp:60-64). Level 0 must equal the real
+    cv2 output (committed fixture), and the whole extraction must equal the gray-input path on the converted image."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bgr_golden.npz"))
+    E1 = api.ORB(500, 1.2, 1, 28, 15)
+    for name in ("rand", "sweep", "scene"):
+        reps = 2 if name == "rand" else 1      # the 61-row fixture is lower than one FAST cell: stack it (the conversion is per pixel)
+        E1.Extract(np.tile(g[name + "_bgr"], (reps, 1, 1)))
+        assert np.array_equal(E1.mvImagePyramid(0), np.tile(g[name + "_gray"], (reps, 1))), name
+    # unaligned rows / sub-views: a BGR image cropped so that the row start is not 4-byte aligned
+    crop = np.ascontiguousarray(g["scene_bgr"][:, 1:158])
+    E1.Extract(crop)
+    assert np.array_equal(E1.mvImagePyramid(0), oracle.bgr2gray(crop))
+    # full path at the benchmark geometry
+    from mcvslam_b200 import synth
+    rng = np.random.default_rng(3)
+    gray = synth.scene(77)
+    tint = rng.integers(-20, 21, (480, 640, 3))
+    bgr = np.clip(gray[..., None].astype(np.int64) + tint, 0, 255).astype(np.uint8)
+    E = api.ORB(2000, 1.2, 8, 28, 15)
+    n1, k1, d1 = E.Extract(bgr)
+    n2, k2, d2 = E.Extract(oracle.bgr2gray(bgr))
+    assert n1 == n2 and k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes()
+    O = oracle.Orb(2000, 1.2, 8, 28, 15)
+    n3, k3, d3 = O.extract(oracle.bgr2gray(bgr))
+    assert n1 == n3 and k1.tobytes() == k3.tobytes() and d1.tobytes() == d3.tobytes()
+
+
+@pytest.mark.gpu
+def test_rig_bgr_triplets(api, oracle):
+    from mcvslam_b200 import synth
+    frames = np.stack([synth.triplet(40 + s) for s in range(3)])                      # (3, 3, 480, 640)
+    rng = np.random.default_rng(5)
+    bgr = np.clip(frames[..., None].astype(np.int64) + rng.integers(-15, 16, frames.shape + (3,)), 0, 255).astype(np.uint8)
+    gray = np.stack([[oracle.bgr2gray(bgr[f, c]) for c in range(3)] for f in range(3)])
+    rig = api.Rig(device=0)
+    ref = rig.process(gray)
+    rig.set_input_channels(3)
+    out = rig.process(bgr)
+    rig.set_input_channels(1)
+    for key in ("counts", "kps", "desc", "u_right", "depth_left"):
+        assert out[key].tobytes() == ref[key].tobytes(), key
+    rig.close()
