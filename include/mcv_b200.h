@@ -232,6 +232,25 @@ mcv_status mcv_project_match(const mcv_keypoint* kps, const uint8_t* desc, int n
                              const uint8_t* mp_desc, const int32_t* mp_level, int n_mp, float r_threshold, int32_t* out_idx,
                              int32_t* out_dist, int* n_matched);
 
+/* Map::Fuse matching front-end (src/Map.cpp:478-527) for an ORDERED array of MapPoints against one camera's keypoints: the
+ * viewing-angle gate, Object::Map / Project, GetFeaturesInArea(uv, 10), the level and reprojection gates (as written in the
+ * reference, incl. its use of kf->depth_left and mvLevelSigma2 in the stereo branch), KnnMatch + FilterRatio() +
+ * FilterThreshold(). Ow = camera centre (3), depth_left [n] = KeyFrame::depth_left, bf = KeyFrame::bf, mp_normal [n_mp][3] =
+ * MapPoint::GetNormalVector(). out_idx[m] = the keypoint index the reference passes to AddMapPoint / ReplaceMappoint, or -1.
+ * The map surgery itself (src/Map.cpp:528-547) stays with the caller. */
+mcv_status mcv_fuse_match(const mcv_keypoint* kps, const uint8_t* desc, int n, int w, int hgt, const float* level_sigma2,
+                          const float* inv_level_sigma2, int nlevels, const float* Rcw, const float* tcw, const float* Ow, const float* intr,
+                          const float* depth_left, float bf, const float* mp_xyz, const float* mp_normal, const uint8_t* mp_desc,
+                          const int32_t* mp_level, int n_mp, int32_t* out_idx, int32_t* out_dist, int* n_matched);
+
+/* Tracker::Wnd_Track (src/Tracker.cpp:341-360): every listed keypoint q_idx[q] of camera 1 (those owning a MapPoint, in the
+ * caller's order) against the keypoints of camera 2 inside a +-20 px window, KnnMatch + FilterRatio() + FilterThreshold()
+ * (+ FilterOrientation, the identity on one match). out_idx[q] = the camera-2 index the reference hands to AddMapPoint — as
+ * written that is candi_idxs[queryIdx], the FIRST candidate of the window — out_best[q] = the candidate the match belongs to,
+ * out_dist[q] = its Hamming distance; -1 where nothing passes. */
+mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1, const int32_t* q_idx, int n_q, const mcv_keypoint* kps2,
+                         const uint8_t* desc2, int n2, int w, int hgt, int32_t* out_idx, int32_t* out_best, int32_t* out_dist, int* n_matched);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Test / measurement taps (used by tests/ and bench.py only).
  * ---------------------------------------------------------------------------------------------------------- */

@@ -31,7 +31,7 @@ EXPORTS = [
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
     "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_set_input_channels", "mcv_orb_set_input_channels", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
-    "mcv_project_match", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
+    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
 ]
 
@@ -103,6 +103,8 @@ def lib():
         L.mcv_rig_stage_ms.argtypes = [vp, vp, i, C.POINTER(i)]
         L.mcv_stereo_match.argtypes = [vp, vp, vp, vp, i, vp, vp, i, f, f, vp, vp, vp, vp]
         L.mcv_project_match.argtypes = [vp, vp, i, i, i, vp, i, vp, vp, vp, vp, vp, vp, i, f, vp, vp, C.POINTER(i)]
+        L.mcv_fuse_match.argtypes = [vp, vp, i, i, i, vp, vp, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, i, vp, vp, C.POINTER(i)]
+        L.mcv_wnd_track.argtypes = [vp, vp, i, vp, i, vp, vp, i, i, i, vp, vp, vp, C.POINTER(i)]
         L.mcv_debug_sincosf.argtypes = [vp, i, vp, vp]
         L.mcv_debug_fast_atan2.argtypes = [vp, vp, i, vp]
         L.mcv_debug_level_keypoints.argtypes = [vp, i, i, i, vp, i, C.POINTER(i)]
@@ -366,6 +368,32 @@ def ProjectBunchMapPoints(kps, desps, w, h, scale_factors, Rcw, tcw, intrinsics,
     _check(lib().mcv_project_match(_p(kps), _p(desps), len(kps), w, h, _p(sf), len(sf), _p(R), _p(t), _p(K), _p(xyz), _p(md), _p(ml), n_mp,
                                    r_threshold, _p(oi), _p(od), C.byref(cnt)))
     return cnt.value, oi, od
+
+
+def FuseMatch(kps, desps, w, h, level_sigma2, inv_level_sigma2, Rcw, tcw, Ow, intrinsics, depth_left, bf, mp_xyz, mp_normal, mp_desc, mp_level):
+    """Matching front-end of Map::Fuse (src/Map.cpp:478-527) for an ordered MapPoint array. Returns (cnt, idx, dist)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desps = _u8(desps)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    s2, is2, R, t, O, K, dl, xyz, nrm = map(f32, (level_sigma2, inv_level_sigma2, Rcw, tcw, Ow, intrinsics, depth_left, mp_xyz, mp_normal))
+    md = _u8(mp_desc); ml = np.ascontiguousarray(mp_level, np.int32)
+    n_mp = len(ml)
+    oi = np.full(n_mp, -1, np.int32); od = np.full(n_mp, -1, np.int32)
+    cnt = C.c_int(0)
+    _check(lib().mcv_fuse_match(_p(kps), _p(desps), len(kps), w, h, _p(s2), _p(is2), len(s2), _p(R), _p(t), _p(O), _p(K), _p(dl), bf, _p(xyz),
+                                _p(nrm), _p(md), _p(ml), n_mp, _p(oi), _p(od), C.byref(cnt)))
+    return cnt.value, oi, od
+
+
+def WndTrack(kps1, desps1, q_idx, kps2, desps2, w, h):
+    """Tracker::Wnd_Track (src/Tracker.cpp:341-360). Returns (cnt, idx [what the reference reports: the window's first
+    candidate], best [the candidate the match belongs to], dist)."""
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); desps1 = _u8(desps1); kps2 = np.ascontiguousarray(kps2, KP_DTYPE); desps2 = _u8(desps2)
+    q = np.ascontiguousarray(q_idx, np.int32)
+    oi = np.full(len(q), -1, np.int32); ob = np.full(len(q), -1, np.int32); od = np.full(len(q), -1, np.int32)
+    cnt = C.c_int(0)
+    _check(lib().mcv_wnd_track(_p(kps1), _p(desps1), len(kps1), _p(q), len(q), _p(kps2), _p(desps2), len(kps2), w, h, _p(oi), _p(ob), _p(od),
+                               C.byref(cnt)))
+    return cnt.value, oi, ob, od
 
 
 class Rig:

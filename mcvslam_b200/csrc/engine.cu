@@ -665,6 +665,93 @@ mcv_status mcv_project_match(const mcv_keypoint* kps, const uint8_t* desc, int n
     return MCV_OK;
 }
 
+mcv_status mcv_fuse_match(const mcv_keypoint* kps, const uint8_t* desc, int n, int w, int hgt, const float* level_sigma2,
+                          const float* inv_level_sigma2, int nlevels, const float* Rcw, const float* tcw, const float* Ow, const float* intr,
+                          const float* depth_left, float bf, const float* mp_xyz, const float* mp_normal, const uint8_t* mp_desc,
+                          const int32_t* mp_level, int n_mp, int32_t* out_idx, int32_t* out_dist, int* n_matched) {
+    if (n < 0 || n_mp < 0 || w <= 0 || hgt <= 0 || nlevels < 1 || !level_sigma2 || !inv_level_sigma2 || !Rcw || !tcw || !Ow || !intr || n >= (1 << 21))
+        return MCV_ERR_BAD_ARG;
+    if (n_mp > 0 && (!mp_xyz || !mp_normal || !mp_desc || !mp_level || !out_idx || !out_dist)) return MCV_ERR_BAD_ARG;
+    if (n > 0 && (!kps || !desc || !depth_left)) return MCV_ERR_BAD_ARG;
+    for (int i = 0; i < n; ++i) if (kps[i].octave < 0 || kps[i].octave >= nlevels) return MCV_ERR_BAD_ARG;
+    if (n_matched) *n_matched = 0;
+    if (n_mp == 0) return MCV_OK;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b_kps, b_desc, b_f, b_dl, b_xyz, b_nrm, b_mpd, b_lvl, b_oi, b_od;
+    if ((st = b_kps.reserve(std::max<size_t>(28, (size_t)n * sizeof(mcv_keypoint))))) return st;
+    if ((st = b_desc.reserve(std::max<size_t>(32, (size_t)n * 32)))) return st;
+    if ((st = b_dl.reserve(std::max<size_t>(4, (size_t)n * 4)))) return st;
+    if ((st = b_f.reserve((size_t)(2 * nlevels + 20) * 4))) return st;
+    if ((st = b_xyz.reserve((size_t)n_mp * 12))) return st;
+    if ((st = b_nrm.reserve((size_t)n_mp * 12))) return st;
+    if ((st = b_mpd.reserve((size_t)n_mp * 32))) return st;
+    if ((st = b_lvl.reserve((size_t)n_mp * 4))) return st;
+    if ((st = b_oi.reserve((size_t)n_mp * 4))) return st;
+    if ((st = b_od.reserve((size_t)n_mp * 4))) return st;
+    std::vector<float> f(2 * nlevels + 20);
+    memcpy(f.data(), Rcw, 36); memcpy(f.data() + 9, tcw, 12); memcpy(f.data() + 12, intr, 16); memcpy(f.data() + 16, Ow, 12);
+    f[19] = bf;
+    memcpy(f.data() + 20, level_sigma2, (size_t)nlevels * 4); memcpy(f.data() + 20 + nlevels, inv_level_sigma2, (size_t)nlevels * 4);
+    if (n) {
+        MCV_CUDA(cudaMemcpyAsync(b_kps.p, kps, (size_t)n * sizeof(mcv_keypoint), cudaMemcpyHostToDevice, s));
+        MCV_CUDA(cudaMemcpyAsync(b_desc.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+        MCV_CUDA(cudaMemcpyAsync(b_dl.p, depth_left, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    }
+    MCV_CUDA(cudaMemcpyAsync(b_f.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_xyz.p, mp_xyz, (size_t)n_mp * 12, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_nrm.p, mp_normal, (size_t)n_mp * 12, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_mpd.p, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_lvl.p, mp_level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, s));
+    launch_fuse_match(b_kps.as<mcv_keypoint>(), b_desc.as<uint8_t>(), n, w, hgt, b_f.as<float>(), nlevels, b_dl.as<float>(), b_xyz.as<float>(),
+                      b_nrm.as<float>(), b_mpd.as<uint8_t>(), b_lvl.as<int32_t>(), n_mp, b_oi.as<int32_t>(), b_od.as<int32_t>(), s);
+    MCV_CUDA(cudaGetLastError());
+    MCV_CUDA(cudaMemcpyAsync(out_idx, b_oi.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(out_dist, b_od.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    if (n_matched) { int c = 0; for (int m = 0; m < n_mp; ++m) c += out_idx[m] >= 0; *n_matched = c; }
+    return MCV_OK;
+}
+
+mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1, const int32_t* q_idx, int n_q, const mcv_keypoint* kps2,
+                         const uint8_t* desc2, int n2, int w, int hgt, int32_t* out_idx, int32_t* out_best, int32_t* out_dist, int* n_matched) {
+    if (n1 < 0 || n2 < 0 || n_q < 0 || w <= 0 || hgt <= 0 || n2 >= (1 << 21)) return MCV_ERR_BAD_ARG;
+    if (n_q > 0 && (!kps1 || !desc1 || !q_idx || !out_idx || !out_best || !out_dist)) return MCV_ERR_BAD_ARG;
+    if (n2 > 0 && (!kps2 || !desc2)) return MCV_ERR_BAD_ARG;
+    for (int q = 0; q < n_q; ++q) if (q_idx[q] < 0 || q_idx[q] >= n1) return MCV_ERR_BAD_ARG;
+    if (n_matched) *n_matched = 0;
+    if (n_q == 0) return MCV_OK;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b_k1, b_d1, b_q, b_k2, b_d2, b_oi, b_ob, b_od;
+    if ((st = b_k1.reserve((size_t)n1 * sizeof(mcv_keypoint)))) return st;
+    if ((st = b_d1.reserve((size_t)n1 * 32))) return st;
+    if ((st = b_q.reserve((size_t)n_q * 4))) return st;
+    if ((st = b_k2.reserve(std::max<size_t>(28, (size_t)n2 * sizeof(mcv_keypoint))))) return st;
+    if ((st = b_d2.reserve(std::max<size_t>(32, (size_t)n2 * 32)))) return st;
+    if ((st = b_oi.reserve((size_t)n_q * 4))) return st;
+    if ((st = b_ob.reserve((size_t)n_q * 4))) return st;
+    if ((st = b_od.reserve((size_t)n_q * 4))) return st;
+    MCV_CUDA(cudaMemcpyAsync(b_k1.p, kps1, (size_t)n1 * sizeof(mcv_keypoint), cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_d1.p, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_q.p, q_idx, (size_t)n_q * 4, cudaMemcpyHostToDevice, s));
+    if (n2) {
+        MCV_CUDA(cudaMemcpyAsync(b_k2.p, kps2, (size_t)n2 * sizeof(mcv_keypoint), cudaMemcpyHostToDevice, s));
+        MCV_CUDA(cudaMemcpyAsync(b_d2.p, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    }
+    launch_wnd_track(b_k1.as<mcv_keypoint>(), b_d1.as<uint8_t>(), b_q.as<int32_t>(), n_q, b_k2.as<mcv_keypoint>(), b_d2.as<uint8_t>(), n2, w, hgt,
+                     b_oi.as<int32_t>(), b_ob.as<int32_t>(), b_od.as<int32_t>(), s);
+    MCV_CUDA(cudaGetLastError());
+    MCV_CUDA(cudaMemcpyAsync(out_idx, b_oi.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(out_best, b_ob.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(out_dist, b_od.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    if (n_matched) { int c = 0; for (int q = 0; q < n_q; ++q) c += out_idx[q] >= 0; *n_matched = c; }
+    return MCV_OK;
+}
+
 mcv_status mcv_debug_sincosf(const float* a, int n, float* so, float* co) {
     if (n <= 0 || !a || !so || !co) return MCV_ERR_BAD_ARG;
     cudaStream_t s;

@@ -110,6 +110,11 @@ int launch_knn2_candidates(const uint8_t* d_q, int nq, const uint8_t* d_t, const
 int launch_project(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_scale, const float* d_pose,
                    const float* d_xyz, const uint8_t* d_mp_desc, const int32_t* d_level, int n_mp, float r_th, int32_t* d_idx,
                    int32_t* d_dist, cudaStream_t s);
+int launch_fuse_match(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_par, int n_levels,
+                      const float* d_depth_left, const float* d_xyz, const float* d_normal, const uint8_t* d_mp_desc, const int32_t* d_level,
+                      int n_mp, int32_t* d_idx, int32_t* d_dist, cudaStream_t s);
+int launch_wnd_track(const mcv_keypoint* d_kps1, const uint8_t* d_desc1, const int32_t* d_qidx, int n_q, const mcv_keypoint* d_kps2,
+                     const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_idx, int32_t* d_best, int32_t* d_dist, cudaStream_t s);
 int launch_debug_sincosf(const float* d_a, int n, float* d_s, float* d_c, cudaStream_t s);
 int launch_debug_atan2(const float* d_y, const float* d_x, int n, float* d_o, cudaStream_t s);
 int launch_popc_peak(int iters, unsigned* d_sink, int blocks, int threads, cudaStream_t s);

@@ -214,6 +214,147 @@ int launch_project(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Window matching shared by Map::Fuse and Tracker::Wnd_Track: GetFeaturesInArea(x, y, r) (src/Object.cpp:263-308) over the
+// 30x30 grid of AssignFeaturesToGrid (src/Object.cpp:182-201,249-257) + first-party 2-NN (src/Matcher.cpp:256-275). One warp
+// per query; lanes stride over the keypoints; a candidate's key is (distance, grid-cell-major order, index), so the packed
+// minimum reproduces the reference's candidate-list order for ties. `gate(j)` is the caller's extra per-candidate test.
+// Returns in every lane the two smallest keys (SENT when absent) and, in `first`, the smallest order key (first candidate).
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned long long WM_SENT = 999ull << 32;
+
+template <typename Gate>
+__device__ __forceinline__ void window_knn2(const mcv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int n, int w, int h, float x,
+                                            float y, float r, uint4 a0, uint4 a1, Gate gate, unsigned long long& k0, unsigned long long& k1,
+                                            unsigned& first) {
+    const int lane = threadIdx.x & 31;
+    k0 = WM_SENT; k1 = WM_SENT; first = 0xffffffffu;
+    bool ok = x >= 0.f && y >= 0.f && x < (float)w && y < (float)h;
+    const float winv = (float)((double)GRID_N / w), hinv = (float)((double)GRID_N / h);
+    const int min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(x, r), winv)));
+    const int max_cx = min(GRID_N - 1, (int)ceilf(__fmul_rn(__fadd_rn(x, r), winv)));
+    const int min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(y, r), hinv)));
+    const int max_cy = min(GRID_N - 1, (int)ceilf(__fmul_rn(__fadd_rn(y, r), hinv)));
+    ok = ok && !(min_cx >= GRID_N || max_cx < 0 || min_cy >= GRID_N || max_cy < 0);
+    if (ok) {
+        for (int j = lane; j < n; j += 32) {
+            const float kx = kps[j].x, ky = kps[j].y;
+            const int gx = (int)roundf(__fmul_rn(kx, winv)), gy = (int)roundf(__fmul_rn(ky, hinv));
+            if (gx < 0 || gx >= GRID_N || gy < 0 || gy >= GRID_N) continue;
+            if (gx < min_cx || gx > max_cx || gy < min_cy || gy > max_cy) continue;
+            if (!(fabsf(__fsub_rn(kx, x)) < r && fabsf(__fsub_rn(ky, y)) < r)) continue;
+            if (!gate(j)) continue;
+            const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32));
+            const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32 + 16));
+            const unsigned order = ((unsigned)(gx * GRID_N + gy) << 21) | (unsigned)j;
+            const unsigned long long key = ((unsigned long long)hamming256(a0, a1, b0, b1) << 32) | order;
+            const unsigned long long hi = key > k0 ? key : k0;
+            k1 = k1 < hi ? k1 : hi;
+            k0 = k0 < key ? k0 : key;
+            first = min(first, order);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0, l1 = k1 < o1 ? k1 : o1;
+        k0 = lo; k1 = hi < l1 ? hi : l1;
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    }
+}
+
+// FilterRatio() / FilterThreshold() defaults on one 2-NN row (src/Matcher.cpp:100-111,22-33; include/Matcher.hpp:14,55)
+__device__ __forceinline__ bool ratio_threshold_pass(unsigned long long k0, unsigned long long k1) {
+    if (k0 == WM_SENT) return false;
+    const float d0 = (float)(unsigned)(k0 >> 32), d1 = (float)(unsigned)(k1 >> 32);
+    return __fdiv_rn(d0, d1) <= 0.6f && !(d0 > 46.0f);
+}
+
+// Map::Fuse matching front-end (src/Map.cpp:478-527). par = Rcw (9) | tcw (3) | fx fy cx cy | Ow (3) | bf | sigma2[L] | inv_sigma2[L]
+__global__ void __launch_bounds__(256) k_fuse_match(const mcv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int n, int w, int h,
+                                                    const float* __restrict__ par, int n_levels, const float* __restrict__ depth_left,
+                                                    const float* __restrict__ xyz, const float* __restrict__ normal,
+                                                    const uint8_t* __restrict__ mp_desc, const int32_t* __restrict__ mp_level, int n_mp,
+                                                    int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= n_mp) return;                                   // warp-uniform
+    if (lane == 0) { out_idx[m] = -1; out_dist[m] = -1; }
+    const float X = xyz[3 * m], Y = xyz[3 * m + 1], Z = xyz[3 * m + 2];
+    // viewing angle (:483-488): PO = Xw - Ow in float; cv::norm and Mat::dot accumulate the products in double
+    const float po0 = __fsub_rn(X, par[16]), po1 = __fsub_rn(Y, par[17]), po2 = __fsub_rn(Z, par[18]);
+    const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)po0), __dmul_rn((double)po1, (double)po1)), __dmul_rn((double)po2, (double)po2));
+    const float dist3d = __double2float_rn(__dsqrt_rn(n2));
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)normal[3 * m]), __dmul_rn((double)po1, (double)normal[3 * m + 1])),
+                                 __dmul_rn((double)po2, (double)normal[3 * m + 2]));
+    if (dot < __dmul_rn(0.5, (double)dist3d)) return;
+    float pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)  // Object::Map: mRcw * x3D + mtcw, float gemm left to right
+        pc[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(par[3 * r], X), __fmul_rn(par[3 * r + 1], Y)), __fmul_rn(par[3 * r + 2], Z)), par[9 + r]);
+    const float z = pc[2];
+    if (z <= 0.f) return;
+    const float invz = __double2float_rn(__ddiv_rn(1.0, (double)z));   // const float invz = 1. / z
+    const float u = __fadd_rn(__fdiv_rn(__fmul_rn(par[12], pc[0]), pc[2]), par[14]);
+    const float v = __fadd_rn(__fdiv_rn(__fmul_rn(par[13], pc[1]), pc[2]), par[15]);
+    const float ur = __fsub_rn(u, __fmul_rn(par[19], invz));
+    const int lvl = mp_level[m], lvl_lo = max(0, lvl - 1);
+    const float* sigma2 = par + 20;
+    const float* inv_sigma2 = par + 20 + n_levels;
+    auto gate = [&](int j) {
+        const int level = kps[j].octave;
+        if (level < lvl_lo || level > lvl) return false;
+        const float ex = __fsub_rn(u, kps[j].x), ey = __fsub_rn(v, kps[j].y);
+        const float dl = depth_left[j];
+        if (dl >= 0.f) {   // "stereo" branch exactly as written (:505-516)
+            const float er = __fsub_rn(ur, dl);
+            const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+            return !((double)__fmul_rn(e2, sigma2[level]) > 7.8);
+        }
+        const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+        return !((double)__fmul_rn(e2, inv_sigma2[level]) > 5.99);
+    };
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(mp_desc + (size_t)m * 32));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(mp_desc + (size_t)m * 32 + 16));
+    unsigned long long k0, k1; unsigned first;
+    window_knn2(kps, desc, n, w, h, u, v, 10.f, a0, a1, gate, k0, k1, first);
+    if (!ratio_threshold_pass(k0, k1)) return;
+    if (lane == 0) { out_idx[m] = (int)(k0 & 0x1fffffu); out_dist[m] = (int)(k0 >> 32); }
+}
+
+// Tracker::Wnd_Track (src/Tracker.cpp:341-360): +-20 px window of obj2 around every listed keypoint of obj1. out_idx = the
+// index the reference reports (candi_idxs[queryIdx] = the window's FIRST candidate), out_best = the matched candidate.
+__global__ void __launch_bounds__(256) k_wnd_track(const mcv_keypoint* __restrict__ kps1, const uint8_t* __restrict__ desc1,
+                                                   const int32_t* __restrict__ q_idx, int n_q, const mcv_keypoint* __restrict__ kps2,
+                                                   const uint8_t* __restrict__ desc2, int n2, int w, int h, int32_t* __restrict__ out_idx,
+                                                   int32_t* __restrict__ out_best, int32_t* __restrict__ out_dist) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= n_q) return;
+    if (lane == 0) { out_idx[q] = -1; out_best[q] = -1; out_dist[q] = -1; }
+    const int i = q_idx[q];
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(desc1 + (size_t)i * 32));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(desc1 + (size_t)i * 32 + 16));
+    unsigned long long k0, k1; unsigned first;
+    window_knn2(kps2, desc2, n2, w, h, kps1[i].x, kps1[i].y, 20.f, a0, a1, [](int) { return true; }, k0, k1, first);
+    if (!ratio_threshold_pass(k0, k1)) return;
+    if (lane == 0) { out_idx[q] = (int)(first & 0x1fffffu); out_best[q] = (int)(k0 & 0x1fffffu); out_dist[q] = (int)(k0 >> 32); }
+}
+
+int launch_fuse_match(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_par, int n_levels,
+                      const float* d_depth_left, const float* d_xyz, const float* d_normal, const uint8_t* d_mp_desc, const int32_t* d_level,
+                      int n_mp, int32_t* d_idx, int32_t* d_dist, cudaStream_t s) {
+    if (n_mp <= 0) return 0;
+    k_fuse_match<<<(n_mp + 7) / 8, 256, 0, s>>>(d_kps, d_desc, n, w, h, d_par, n_levels, d_depth_left, d_xyz, d_normal, d_mp_desc, d_level, n_mp,
+                                               d_idx, d_dist);
+    return 1;
+}
+
+int launch_wnd_track(const mcv_keypoint* d_kps1, const uint8_t* d_desc1, const int32_t* d_qidx, int n_q, const mcv_keypoint* d_kps2,
+                     const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_idx, int32_t* d_best, int32_t* d_dist, cudaStream_t s) {
+    if (n_q <= 0) return 0;
+    k_wnd_track<<<(n_q + 7) / 8, 256, 0, s>>>(d_kps1, d_desc1, d_qidx, n_q, d_kps2, d_desc2, n2, w, h, d_idx, d_best, d_dist);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // test taps + integer-pipe peak
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_debug_sincosf(const float* a, int n, float* s, float* c) {

@@ -357,10 +357,11 @@ class Matcher {
 // ---------------------------------------------------------------------------------------------------------
 // Object / Frame: the callers either side of the path, reduced to what the path reads and writes.
 // ---------------------------------------------------------------------------------------------------------
-struct MapPointView {      // what ProjectBunchMapPoints reads of a MapPoint: GetWorldPos(), GetDesp(), level
+struct MapPointView {      // what ProjectBunchMapPoints / Map::Fuse read of a MapPoint: GetWorldPos(), GetDesp(), level, GetNormalVector()
     float xyz[3];
     uint8_t desp[32];
     int level;
+    float normal[3] = {0, 0, 0};
 };
 
 class Object {
@@ -392,12 +393,57 @@ class Object {
         return (uint)cnt;
     }
 
+    // Matching front-end of Map::Fuse(obj1 = this, kf, mps) (src/Map.cpp:478-527) for an ORDERED vector of MapPoint views:
+    // matched_idx[m] = the keypoint index the reference hands to AddMapPoint / ReplaceMappoint (best_idx), or -1. The map
+    // surgery (src/Map.cpp:528-547) stays with the caller. kf_depth_left / kf_bf = kf->depth_left, kf->bf.
+    uint FuseMatch(const std::vector<MapPointView>& mps, const std::vector<float>& kf_depth_left, float kf_bf, std::vector<int>& matched_idx,
+                   std::vector<int>* matched_dist = nullptr) {
+        const int n_mp = (int)mps.size();
+        std::vector<float> xyz((size_t)n_mp * 3 + 3), nrm((size_t)n_mp * 3 + 3);
+        std::vector<uint8_t> md((size_t)n_mp * 32 + 32);
+        std::vector<int32_t> lvl((size_t)n_mp + 1), od((size_t)n_mp + 1);
+        for (int m = 0; m < n_mp; ++m) {
+            memcpy(&xyz[3 * (size_t)m], mps[m].xyz, 12); memcpy(&nrm[3 * (size_t)m], mps[m].normal, 12);
+            memcpy(&md[32 * (size_t)m], mps[m].desp, 32); lvl[m] = mps[m].level;
+        }
+        if (kf_depth_left.size() != kps.size()) throw std::runtime_error("FuseMatch: depth_left must have one entry per keypoint");
+        matched_idx.assign((size_t)n_mp, -1);
+        float Ow[3];   // mOw = -mRwc * mtcw (src/Object.cpp:174)
+        for (int r = 0; r < 3; ++r) Ow[r] = -((Rcw[r] * tcw[0] + Rcw[3 + r] * tcw[1]) + Rcw[6 + r] * tcw[2]);
+        int cnt = 0;
+        const cv::Mat d = (desps.empty() || desps.isContinuous()) ? desps : desps.clone();
+        const mcv_status st = mcv_fuse_match(mcv_host::kp_ptr(kps), d.data, (int)kps.size(), img.cols, img.rows, extractor->mvLevelSigma2.data(),
+                                             extractor->mvInvLevelSigma2.data(), (int)extractor->mvLevelSigma2.size(), Rcw, tcw, Ow, intr,
+                                             kf_depth_left.data(), kf_bf, xyz.data(), nrm.data(), md.data(), lvl.data(), n_mp, matched_idx.data(),
+                                             od.data(), &cnt);
+        if (st != MCV_OK) throw std::runtime_error(std::string("FuseMatch: ") + mcv_last_error());
+        if (matched_dist) matched_dist->assign(od.begin(), od.begin() + n_mp);
+        return (uint)cnt;
+    }
+
     cv::Mat img;
     Keypoints kps;
     Desps desps;
     ORB* extractor = nullptr;
     float Rcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcw[3] = {0, 0, 0}, intr[4] = {1, 1, 0, 0};
 };
+
+// Tracker::Wnd_Track(obj1, obj2) (src/Tracker.cpp:341-360) for the keypoints of obj1 that own a MapPoint (`mp_kp_idxs`, the
+// order of obj1->GetAllMapPointsIdxs()). matched[q] = the obj2 index the reference passes to AddMapPoint, or -1.
+inline uint Wnd_Track(const Object& obj1, const std::vector<int>& mp_kp_idxs, const Object& obj2, std::vector<int>& matched,
+                      std::vector<int>* matched_dist = nullptr) {
+    const int nq = (int)mp_kp_idxs.size();
+    matched.assign((size_t)nq, -1);
+    std::vector<int32_t> best((size_t)nq + 1), od((size_t)nq + 1);
+    int cnt = 0;
+    const cv::Mat d1 = (obj1.desps.empty() || obj1.desps.isContinuous()) ? obj1.desps : obj1.desps.clone();
+    const cv::Mat d2 = (obj2.desps.empty() || obj2.desps.isContinuous()) ? obj2.desps : obj2.desps.clone();
+    const mcv_status st = mcv_wnd_track(mcv_host::kp_ptr(obj1.kps), d1.data, (int)obj1.kps.size(), mp_kp_idxs.data(), nq, mcv_host::kp_ptr(obj2.kps),
+                                        d2.data, (int)obj2.kps.size(), obj2.img.cols, obj2.img.rows, matched.data(), best.data(), od.data(), &cnt);
+    if (st != MCV_OK) throw std::runtime_error(std::string("Wnd_Track: ") + mcv_last_error());
+    if (matched_dist) matched_dist->assign(od.begin(), od.begin() + nq);
+    return (uint)cnt;
+}
 using ObjectRef = std::shared_ptr<Object>;
 
 class Frame {

@@ -256,6 +256,33 @@ def project_match(kps, desc, W, H, scale_factors, Rcw, tcw, intr, mp_xyz, mp_des
     return cnt, oi, od
 
 
+def fuse_match(kps, desc, W, H, sigma2, inv_sigma2, Rcw, tcw, Ow, intr, depth_left, bf, mp_xyz, mp_normal, mp_desc, mp_level):
+    """Map::Fuse matching front-end (src/Map.cpp:478-527). Returns (cnt, out_idx, out_dist)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = _u8(desc)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    sigma2, inv_sigma2, Rcw, tcw, Ow, intr, depth_left, mp_xyz, mp_normal = map(f32, (sigma2, inv_sigma2, Rcw, tcw, Ow, intr, depth_left, mp_xyz, mp_normal))
+    mp_desc = _u8(mp_desc); mp_level = np.ascontiguousarray(mp_level, np.int32)
+    n_mp = len(mp_level)
+    oi = np.empty(n_mp, np.int32); od = np.empty(n_mp, np.int32)
+    L = lib()
+    L.ora_fuse_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_float] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p]
+    cnt = L.ora_fuse_match(_p(kps), _p(desc), len(kps), W, H, _p(sigma2), _p(inv_sigma2), _p(Rcw), _p(tcw), _p(Ow), _p(intr), _p(depth_left),
+                           bf, _p(mp_xyz), _p(mp_normal), _p(mp_desc), _p(mp_level), n_mp, _p(oi), _p(od))
+    return cnt, oi, od
+
+
+def wnd_track(kps1, desc1, q_idx, kps2, desc2, W, H):
+    """Tracker::Wnd_Track (src/Tracker.cpp:341-360). Returns (cnt, out_idx [reference behaviour: first candidate], out_best, out_dist)."""
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); desc1 = _u8(desc1); kps2 = np.ascontiguousarray(kps2, KP_DTYPE); desc2 = _u8(desc2)
+    q_idx = np.ascontiguousarray(q_idx, np.int32)
+    n_q = len(q_idx)
+    oi = np.empty(n_q, np.int32); ob = np.empty(n_q, np.int32); od = np.empty(n_q, np.int32)
+    L = lib()
+    L.ora_wnd_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    cnt = L.ora_wnd_track(_p(kps1), _p(desc1), _p(q_idx), n_q, _p(kps2), _p(desc2), len(kps2), W, H, _p(oi), _p(ob), _p(od))
+    return cnt, oi, ob, od
+
+
 def bench_frames(imgs, nfeatures, sf, nlevels, ini, mn, bf, b, n_threads, repeat=1):
     """imgs: (n_frames, 3, H, W) u8. Returns (seconds, total_keypoints)."""
     imgs = _u8(imgs)

@@ -654,6 +654,93 @@ int ora_project_match(const KeyPoint* kps, const uint8_t* desc, int n, int W, in
     return cnt;
 }
 
+// ---- Map::Fuse matching front-end (src/Map.cpp:478-527) over an ORDERED MapPoint array ----
+// Per MapPoint: viewing-angle gate (:487-488), Object::Map + z gate (:490-492), projection (:494), GetFeaturesInArea(uv, 10)
+// (:495), per candidate the level gate (:503) and the reprojection gates (:505-524 — as written: the stereo branch compares the
+// predicted right coordinate with kf->depth_left[idx] and scales by mvLevelSigma2, the mono branch by mvInvLevelSigma2), then
+// KnnMatch({desp}, desps).FilterRatio().FilterThreshold() (:527). out_idx[m] = ori_kp_idx[res[0].trainIdx] or -1. The map
+// surgery that follows (:528-547) is pointer-graph state and stays with the caller.
+// cv::Mat arithmetic restated from OpenCV: Mat - Mat and the 3x3 gemm in float (pinned against cv2.gemm), cv::norm and
+// Mat::dot accumulate the float products in double.
+int ora_fuse_match(const KeyPoint* kps, const uint8_t* desc, int n, int W, int H, const float* sigma2, const float* inv_sigma2,
+                   const float* Rcw, const float* tcw, const float* Ow, const float* intr, const float* depth_left, float bf,
+                   const float* mp_xyz, const float* mp_normal, const uint8_t* mp_desc, const int* mp_level, int n_mp, int* out_idx,
+                   int* out_dist) {
+    FeatureGrid* G = new FeatureGrid();
+    G->build(kps, n, W, H);
+    int cnt = 0; vector<size_t> cand, ori; vector<const uint8_t*> c;
+    for (int m = 0; m < n_mp; ++m) {
+        out_idx[m] = -1; out_dist[m] = -1;
+        const float* P = mp_xyz + 3 * m; const float* Pn = mp_normal + 3 * m;
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist3D = (float)sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);   // cv::norm
+        const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];                   // Mat::dot
+        if (dot < 0.5 * dist3D) continue;
+        float pc[3];
+        for (int r = 0; r < 3; ++r) pc[r] = (Rcw[3 * r] * P[0] + Rcw[3 * r + 1] * P[1] + Rcw[3 * r + 2] * P[2]) + tcw[r];
+        const float z = pc[2];
+        if (z <= 0) continue;
+        const float invz = 1. / z;
+        const float u = intr[0] * pc[0] / pc[2] + intr[2], v = intr[1] * pc[1] / pc[2] + intr[3];
+        G->query(kps, u, v, 10, cand);
+        ori.clear();
+        for (size_t idx : cand) {
+            const KeyPoint& kp = kps[idx];
+            const int level = kp.octave;
+            if (level < max(0, int(mp_level[m] - 1)) || level > mp_level[m]) continue;
+            if (depth_left[idx] >= 0) {
+                const float ur = u - bf * invz;
+                const float ex = u - kp.x, ey = v - kp.y, er = ur - depth_left[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * sigma2[level] > 7.8) continue;
+            } else {
+                const float ex = u - kp.x, ey = v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_sigma2[level] > 5.99) continue;
+            }
+            ori.push_back(idx);
+        }
+        // KnnMatch({desp}, {}) leaves the sentinel pair (distance 999, 999) and FilterRatio drops it (999 / 999 > 0.6): an empty
+        // candidate list never matches (src/Matcher.cpp:256-275,100-111)
+        if (ori.empty()) continue;
+        c.resize(ori.size());
+        for (size_t j = 0; j < ori.size(); ++j) c[j] = desc + ori[j] * 32;
+        unsigned d[2], di[2];
+        knn2_stream(mp_desc + (size_t)m * 32, c.data(), (int)c.size(), d, di);
+        if (!ratio_pass((float)d[0], (float)d[1], 0.6f)) continue;
+        if ((float)d[0] > 46) continue;
+        out_idx[m] = (int)ori[di[0]]; out_dist[m] = (int)d[0]; cnt++;
+    }
+    delete G;
+    return cnt;
+}
+
+// ---- Tracker::Wnd_Track (src/Tracker.cpp:341-360): every keypoint of obj1 that owns a MapPoint (q_idx, in the caller's order)
+// is matched inside a +-20 px window of obj2. As written, the reference takes candi_idxs[t_res[0].queryIdx] — queryIdx is
+// always 0 — so a successful match reports the FIRST candidate of the window, not the best one; out_idx reproduces that, and
+// out_best holds the index the match really belongs to. FilterOrientation on a single match keeps it (its bin is the fullest).
+int ora_wnd_track(const KeyPoint* kps1, const uint8_t* desc1, const int* q_idx, int n_q, const KeyPoint* kps2, const uint8_t* desc2, int n2,
+                  int W, int H, int* out_idx, int* out_best, int* out_dist) {
+    FeatureGrid* G = new FeatureGrid();
+    G->build(kps2, n2, W, H);
+    int cnt = 0; vector<size_t> cand; vector<const uint8_t*> c;
+    for (int q = 0; q < n_q; ++q) {
+        out_idx[q] = -1; out_best[q] = -1; out_dist[q] = -1;
+        const KeyPoint& kp = kps1[q_idx[q]];
+        G->query(kps2, kp.x, kp.y, 20, cand);
+        if (cand.empty()) continue;
+        c.resize(cand.size());
+        for (size_t j = 0; j < cand.size(); ++j) c[j] = desc2 + cand[j] * 32;
+        unsigned d[2], di[2];
+        knn2_stream(desc1 + (size_t)q_idx[q] * 32, c.data(), (int)c.size(), d, di);
+        if (!ratio_pass((float)d[0], (float)d[1], 0.6f)) continue;
+        if ((float)d[0] > 46) continue;
+        out_idx[q] = (int)cand[0]; out_best[q] = (int)cand[di[0]]; out_dist[q] = (int)d[0]; cnt++;
+    }
+    delete G;
+    return cnt;
+}
+
 // ---- CPU baseline driver: n_frames three-camera frames (L, R, W images, each w*h contiguous), n_threads workers,
 // each worker owns its three extractors (as Frame's statics) and runs extract x3 + stereo. Returns seconds. ----
 double ora_bench_frames(const uint8_t* imgs, int n_frames, int w, int h, int nfeatures, float sf, int nlevels, int ini, int mn,

@@ -4,6 +4,7 @@
 //
 //   host_mirror_test <tmp dir>             full check on cuda:0; exit 0 = all equal
 //   host_mirror_test <tmp dir> --no-device asserts the no-CPU-fallback behaviour on a box without a GPU
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -28,6 +29,11 @@ int ora_stereo_match(void* hl, void* hr, const cv::KeyPoint* kl, const uint8_t* 
 int ora_project_match(const cv::KeyPoint* kps, const uint8_t* desc, int n, int W, int H, const float* scale_factors, const float* Rcw, const float* tcw,
                       const float* intr, const float* mp_xyz, const uint8_t* mp_desc, const int* mp_level, int n_mp, float r_threshold, int* out_idx,
                       int* out_dist);
+int ora_fuse_match(const cv::KeyPoint* kps, const uint8_t* desc, int n, int W, int H, const float* sigma2, const float* inv_sigma2, const float* Rcw,
+                   const float* tcw, const float* Ow, const float* intr, const float* depth_left, float bf, const float* mp_xyz, const float* mp_normal,
+                   const uint8_t* mp_desc, const int* mp_level, int n_mp, int* out_idx, int* out_dist);
+int ora_wnd_track(const cv::KeyPoint* kps1, const uint8_t* desc1, const int* q_idx, int n_q, const cv::KeyPoint* kps2, const uint8_t* desc2, int n2, int W,
+                  int H, int* out_idx, int* out_best, int* out_dist);
 int ora_distribute_octree(const cv::KeyPoint* in, int n, int minX, int maxX, int minY, int maxY, int N, cv::KeyPoint* out, int cap);
 }
 
@@ -260,6 +266,32 @@ int main(int argc, char** argv) {
             const int cnt_ref = ora_project_match(ol.kps.data(), ol.desc.data(), nl, 640, 480, frame.LEFT->extractor->mvScaleFactor.data(), R, t,
                                                   frame.LEFT->intr, xyz.data(), md.data(), lvl.data(), (int)mps.size(), r_th, oi.data(), od.data());
             CHECK((int)cnt == cnt_ref && cnt > 500 && mi == oi && mdist == od, "ProjectBunchMapPoints(r=%g): %u vs %d", r_th, cnt, cnt_ref);
+        }
+
+        // ---- Map::Fuse front-end on the LEFT object (kf = this frame: its depth_left / bf), Tracker::Wnd_Track LEFT -> WIDE ----
+        {
+            std::vector<float> nrm;
+            const float Ow[3] = {-t[0], -t[1], -t[2]};   // R = I
+            for (auto& mp : mps) {
+                float v[3] = {mp.xyz[0] - Ow[0], mp.xyz[1] - Ow[1], mp.xyz[2] - Ow[2]};
+                const float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                for (int a = 0; a < 3; ++a) mp.normal[a] = v[a] / len;
+                if (r.range(0, 10) == 0) mp.normal[2] = -mp.normal[2];   // some back-facing
+                nrm.insert(nrm.end(), mp.normal, mp.normal + 3);
+            }
+            std::vector<int> mi, mdist, oi(mps.size()), od(mps.size());
+            const uint cnt = frame.LEFT->FuseMatch(mps, frame.depth_left, Frame::bf(), mi, &mdist);
+            const int cnt_ref = ora_fuse_match(ol.kps.data(), ol.desc.data(), nl, 640, 480, frame.LEFT->extractor->mvLevelSigma2.data(),
+                                               frame.LEFT->extractor->mvInvLevelSigma2.data(), R, t, Ow, frame.LEFT->intr, frame.depth_left.data(), Frame::bf(),
+                                               xyz.data(), nrm.data(), md.data(), lvl.data(), (int)mps.size(), oi.data(), od.data());
+            CHECK((int)cnt == cnt_ref && cnt > 100 && mi == oi && mdist == od, "FuseMatch: %u vs %d", cnt, cnt_ref);
+            std::vector<int> q;
+            for (int i = 0; i < nl; i += 3) q.push_back(i);
+            std::vector<int> wm, wd, wi(q.size()), wb(q.size()), wdd(q.size());
+            const uint wcnt = Wnd_Track(*frame.LEFT, q, *frame.RIGHT, wm, &wd);
+            const int wref = ora_wnd_track(ol.kps.data(), ol.desc.data(), q.data(), (int)q.size(), orr.kps.data(), orr.desc.data(), (int)orr.kps.size(), 640, 480,
+                                           wi.data(), wb.data(), wdd.data());
+            CHECK((int)wcnt == wref && wm == wi && wd == wdd, "Wnd_Track: %u vs %d", wcnt, wref);
         }
 
         // ---- batched rig == per-frame Frame ----

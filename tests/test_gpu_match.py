@@ -139,3 +139,76 @@ def test_projection(api, oracle):
         cnto, oio, odo = oracle.project_match(k, d, 640, 480, E.mvScaleFactor, R, t, [fx, fy, cx, cy], pw, md, lvl, r_th)
         assert cnt == cnto and cnt > 1000
         assert np.array_equal(oi, oio) and np.array_equal(od, odo)
+
+
+def _fuse_scene(oracle_or_api_orb, rng, k, d, n_mp):
+    """MapPoints placed on / near the keypoints of one extracted image, as Map::Fuse meets them."""
+    n = len(k)
+    fx = fy = 955.40503 * 640 / 512; cx, cy = 320.0, 240.0
+    th = 0.015
+    R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], np.float32)
+    t = np.array([0.03, -0.02, 0.05], np.float32)
+    Ow = (-R.T @ t).astype(np.float32)
+    src = rng.integers(0, n, n_mp)
+    z = rng.uniform(2, 50, n_mp).astype(np.float32)
+    u = k["x"][src] + rng.normal(0, 1.2, n_mp).astype(np.float32); v = k["y"][src] + rng.normal(0, 1.2, n_mp).astype(np.float32)
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1).astype(np.float32)
+    pw = ((pc - t) @ R).astype(np.float32)
+    pw[:40, 2] = -5 - pw[:40, 2]                                   # behind the camera
+    view = pw - Ow
+    nrm = (view / np.linalg.norm(view, axis=1, keepdims=True)).astype(np.float32)
+    # rotate some normals away: beyond 60 degrees, and some right on the boundary
+    ang = rng.uniform(0, np.pi / 2, n_mp); ang[100:140] = np.pi / 3
+    perp = np.cross(nrm, np.array([0.3, 1.0, 0.2], np.float32)); perp /= np.linalg.norm(perp, axis=1, keepdims=True)
+    nrm = (nrm * np.cos(ang)[:, None] + perp * np.sin(ang)[:, None]).astype(np.float32)
+    md = d[src].copy()
+    flips = rng.integers(0, 41, n_mp)
+    for m in range(n_mp):
+        bits = rng.choice(256, flips[m], replace=False)
+        np.bitwise_xor.at(md[m], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    lvl = np.clip(k["octave"][src].astype(np.int32) + rng.integers(-1, 2, n_mp), 0, 7).astype(np.int32)
+    depth_left = np.where(rng.random(n) < 0.5, rng.uniform(0, 640, n), -1).astype(np.float32)
+    # make the "stereo" residual small for a share of them so that branch also passes
+    return dict(R=R, t=t, Ow=Ow, K=[fx, fy, cx, cy], pw=pw, nrm=nrm, md=md, lvl=lvl, depth_left=depth_left, u=u, z=z, src=src)
+
+
+@pytest.mark.gpu
+def test_fuse_match(api, oracle):
+    """Map::Fuse matching front-end (src/Map.cpp:478-527): CUDA == oracle, every MapPoint."""
+    img = synth.scene(56)
+    E = api.ORB(2000, 1.2, 8, 28, 15)
+    n, k, d = E.Extract(img)
+    rng = np.random.default_rng(21)
+    S = _fuse_scene(E, rng, k, d, 12000)
+    bf = 955.40503
+    # stereo branch as written compares ur = u - bf / z with depth_left[idx]: give half of the keypoints a value near it
+    ur = S["u"] - bf / S["z"]
+    S["depth_left"][S["src"][::2]] = (ur[::2] + rng.normal(0, 0.4, len(ur[::2]))).astype(np.float32)
+    s2 = E.mvLevelSigma2; is2 = E.mvInvLevelSigma2
+    cnt, oi, od = api.FuseMatch(k, d, 640, 480, s2, is2, S["R"], S["t"], S["Ow"], S["K"], S["depth_left"], bf, S["pw"], S["nrm"], S["md"], S["lvl"])
+    cnto, oio, odo = oracle.fuse_match(k, d, 640, 480, s2, is2, S["R"], S["t"], S["Ow"], S["K"], S["depth_left"], bf, S["pw"], S["nrm"], S["md"], S["lvl"])
+    assert cnt == cnto and cnt > 500, (cnt, cnto)
+    assert np.array_equal(oi, oio) and np.array_equal(od, odo)
+    # both gates are exercised: some matched keypoints carry depth, some do not
+    m = oi[oi >= 0]
+    assert (S["depth_left"][m] >= 0).any() and (S["depth_left"][m] < 0).any()
+    # no MapPoints / no keypoints
+    assert api.FuseMatch(k[:0], d[:0], 640, 480, s2, is2, S["R"], S["t"], S["Ow"], S["K"], S["depth_left"][:0], bf, S["pw"][:5], S["nrm"][:5], S["md"][:5], S["lvl"][:5])[0] == 0
+
+
+@pytest.mark.gpu
+def test_wnd_track(api, oracle):
+    """Tracker::Wnd_Track (src/Tracker.cpp:341-360) between two views of a scene: CUDA == oracle, incl. the reference's
+    first-candidate index."""
+    a = synth.scene(57)
+    b = np.roll(a, (3, -5), (0, 1))                                # second view: small shift
+    E = api.ORB(2000, 1.2, 8, 28, 15)
+    n1, k1, d1 = E.Extract(a)
+    n2, k2, d2 = E.Extract(b)
+    rng = np.random.default_rng(4)
+    q = np.sort(rng.choice(n1, 1200, replace=False)).astype(np.int32)   # keypoints owning a MapPoint
+    cnt, oi, ob, od = api.WndTrack(k1, d1, q, k2, d2, 640, 480)
+    cnto, oio, obo, odo = oracle.wnd_track(k1, d1, q, k2, d2, 640, 480)
+    assert cnt == cnto and cnt > 100, (cnt, cnto)
+    assert np.array_equal(oi, oio) and np.array_equal(ob, obo) and np.array_equal(od, odo)
+    assert (oi[oi >= 0] != ob[oi >= 0]).any()                      # the reference's queryIdx slip is visible in the data
