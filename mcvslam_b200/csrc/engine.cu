@@ -70,7 +70,7 @@ struct mcv_orb {
     bool have_plan = false;
     int cap_images = 0;     // workspace capacity (images)
     int last_images = 0;    // images processed by the last extract
-    DevBuf tabs, src, pyr, blur, score, nz_list, nz_cnt, cell_raw, cell_pts, cell_cnt, arena_a, arena_b, oct_idx, out_pts, out_cnt, kps, desc, counts, seeds, misc;
+    DevBuf tabs, src, pyr, blur, score, nz_list, nz_cnt, cell_raw, cell_pts, cell_cnt, fallback, arena_a, arena_b, oct_idx, out_pts, out_cnt, kps, desc, counts, seeds, misc;
     HostBuf h_stage;
     int last_cap = 0;       // per-image keypoint slots of the last extract (layout of kps/desc)
     int channels = 1;       // input images: 1 = CV_8UC1 gray, 3 = CV_8UC3 BGR (cvtColor fused into the level-0 write)
@@ -227,6 +227,7 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
         if ((st = h->arena_b.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->oct_idx.reserve((size_t)P.cand_per_image * n_images * 2))) return st;
         if ((st = h->cell_cnt.reserve((size_t)P.cells_per_image * n_images * 4))) return st;
+        if ((st = h->fallback.reserve(((size_t)P.cells_per_image * n_images + 4) * 4))) return st;
         if ((st = h->out_pts.reserve((size_t)P.out_per_image * n_images * 4))) return st;
         if ((st = h->out_cnt.reserve((size_t)P.n_levels * n_images * 4 * 2))) return st;   // counts | per-task overflow flags (launch_octree)
         h->cap_images = n_images;
@@ -254,7 +255,7 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
     prof_mark(h, 2);
     n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->nz_list.as<unsigned>(), h->nz_cnt.as<int>(), h->cell_raw.as<uint32_t>(),
-                           h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), n_images, h->stream,
+                           h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->fallback.as<int>(), n_images, h->stream,
                            (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 3] : nullptr);
     if (signal_front) MCV_CUDA(cudaEventRecord(signal_front, h->stream));
     prof_mark(h, 4);
@@ -304,7 +305,7 @@ void mcv_orb_destroy(mcv_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->score, &h->nz_list, &h->nz_cnt, &h->cell_raw, &h->cell_pts, &h->cell_cnt, &h->arena_a, &h->arena_b, &h->oct_idx, &h->out_pts, &h->out_cnt,
+    for (DevBuf* b : {&h->tabs, &h->src, &h->pyr, &h->blur, &h->score, &h->nz_list, &h->nz_cnt, &h->cell_raw, &h->cell_pts, &h->cell_cnt, &h->fallback, &h->arena_a, &h->arena_b, &h->oct_idx, &h->out_pts, &h->out_cnt,
                       &h->kps, &h->desc, &h->counts, &h->seeds, &h->misc})
         b->release();
     h->h_stage.release();

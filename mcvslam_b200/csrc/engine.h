@@ -83,7 +83,7 @@ int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t
                    const int* d_tabs, int n_images, cudaStream_t s);
 int launch_blur(const Plan& P, const uint8_t* d_pyr, uint8_t* d_blur, int n_images, cudaStream_t s);
 int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
-                      uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s, cudaEvent_t after_score = nullptr);
+                      uint32_t* d_cell_pts, int* d_cell_cnt, int* d_fallback, int n_images, cudaStream_t s, cudaEvent_t after_score = nullptr);
 int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
                   uint16_t* d_oct_idx, uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s);
 int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blur, const uint32_t* d_out_pts, const int* d_out_cnt,

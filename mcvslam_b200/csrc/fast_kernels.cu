@@ -101,7 +101,7 @@ __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_belo
 
 __global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
                                                                unsigned* __restrict__ nz_list, int* __restrict__ nz_cnt,
-                                                               const __grid_constant__ Plan P, const __grid_constant__ StripTable T) {
+                                                               const __grid_constant__ Plan P, const __grid_constant__ StripTable T, int Tm) {
     __shared__ unsigned s_q[FS_WARPS][FS_QCAP];
     const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sid = blockIdx.x * FS_WARPS + warp;
@@ -124,7 +124,6 @@ __global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __r
     unsigned colmask = 0;                                   // bit 7 of byte k set iff column x0 + k is inside the region
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (x0 + k >= x_lo && x0 + k < x_hi) colmask |= 0x80u << (8 * k);
-    const int Tm = P.min_th;
     const unsigned add = 255u - (unsigned)Tm, add_lo7 = (add & 0x7fu) * 0x01010101u;
     const bool add_hi = (add & 0x80u) != 0;
     const unsigned lt = (1u << lane) - 1;
@@ -271,7 +270,7 @@ __global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __
 constexpr int ORD_WARPS = 8;
 
 __global__ void __launch_bounds__(32 * ORD_WARPS) k_cell_order(const uint32_t* __restrict__ cell_raw, uint32_t* __restrict__ cell_pts,
-                                                               int* __restrict__ cell_cnt, const __grid_constant__ Plan P) {
+                                                               int* __restrict__ cell_cnt, const __grid_constant__ Plan P, int* __restrict__ fallback) {
     const int img = blockIdx.y, lane = threadIdx.x & 31;
     int cell = blockIdx.x * ORD_WARPS + (threadIdx.x >> 5);
     if (cell >= P.cells_per_image) return;
@@ -281,7 +280,12 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) k_cell_order(const uint32_t* _
     cell -= g.cell_base;
     int* cnt_p = cell_cnt + (size_t)img * P.cells_per_image + g.cell_base + cell;
     const int n = *cnt_p;
-    if (n == 0) return;
+    if (n == 0) {
+        // nothing at iniThFAST: the reference re-runs cv::FAST on this cell with minThFAST (ORBextractor.cc:619-623) -> queue the
+        // cell for k_cell_fallback. fallback[0] = count, fallback[1 + i] = image * cells_per_image + cell index
+        if (fallback && lane == 0) fallback[1 + atomicAdd(&fallback[0], 1)] = img * P.cells_per_image + g.cell_base + cell;
+        return;
+    }
     const size_t off = (size_t)img * P.cand_per_image + g.cand_off + (size_t)cell * g.cell_cap;
     const uint32_t* in = cell_raw + off;
     uint32_t* out = cell_pts + off;
@@ -320,6 +324,86 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) k_cell_order(const uint32_t* _
     if (lane == 0) *cnt_p = kept;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// minThFAST fallback for the cells that came up empty at iniThFAST (ORBextractor.cc:619-623): one warp per queued cell
+// recomputes the cell's score map at minThFAST into a shared-memory tile (ring of zeros = "neighbours outside the cell's own
+// cv::FAST image do not exist"), runs the strict 8-neighbour NMS on it and writes the survivors in row-major order — the
+// order cv::FAST emits them in — straight into cell_pts. The dense pass only ever scores at iniThFAST: on textured images
+// (every cell has an iniThFAST corner) this queue is almost empty and four fifths of the exact scoring work disappears.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FB_WARPS = 4;
+constexpr int FB_MAX_CELL = 78;                  // w_cell, h_cell <= 78: tile of 80 x 80 bytes per warp
+constexpr int FB_TP = FB_MAX_CELL + 2;
+
+__global__ void __launch_bounds__(32 * FB_WARPS) k_cell_fallback(const uint8_t* __restrict__ pyr, const int* __restrict__ fallback,
+                                                                uint32_t* __restrict__ cell_pts, int* __restrict__ cell_cnt,
+                                                                const __grid_constant__ Plan P) {
+    __shared__ uint8_t s_tile[FB_WARPS][FB_TP * FB_TP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = fallback[0];
+    const unsigned lt = (1u << lane) - 1;
+    uint8_t* tile = s_tile[warp];
+    const int Tm = P.min_th;
+    for (int item = blockIdx.x * FB_WARPS + warp; item < n_items; item += gridDim.x * FB_WARPS) {
+        const int code = fallback[1 + item];
+        const int img = code / P.cells_per_image;
+        int cell = code - img * P.cells_per_image;
+        int level = 0;
+        while (level + 1 < P.n_levels && cell >= P.lv[level + 1].cell_base) ++level;
+        const LevelGeom& g = P.lv[level];
+        cell -= g.cell_base;
+        const int cy = cell / g.n_cols, cx = cell - cy * g.n_cols;
+        // the cell's own detection region (level coordinates), clipped to the level's
+        const int x0 = EDGE_THRESHOLD + cx * g.w_cell, y0 = EDGE_THRESHOLD + cy * g.h_cell;
+        const int cw = min(g.w_cell, g.w - EDGE_THRESHOLD - x0), ch = min(g.h_cell, g.h - EDGE_THRESHOLD - y0);
+        const int pitch = g.pitch;
+        const uint8_t* src = pyr + (size_t)img * P.pyr_bytes + g.img_off;
+        __syncwarp();
+        for (int i = lane; i < FB_TP * (ch + 2); i += 32) tile[i] = 0;
+        __syncwarp();
+        if (cw > 0 && ch > 0) {
+            const int n_px = cw * ch;
+            for (int i0 = 0; i0 < n_px; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < n_px) {
+                    const int ry = i / cw, rx = i - ry * cw;
+                    const uint8_t* c = src + (size_t)(y0 + ry) * pitch + (x0 + rx);
+                    // same necessary condition as the dense pass: two compass points 90 degrees apart differ by more than T
+                    const int v = c[0];
+                    const bool vert = abs((int)c[-3 * pitch] - v) > Tm || abs((int)c[3 * pitch] - v) > Tm;
+                    const bool horz = abs((int)c[-3] - v) > Tm || abs((int)c[3] - v) > Tm;
+                    if (vert && horz) {
+                        const int sc = fast_score16(c, pitch);
+                        if (sc >= Tm) tile[(ry + 1) * FB_TP + rx + 1] = (uint8_t)sc;
+                    }
+                }
+            }
+            __syncwarp();
+            uint32_t* out = cell_pts + (size_t)img * P.cand_per_image + g.cand_off + (size_t)cell * g.cell_cap;
+            int kept = 0;
+            for (int i0 = 0; i0 < n_px; i0 += 32) {
+                const int i = i0 + lane;
+                bool keep = false;
+                int ry = 0, rx = 0, sc = 0;
+                if (i < n_px) {
+                    ry = i / cw; rx = i - ry * cw;
+                    const uint8_t* t = tile + (ry + 1) * FB_TP + rx + 1;
+                    sc = t[0];
+                    if (sc) {
+                        const int m = max(max(max((int)t[-1], (int)t[1]), max((int)t[-FB_TP], (int)t[FB_TP])),
+                                          max(max((int)t[-FB_TP - 1], (int)t[-FB_TP + 1]), max((int)t[FB_TP - 1], (int)t[FB_TP + 1])));
+                        keep = sc > m;
+                    }
+                }
+                const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                if (keep) out[kept + __popc(mk & lt)] = pack_pt(x0 + rx - BORDER, y0 + ry - BORDER, sc);
+                kept += __popc(mk);
+            }
+            if (lane == 0) cell_cnt[(size_t)img * P.cells_per_image + g.cell_base + cell] = kept;
+        }
+    }
+}
+
 // strip table shared by k_fast_score and k_nms_sparse; its total is Plan::n_fast_strips (fast_strip_table is also what
 // build_plan uses to size the list segments)
 int fast_strip_table(const Plan& P, StripTable& T) {
@@ -335,17 +419,28 @@ int fast_strip_table(const Plan& P, StripTable& T) {
 }
 
 int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
-                      uint32_t* d_cell_pts, int* d_cell_cnt, int n_images, cudaStream_t s, cudaEvent_t after_score) {
+                      uint32_t* d_cell_pts, int* d_cell_cnt, int* d_fallback, int n_images, cudaStream_t s, cudaEvent_t after_score) {
     StripTable T{};
     const int n = fast_strip_table(P, T);
+    // two-pass thresholds: dense scoring at iniThFAST, minThFAST only for the cells that stay empty (k_cell_fallback). Needs the
+    // cell to fit the fallback tile; otherwise (and when both thresholds agree) the dense pass scores at minThFAST as before
+    // and k_cell_order applies the "any corner >= ini ? ini : min" rule on the survivors.
+    const bool two_pass = d_fallback && P.ini_th > P.min_th && P.max_cell_w <= FB_MAX_CELL && P.max_cell_h <= FB_MAX_CELL;
     cudaMemsetAsync(d_cell_cnt, 0, (size_t)n_images * P.cells_per_image * sizeof(int), s);
+    if (two_pass) cudaMemsetAsync(d_fallback, 0, sizeof(int), s);
     if (n > 0)
-        k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_score, d_nz_list, d_nz_cnt, P, T);
+        k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_score, d_nz_list, d_nz_cnt, P, T,
+                                                                                             two_pass ? P.ini_th : P.min_th);
     if (after_score) cudaEventRecord(after_score, s);   // stage boundary for mcv_rig_stage_ms
     if (n > 0)
         k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(d_score, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
-    k_cell_order<<<dim3((P.cells_per_image + ORD_WARPS - 1) / ORD_WARPS, n_images), 32 * ORD_WARPS, 0, s>>>(d_cell_raw, d_cell_pts, d_cell_cnt, P);
-    return 3;
+    k_cell_order<<<dim3((P.cells_per_image + ORD_WARPS - 1) / ORD_WARPS, n_images), 32 * ORD_WARPS, 0, s>>>(d_cell_raw, d_cell_pts, d_cell_cnt, P,
+                                                                                                          two_pass ? d_fallback : nullptr);
+    if (!two_pass) return 3;
+    const int max_items = P.cells_per_image * n_images;
+    const int ctas = std::max(1, std::min((max_items + FB_WARPS - 1) / FB_WARPS, NUM_SMS * 4));
+    k_cell_fallback<<<ctas, 32 * FB_WARPS, 0, s>>>(d_pyr, d_fallback, d_cell_pts, d_cell_cnt, P);
+    return 4;
 }
 
 }  // namespace mcv
