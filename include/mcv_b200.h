@@ -251,6 +251,23 @@ mcv_status mcv_fuse_match(const mcv_keypoint* kps, const uint8_t* desc, int n, i
 mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1, const int32_t* q_idx, int n_q, const mcv_keypoint* kps2,
                          const uint8_t* desc2, int n2, int w, int hgt, int32_t* out_idx, int32_t* out_best, int32_t* out_dist, int* n_matched);
 
+/* Object::ComputeBow (src/Object.cpp:238-247): DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
+ * (modules/DBow3/src/Vocabulary.cpp:572-672). The vocabulary is handed over once as flat arrays — what a maintainer gets by
+ * walking DBoW3's m_nodes after Vocabulary::load: child_off [n_nodes+1] / child_ids = m_nodes[i].children in stored order
+ * (node 0 = root), node_desc [n_nodes][32] = m_nodes[i].descriptor, word_id / weight [n_nodes] = the leaf fields, L = m_L,
+ * weighting = DBoW3::WeightingType (0 TF_IDF, 1 TF, 2 IDF, 3 BINARY), norm = what ScoringObject::mustNormalize reports
+ * (0 none, 1 L1, 2 L2; orbvoc: TF_IDF + L1). The tree lives in device memory; the descent (k Hamming distances per level) runs
+ * on the GPU, the std::map assembly of the two vectors — whose insertion order defines the double sums — on the host. */
+typedef struct mcv_voc mcv_voc;
+mcv_status mcv_voc_create(int n_nodes, const int32_t* child_off, const uint32_t* child_ids, const uint8_t* node_desc, const int32_t* word_id,
+                          const double* weight, int L, int weighting, int norm, int device, mcv_voc** out);
+void mcv_voc_destroy(mcv_voc* v);
+/* Per feature: out_word / out_weight / out_nid (each may be NULL). BowVector: bow_ids ascending + bow_vals, *n_bow entries (<= n).
+ * FeatureVector flattened as mcv_dbow_match takes it: fv_nodes ascending [*n_fv], fv_off [*n_fv + 1], fv_idx [<= n]. Buffers
+ * must hold n (+1 for fv_off) entries. */
+mcv_status mcv_bow_transform(mcv_voc* v, const uint8_t* desc, int n, int levelsup, int32_t* out_word, double* out_weight, uint32_t* out_nid,
+                             uint32_t* bow_ids, double* bow_vals, int* n_bow, uint32_t* fv_nodes, int32_t* fv_off, int32_t* fv_idx, int* n_fv);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Test / measurement taps (used by tests/ and bench.py only).
  * ---------------------------------------------------------------------------------------------------------- */

@@ -31,7 +31,7 @@ EXPORTS = [
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
     "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_set_input_channels", "mcv_orb_set_input_channels", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
-    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
+    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
 ]
 
@@ -105,6 +105,10 @@ def lib():
         L.mcv_project_match.argtypes = [vp, vp, i, i, i, vp, i, vp, vp, vp, vp, vp, vp, i, f, vp, vp, C.POINTER(i)]
         L.mcv_fuse_match.argtypes = [vp, vp, i, i, i, vp, vp, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, i, vp, vp, C.POINTER(i)]
         L.mcv_wnd_track.argtypes = [vp, vp, i, vp, i, vp, vp, i, i, i, vp, vp, vp, C.POINTER(i)]
+        L.mcv_voc_create.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(vp)]
+        L.mcv_voc_destroy.argtypes = [vp]
+        L.mcv_voc_destroy.restype = None
+        L.mcv_bow_transform.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, C.POINTER(i)]
         L.mcv_debug_sincosf.argtypes = [vp, i, vp, vp]
         L.mcv_debug_fast_atan2.argtypes = [vp, vp, i, vp]
         L.mcv_debug_level_keypoints.argtypes = [vp, i, i, i, vp, i, C.POINTER(i)]
@@ -327,8 +331,11 @@ class Matcher:
 
     @staticmethod
     def DBowMatch(desp1, bow_feat1, desp2, bow_feat2):
-        """bow_feat*: dict node_id -> list of feature indices (DBoW3::FeatureVector)."""
+        """bow_feat*: dict node_id -> list of feature indices (DBoW3::FeatureVector), or the flattened triple
+        (fv_nodes, fv_off, fv_idx) that Vocabulary.transform returns."""
         def flat(fv):
+            if isinstance(fv, tuple):
+                return np.ascontiguousarray(fv[0], np.uint32), np.ascontiguousarray(fv[1], np.int32), np.ascontiguousarray(fv[2], np.int32)
             ids = np.array(sorted(fv.keys()), np.uint32)
             off = np.zeros(len(ids) + 1, np.int32)
             idx = []
@@ -394,6 +401,41 @@ def WndTrack(kps1, desps1, q_idx, kps2, desps2, w, h):
     _check(lib().mcv_wnd_track(_p(kps1), _p(desps1), len(kps1), _p(q), len(q), _p(kps2), _p(desps2), len(kps2), w, h, _p(oi), _p(ob), _p(od),
                                C.byref(cnt)))
     return cnt.value, oi, ob, od
+
+
+class Vocabulary:
+    """DBoW3::Vocabulary reduced to what Object::ComputeBow needs (src/Object.cpp:238-247): transform(). `voc` = the flat arrays
+    (child_off, child_ids, node_desc, word_id, weight, L, weighting, norm) described in include/mcv_b200.h."""
+
+    def __init__(self, voc, device=0):
+        co = np.ascontiguousarray(voc["child_off"], np.int32); ci = np.ascontiguousarray(voc["child_ids"], np.uint32)
+        nd = _u8(voc["node_desc"]); wi = np.ascontiguousarray(voc["word_id"], np.int32); ww = np.ascontiguousarray(voc["weight"], np.float64)
+        self._v = C.c_void_p()
+        _check(lib().mcv_voc_create(len(wi), _p(co), _p(ci), _p(nd), _p(wi), _p(ww), int(voc["L"]), int(voc["weighting"]), int(voc["norm"]), device,
+                                    C.byref(self._v)))
+
+    def close(self):
+        if getattr(self, "_v", None) and self._v.value:
+            lib().mcv_voc_destroy(self._v)
+            self._v = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform(self, desps, levelsup=4):
+        """voc.transform(v_desps, bow_vector, bow_feature, levelsup). Returns dict(word, weight, nid, bow_ids, bow_vals, fv_nodes,
+        fv_off, fv_idx) — fv_* is the FeatureVector in the flattened form Matcher.DBowMatch takes."""
+        d = _u8(desps); n = len(d)
+        ow = np.zeros(n, np.int32); owt = np.zeros(n, np.float64); onid = np.zeros(n, np.uint32)
+        bi = np.zeros(n + 1, np.uint32); bv = np.zeros(n + 1, np.float64); fn = np.zeros(n + 1, np.uint32); fo = np.zeros(n + 2, np.int32); fi = np.zeros(n + 1, np.int32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        _check(lib().mcv_bow_transform(self._v, _p(d), n, levelsup, _p(ow), _p(owt), _p(onid), _p(bi), _p(bv), C.byref(nb), _p(fn), _p(fo), _p(fi), C.byref(nf)))
+        k, m = nb.value, nf.value
+        return dict(word=ow, weight=owt, nid=onid, bow_ids=bi[:k].copy(), bow_vals=bv[:k].copy(), fv_nodes=fn[:m].copy(), fv_off=fo[:m + 1].copy(),
+                    fv_idx=fi[:fo[m]].copy())
 
 
 class Rig:

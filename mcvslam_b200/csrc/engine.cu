@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <cfloat>
 
 namespace mcv {
@@ -750,6 +751,103 @@ mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1,
     MCV_CUDA(cudaMemcpyAsync(out_dist, b_od.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaStreamSynchronize(s));
     if (n_matched) { int c = 0; for (int q = 0; q < n_q; ++q) c += out_idx[q] >= 0; *n_matched = c; }
+    return MCV_OK;
+}
+
+// ---- Object::ComputeBow: DBoW3 vocabulary on the device + Vocabulary::transform ----
+struct mcv_voc {
+    int device = 0, n_nodes = 0, L = 0, weighting = 0, norm = 1;
+    DevBuf child_off, child_ids, node_desc, feat, leaf, nid;
+    std::vector<int32_t> word_id, h_child_off;
+    std::vector<double> weight;
+};
+
+mcv_status mcv_voc_create(int n_nodes, const int32_t* child_off, const uint32_t* child_ids, const uint8_t* node_desc, const int32_t* word_id,
+                          const double* weight, int L, int weighting, int norm, int device, mcv_voc** out) {
+    if (!out) return MCV_ERR_BAD_ARG;
+    *out = nullptr;
+    if (n_nodes < 1 || !child_off || !node_desc || !word_id || !weight || L < 0 || weighting < 0 || weighting > 3 || norm < 0 || norm > 2) return MCV_ERR_BAD_ARG;
+    if (child_off[0] != 0) return MCV_ERR_BAD_ARG;
+    for (int i = 0; i < n_nodes; ++i) if (child_off[i + 1] < child_off[i] || child_off[i + 1] - child_off[i] >= (1 << 20)) return MCV_ERR_BAD_ARG;
+    const int n_edges = child_off[n_nodes];
+    if (n_edges > 0 && !child_ids) return MCV_ERR_BAD_ARG;
+    for (int e = 0; e < n_edges; ++e) if (child_ids[e] == 0 || child_ids[e] >= (uint32_t)n_nodes) return MCV_ERR_BAD_ARG;
+    if (mcv_device_count() <= device || device < 0) { set_error("no such CUDA device"); return MCV_ERR_NO_DEVICE; }
+    MCV_CUDA(cudaSetDevice(device));
+    mcv_voc* v = new mcv_voc();
+    v->device = device; v->n_nodes = n_nodes; v->L = L; v->weighting = weighting; v->norm = norm;
+    v->word_id.assign(word_id, word_id + n_nodes); v->weight.assign(weight, weight + n_nodes); v->h_child_off.assign(child_off, child_off + n_nodes + 1);
+    mcv_status st;
+    if ((st = v->child_off.reserve((size_t)(n_nodes + 1) * 4)) || (st = v->child_ids.reserve(std::max<size_t>(4, (size_t)n_edges * 4))) ||
+        (st = v->node_desc.reserve((size_t)n_nodes * 32))) { delete v; return st; }
+    cudaMemcpy(v->child_off.p, child_off, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice);
+    if (n_edges) cudaMemcpy(v->child_ids.p, child_ids, (size_t)n_edges * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->node_desc.p, node_desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice);
+    MCV_CUDA(cudaGetLastError());
+    *out = v;
+    return MCV_OK;
+}
+
+void mcv_voc_destroy(mcv_voc* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    for (DevBuf* b : {&v->child_off, &v->child_ids, &v->node_desc, &v->feat, &v->leaf, &v->nid}) b->release();
+    delete v;
+}
+
+mcv_status mcv_bow_transform(mcv_voc* v, const uint8_t* desc, int n, int levelsup, int32_t* out_word, double* out_weight, uint32_t* out_nid,
+                             uint32_t* bow_ids, double* bow_vals, int* n_bow, uint32_t* fv_nodes, int32_t* fv_off, int32_t* fv_idx, int* n_fv) {
+    if (!v || n < 0 || !n_bow || !n_fv || (n > 0 && (!desc || !bow_ids || !bow_vals || !fv_nodes || !fv_off || !fv_idx))) return MCV_ERR_BAD_ARG;
+    *n_bow = 0; *n_fv = 0;
+    if (fv_off) fv_off[0] = 0;
+    if (n == 0) return MCV_OK;
+    MCV_CUDA(cudaSetDevice(v->device));
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    if ((st = v->feat.reserve((size_t)n * 32)) || (st = v->leaf.reserve((size_t)n * 4)) || (st = v->nid.reserve((size_t)n * 4))) return st;
+    MCV_CUDA(cudaMemcpyAsync(v->feat.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    launch_bow_descend(v->feat.as<uint8_t>(), n, v->child_off.as<int32_t>(), v->child_ids.as<uint32_t>(), v->node_desc.as<uint8_t>(), v->L - levelsup,
+                       std::max(v->L, 1) + 32, v->leaf.as<uint32_t>(), v->nid.as<uint32_t>(), s);
+    MCV_CUDA(cudaGetLastError());
+    std::vector<uint32_t> leaf(n), nid(n);
+    MCV_CUDA(cudaMemcpyAsync(leaf.data(), v->leaf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(nid.data(), v->nid.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    // BowVector / FeatureVector assembly (Vocabulary.cpp:586-631, BowVector.cpp, FeatureVector.cpp): std::map insertions in
+    // feature order — the order the weights of one word are summed in is part of the (double) result
+    std::map<uint32_t, double> bow;
+    std::map<uint32_t, std::vector<int32_t>> fv;
+    const bool tf = v->weighting == 0 || v->weighting == 1;
+    for (int i = 0; i < n; ++i) {
+        if (v->h_child_off[leaf[i]] != v->h_child_off[leaf[i] + 1]) { set_error("bow_transform: descent ended on an inner node (malformed vocabulary)"); return MCV_ERR_BAD_ARG; }
+        const uint32_t wid = (uint32_t)v->word_id[leaf[i]];
+        const double w = v->weight[leaf[i]];
+        if (out_word) out_word[i] = (int32_t)wid;
+        if (out_weight) out_weight[i] = w;
+        if (out_nid) out_nid[i] = nid[i];
+        if (!(w > 0)) continue;                        // stopped word
+        auto it = bow.lower_bound(wid);
+        if (it != bow.end() && !(wid < it->first)) { if (tf) it->second += w; }
+        else bow.insert(it, std::make_pair(wid, w));
+        fv[nid[i]].push_back(i);
+    }
+    if (tf && !bow.empty() && v->norm == 0) {
+        const double nd = (double)bow.size();
+        for (auto& e : bow) e.second /= nd;
+    }
+    if (v->norm != 0) {
+        double norm = 0.0;
+        if (v->norm == 1) { for (auto& e : bow) norm += fabs(e.second); }
+        else { for (auto& e : bow) norm += e.second * e.second; norm = sqrt(norm); }
+        if (norm > 0.0) for (auto& e : bow) e.second /= norm;
+    }
+    int k = 0;
+    for (auto& e : bow) { bow_ids[k] = e.first; bow_vals[k] = e.second; ++k; }
+    int m = 0, at = 0;
+    for (auto& e : fv) { fv_nodes[m] = e.first; fv_off[m] = at; for (int32_t f : e.second) fv_idx[at++] = f; ++m; }
+    fv_off[m] = at;
+    *n_bow = k; *n_fv = m;
     return MCV_OK;
 }
 

@@ -115,6 +115,8 @@ int launch_fuse_match(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, i
                       int n_mp, int32_t* d_idx, int32_t* d_dist, cudaStream_t s);
 int launch_wnd_track(const mcv_keypoint* d_kps1, const uint8_t* d_desc1, const int32_t* d_qidx, int n_q, const mcv_keypoint* d_kps2,
                      const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_idx, int32_t* d_best, int32_t* d_dist, cudaStream_t s);
+int launch_bow_descend(const uint8_t* d_desc, int n, const int32_t* d_child_off, const uint32_t* d_child_ids, const uint8_t* d_node_desc,
+                       int nid_level, int max_depth, uint32_t* d_leaf, uint32_t* d_nid, cudaStream_t s);
 int launch_debug_sincosf(const float* d_a, int n, float* d_s, float* d_c, cudaStream_t s);
 int launch_debug_atan2(const float* d_y, const float* d_x, int n, float* d_o, cudaStream_t s);
 int launch_popc_peak(int iters, unsigned* d_sink, int blocks, int threads, cudaStream_t s);

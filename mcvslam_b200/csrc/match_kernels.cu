@@ -355,6 +355,45 @@ int launch_wnd_track(const mcv_keypoint* d_kps1, const uint8_t* d_desc1, const i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// DBoW3::Vocabulary::transform's tree descent (modules/DBow3/src/Vocabulary.cpp:641-672) for a batch of features: one warp per
+// feature, lanes = children of the current node (k = 10 in orbvoc). The reference keeps the FIRST child with the smallest
+// distance (strict '<'), so the key is (distance, position in the children list). out_leaf = the leaf node reached,
+// out_nid = the node passed at depth nid_level = L - levelsup (0 = root when nid_level <= 0).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bow_descend(const uint8_t* __restrict__ desc, int n, const int32_t* __restrict__ child_off,
+                                                     const uint32_t* __restrict__ child_ids, const uint8_t* __restrict__ node_desc,
+                                                     int nid_level, int max_depth, uint32_t* __restrict__ out_leaf, uint32_t* __restrict__ out_nid) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)i * 32));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)i * 32 + 16));
+    unsigned node = 0, nid = 0;
+    for (int level = 1; level <= max_depth; ++level) {      // max_depth bounds a malformed (cyclic) child table
+        const int lo = child_off[node], hi = child_off[node + 1];
+        if (lo == hi) break;                                 // isLeaf()
+        unsigned best = 0xffffffffu;
+        for (int c = lo + lane; c < hi; c += 32) {
+            const unsigned id = child_ids[c];
+            const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(node_desc + (size_t)id * 32));
+            const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(node_desc + (size_t)id * 32 + 16));
+            best = min(best, ((unsigned)hamming256(a0, a1, b0, b1) << 20) | (unsigned)(c - lo));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        node = child_ids[lo + (int)(best & 0xfffffu)];
+        if (level == nid_level) nid = node;
+    }
+    if (lane == 0) { out_leaf[i] = node; out_nid[i] = nid; }
+}
+
+int launch_bow_descend(const uint8_t* d_desc, int n, const int32_t* d_child_off, const uint32_t* d_child_ids, const uint8_t* d_node_desc,
+                       int nid_level, int max_depth, uint32_t* d_leaf, uint32_t* d_nid, cudaStream_t s) {
+    if (n <= 0) return 0;
+    k_bow_descend<<<(n + 7) / 8, 256, 0, s>>>(d_desc, n, d_child_off, d_child_ids, d_node_desc, nid_level, max_depth, d_leaf, d_nid);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // test taps + integer-pipe peak
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_debug_sincosf(const float* a, int n, float* s, float* c) {

@@ -357,6 +357,55 @@ class Matcher {
 // ---------------------------------------------------------------------------------------------------------
 // Object / Frame: the callers either side of the path, reduced to what the path reads and writes.
 // ---------------------------------------------------------------------------------------------------------
+}  // namespace MCVSLAM
+
+// DBoW3 as far as Object::ComputeBow / Matcher::DBowMatch use it (modules/DBow3/src/{BowVector,FeatureVector,Vocabulary}.h)
+namespace DBoW3 {
+typedef unsigned int WordId;
+typedef double WordValue;
+typedef unsigned int NodeId;
+enum WeightingType { TF_IDF, TF, IDF, BINARY };
+enum LNorm { L1, L2 };
+class BowVector : public std::map<WordId, WordValue> {};
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int>> {};
+
+// The vocabulary tree lives in device memory; it is built from the flat arrays a maintainer gets by walking the real
+// DBoW3::Vocabulary's nodes once after load() (INTEGRATION.md shows the loop).
+class Vocabulary {
+   public:
+    Vocabulary() {}
+    Vocabulary(int n_nodes, const int32_t* child_off, const uint32_t* child_ids, const uint8_t* node_desc, const int32_t* word_id, const double* weight,
+               int L, WeightingType weighting, int norm /* 0 none, 1 L1, 2 L2 */, int device = 0) {
+        mcv_voc* raw = nullptr;
+        if (mcv_voc_create(n_nodes, child_off, child_ids, node_desc, word_id, weight, L, (int)weighting, norm, device, &raw) != MCV_OK)
+            throw std::runtime_error(std::string("Vocabulary: ") + mcv_last_error());
+        h.reset(raw, mcv_voc_destroy);
+    }
+    bool empty() const { return !h; }
+    // void transform(const std::vector<cv::Mat>& features, BowVector& v, FeatureVector& fv, int levelsup) const — Vocabulary.cpp:572-633
+    void transform(const std::vector<cv::Mat>& features, BowVector& v, FeatureVector& fv, int levelsup) const {
+        v.clear(); fv.clear();
+        if (empty()) return;
+        const int n = (int)features.size();
+        std::vector<uint8_t> d((size_t)n * 32 + 32);
+        for (int i = 0; i < n; ++i) memcpy(&d[(size_t)i * 32], features[i].data, 32);
+        std::vector<uint32_t> bi((size_t)n + 1), fn((size_t)n + 1);
+        std::vector<double> bv((size_t)n + 1);
+        std::vector<int32_t> fo((size_t)n + 2), fi((size_t)n + 1);
+        int nb = 0, nf = 0;
+        if (mcv_bow_transform(h.get(), d.data(), n, levelsup, nullptr, nullptr, nullptr, bi.data(), bv.data(), &nb, fn.data(), fo.data(), fi.data(), &nf) != MCV_OK)
+            throw std::runtime_error(std::string("Vocabulary::transform: ") + mcv_last_error());
+        for (int k = 0; k < nb; ++k) v.insert(v.end(), std::make_pair(bi[k], bv[k]));
+        for (int m = 0; m < nf; ++m) fv.insert(fv.end(), std::make_pair(fn[m], std::vector<unsigned int>(fi.begin() + fo[m], fi.begin() + fo[m + 1])));
+    }
+
+   private:
+    std::shared_ptr<mcv_voc> h;
+};
+}  // namespace DBoW3
+
+namespace MCVSLAM {
+
 struct MapPointView {      // what ProjectBunchMapPoints / Map::Fuse read of a MapPoint: GetWorldPos(), GetDesp(), level, GetNormalVector()
     float xyz[3];
     uint8_t desp[32];
@@ -421,10 +470,22 @@ class Object {
         return (uint)cnt;
     }
 
+    // Object::ComputeBow (src/Object.cpp:238-247): voc.transform(v_desps, bow_vector, bow_feature, 4), once per object
+    void ComputeBow(const DBoW3::Vocabulary& voc) {
+        if (is_bowed) return;
+        std::vector<cv::Mat> v_desps;
+        for (int i = 0, sz = desps.rows; i < sz; i++) v_desps.push_back(desps.row(i));
+        voc.transform(v_desps, bow_vector, bow_feature, 4);
+        is_bowed = true;
+    }
+
     cv::Mat img;
     Keypoints kps;
     Desps desps;
     ORB* extractor = nullptr;
+    DBoW3::BowVector bow_vector;
+    DBoW3::FeatureVector bow_feature;
+    bool is_bowed = false;
     float Rcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcw[3] = {0, 0, 0}, intr[4] = {1, 1, 0, 0};
 };
 

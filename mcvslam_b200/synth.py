@@ -46,3 +46,41 @@ def descriptors(n, seed, low_entropy=False):
     rng = np.random.default_rng(seed)
     hi = 4 if low_entropy else 256
     return rng.integers(0, hi, (n, 32), dtype=np.uint8)
+
+
+def random_vocabulary(seed, K=10, L=4, weighting=0, norm=1, stop_fraction=0.02, ragged=True):
+    """A synthetic DBoW3-shaped vocabulary (the real orbvoc.dbow3 is K=10, L=6, 1 082 073 nodes; same structure): a K-ary tree of
+    depth L built like HKmeansStep numbers its nodes (children of a node get consecutive ids), node descriptors = parent's with
+    bits flipped (so descents are meaningful and ties between siblings occur), random positive leaf weights with a few zero
+    ("stopped") words. Flat arrays: child_off [n+1], child_ids, node_desc [n][32], word_id [n], weight [n] (float64).
+    weighting: 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY; norm: 0 none, 1 L1, 2 L2."""
+    rng = np.random.default_rng(seed)
+    desc = [rng.integers(0, 256, 32, dtype=np.uint8)]
+    children = [[]]
+    level = [0]
+    frontier = [0]
+    for depth in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            k = K if not ragged or depth == 1 else int(rng.integers(max(2, K - 3), K + 1))
+            for _ in range(k):
+                i = len(desc)
+                d = desc[p].copy()
+                nb = int(rng.integers(2, 40))
+                bits = rng.choice(256, nb, replace=False)
+                np.bitwise_xor.at(d, bits // 8, (1 << (bits % 8)).astype(np.uint8))
+                if rng.random() < 0.05 and children[p]:
+                    d = desc[children[p][-1]].copy()          # duplicate sibling: exact distance tie
+                desc.append(d); children.append([]); level.append(depth); children[p].append(i); nxt.append(i)
+        frontier = nxt
+    n = len(desc)
+    child_off = np.zeros(n + 1, np.int32); ids = []
+    for i in range(n):
+        child_off[i + 1] = child_off[i] + len(children[i]); ids += children[i]
+    word_id = np.full(n, -1, np.int32); weight = np.zeros(n, np.float64)
+    leaves = [i for i in range(n) if not children[i]]
+    word_id[leaves] = np.arange(len(leaves))
+    w = rng.uniform(0.1, 9.0, len(leaves)); w[rng.random(len(leaves)) < stop_fraction] = 0.0
+    weight[leaves] = w if weighting in (0, 2) else np.where(w > 0, 1.0, 0.0)
+    return dict(child_off=child_off, child_ids=np.array(ids, np.uint32), node_desc=np.stack(desc), word_id=word_id, weight=weight, L=L, K=K,
+                weighting=weighting, norm=norm)

@@ -283,6 +283,25 @@ def wnd_track(kps1, desc1, q_idx, kps2, desc2, W, H):
     return cnt, oi, ob, od
 
 
+def bow_transform(desc, voc, levelsup=4):
+    """DBoW3::Vocabulary::transform (modules/DBow3/src/Vocabulary.cpp:572-672) as Object::ComputeBow calls it. `voc` = dict of the
+    flat vocabulary arrays (mcvslam_b200.synth.random_vocabulary layout). Returns dict(word, weight, nid, bow_ids, bow_vals,
+    fv_nodes, fv_off, fv_idx)."""
+    desc = _u8(desc); n = len(desc)
+    co = np.ascontiguousarray(voc["child_off"], np.int32); ci = np.ascontiguousarray(voc["child_ids"], np.uint32)
+    nd = _u8(voc["node_desc"]); wi = np.ascontiguousarray(voc["word_id"], np.int32); ww = np.ascontiguousarray(voc["weight"], np.float64)
+    ow = np.zeros(n, np.int32); owt = np.zeros(n, np.float64); onid = np.zeros(n, np.uint32)
+    bi = np.zeros(n + 1, np.uint32); bv = np.zeros(n + 1, np.float64); fn = np.zeros(n + 1, np.uint32); fo = np.zeros(n + 2, np.int32); fi = np.zeros(n + 1, np.int32)
+    nfv = C.c_int(0)
+    L = lib()
+    L.ora_bow_transform.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p] * 8 + [C.POINTER(C.c_int)]
+    k = L.ora_bow_transform(_p(desc), n, _p(co), _p(ci), _p(nd), _p(wi), _p(ww), int(voc["L"]), levelsup, int(voc["weighting"]), int(voc["norm"]),
+                            _p(ow), _p(owt), _p(onid), _p(bi), _p(bv), _p(fn), _p(fo), _p(fi), C.byref(nfv))
+    m = nfv.value
+    return dict(word=ow, weight=owt, nid=onid, bow_ids=bi[:k].copy(), bow_vals=bv[:k].copy(), fv_nodes=fn[:m].copy(), fv_off=fo[:m + 1].copy(),
+                fv_idx=fi[:fo[m]].copy())
+
+
 def bench_frames(imgs, nfeatures, sf, nlevels, ini, mn, bf, b, n_threads, repeat=1):
     """imgs: (n_frames, 3, H, W) u8. Returns (seconds, total_keypoints)."""
     imgs = _u8(imgs)

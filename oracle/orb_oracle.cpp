@@ -17,6 +17,8 @@
 #include <memory>
 #include <queue>
 #include <thread>
+#include <map>
+#include <limits>
 #include <vector>
 
 #include "ora_primitives.hpp"
@@ -739,6 +741,66 @@ int ora_wnd_track(const KeyPoint* kps1, const uint8_t* desc1, const int* q_idx, 
     }
     delete G;
     return cnt;
+}
+
+// ---- Object::ComputeBow (src/Object.cpp:238-247) = DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
+// (modules/DBow3/src/Vocabulary.cpp:572-633) on a vocabulary passed as flat arrays: child_off/child_ids = m_nodes[i].children in
+// stored order, node_desc = m_nodes[i].descriptor (32 B), word_id / weight = leaf fields, L = m_L. Per feature the tree descent
+// of Vocabulary.cpp:641-672 (strict '<': the first of several equally close children wins), then BowVector::addWeight /
+// addIfNotExist and FeatureVector::addFeature in feature order on real std::maps, then the /= size or BowVector::normalize.
+// Outputs: per-feature word / weight / node, the BowVector as (ids ascending, values) and the FeatureVector flattened the way
+// Matcher::DBowMatch consumes it. Returns the BowVector size; *n_fv = FeatureVector size.
+int ora_bow_transform(const uint8_t* desc, int n, const int* child_off, const unsigned* child_ids, const uint8_t* node_desc, const int* word_id,
+                      const double* weight, int L, int levelsup, int weighting, int norm_type /* 0 none, 1 L1, 2 L2 */, int* out_word, double* out_w,
+                      unsigned* out_nid, unsigned* bow_ids, double* bow_vals, unsigned* fv_nodes, int* fv_off, int* fv_idx, int* n_fv) {
+    map<unsigned, double> v;
+    map<unsigned, vector<unsigned>> fv;
+    const int nid_level = L - levelsup;
+    for (int i = 0; i < n; ++i) {
+        unsigned nid = 0, final_id = 0;   // nid_level <= 0: root
+        int current_level = 0;
+        do {
+            ++current_level;
+            double best_d = std::numeric_limits<double>::max();
+            const unsigned node = final_id;
+            for (int c = child_off[node]; c < child_off[node + 1]; ++c) {
+                const unsigned id = child_ids[c];
+                const double d = (double)hamming256(desc + (size_t)i * 32, node_desc + (size_t)id * 32);
+                if (d < best_d) { best_d = d; final_id = id; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (child_off[final_id] != child_off[final_id + 1]);
+        const unsigned wid = (unsigned)word_id[final_id];
+        const double w = weight[final_id];
+        out_word[i] = (int)wid; out_w[i] = w; out_nid[i] = nid;
+        if (w > 0) {
+            if (weighting == 0 || weighting == 1) {   // TF_IDF, TF: addWeight
+                auto it = v.lower_bound(wid);
+                if (it != v.end() && !(wid < it->first)) it->second += w; else v.insert(it, make_pair(wid, w));
+            } else {                                  // IDF, BINARY: addIfNotExist
+                auto it = v.lower_bound(wid);
+                if (it == v.end() || wid < it->first) v.insert(it, make_pair(wid, w));
+            }
+            fv[nid].push_back((unsigned)i);
+        }
+    }
+    if ((weighting == 0 || weighting == 1) && !v.empty() && norm_type == 0) {
+        const double nd = (double)v.size();
+        for (auto& e : v) e.second /= nd;
+    }
+    if (norm_type != 0) {
+        double norm = 0.0;
+        if (norm_type == 1) { for (auto& e : v) norm += fabs(e.second); }
+        else { for (auto& e : v) norm += e.second * e.second; norm = sqrt(norm); }
+        if (norm > 0.0) for (auto& e : v) e.second /= norm;
+    }
+    int k = 0;
+    for (auto& e : v) { bow_ids[k] = e.first; bow_vals[k] = e.second; ++k; }
+    int m = 0, at = 0;
+    for (auto& e : fv) { fv_nodes[m] = e.first; fv_off[m] = at; for (unsigned f : e.second) fv_idx[at++] = (int)f; ++m; }
+    fv_off[m] = at;
+    *n_fv = m;
+    return k;
 }
 
 // ---- CPU baseline driver: n_frames three-camera frames (L, R, W images, each w*h contiguous), n_threads workers,

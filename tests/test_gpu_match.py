@@ -212,3 +212,33 @@ def test_wnd_track(api, oracle):
     assert cnt == cnto and cnt > 100, (cnt, cnto)
     assert np.array_equal(oi, oio) and np.array_equal(ob, obo) and np.array_equal(od, odo)
     assert (oi[oi >= 0] != ob[oi >= 0]).any()                      # the reference's queryIdx slip is visible in the data
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("weighting,norm,K,L,levelsup", [(0, 1, 10, 4, 2), (0, 2, 10, 3, 1), (1, 0, 8, 3, 4), (2, 1, 10, 4, 3), (3, 0, 33, 2, 1)])
+def test_bow_transform(api, oracle, weighting, norm, K, L, levelsup):
+    """Object::ComputeBow = DBoW3 Vocabulary::transform (modules/DBow3/src/Vocabulary.cpp:572-672): words, nodes, and the two
+    vectors (doubles bit for bit) equal the oracle's, on a synthetic vocabulary with sibling ties and stopped words."""
+    voc = synth.random_vocabulary(100 + weighting * 7 + K, K=K, L=L, weighting=weighting, norm=norm)
+    rng = np.random.default_rng(K + L)
+    leaves = np.where(voc["word_id"] >= 0)[0]
+    d = voc["node_desc"][rng.choice(leaves, 2000)].copy()           # features near words ...
+    flips = rng.integers(0, 60, len(d))
+    for m in range(len(d)):
+        bits = rng.choice(256, flips[m], replace=False)
+        np.bitwise_xor.at(d[m], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    d[-200:] = rng.integers(0, 256, (200, 32), dtype=np.uint8)      # ... and some anywhere
+    V = api.Vocabulary(voc)
+    a = V.transform(d, levelsup)
+    b = oracle.bow_transform(d, voc, levelsup)
+    for key in ("word", "nid", "bow_ids", "fv_nodes", "fv_off", "fv_idx"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["weight"].tobytes() == b["weight"].tobytes() and a["bow_vals"].tobytes() == b["bow_vals"].tobytes()
+    assert len(a["bow_ids"]) > 50 and len(a["fv_nodes"]) >= 1
+    # the FeatureVector is what DBowMatch consumes: run it end to end against the oracle's candidate 2-NN
+    d2 = d[rng.permutation(len(d))]
+    a2 = V.transform(d2, levelsup)
+    r = api.Matcher.DBowMatch(d, (a["fv_nodes"], a["fv_off"], a["fv_idx"]), d2, (a2["fv_nodes"], a2["fv_off"], a2["fv_idx"]))
+    assert len(r.knn) > 100
+    assert V.transform(d[:0], levelsup)["bow_ids"].size == 0
+    V.close()
