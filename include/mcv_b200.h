@@ -251,6 +251,15 @@ mcv_status mcv_fuse_match(const mcv_keypoint* kps, const uint8_t* desc, int n, i
 mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1, const int32_t* q_idx, int n_q, const mcv_keypoint* kps2,
                          const uint8_t* desc2, int n2, int w, int hgt, int32_t* out_idx, int32_t* out_best, int32_t* out_dist, int* n_matched);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150), batched over MapPoints (the reference runs it per
+ * point on keyframe insertion and after Map::Fuse). desc = the observed descriptors of all points back to back (32 B rows, the
+ * order all_ob_desps is filled in, :108-115), mp_off [n_mp + 1] = row range of each point. Per point: all-pairs
+ * HammingDistance, per-row std::sort, median = row[0.5 * (N - 1)], first row with the least median wins. best_idx[m] = BestIdx
+ * (row within the point's range; -1 for a point without observations, which the reference leaves untouched), best_median[m]
+ * (may be NULL) = BestMedian, out_desc (may be NULL) [n_mp][32] = the descriptor the reference clones into MapPoint::desp. */
+mcv_status mcv_distinctive_descriptors(const uint8_t* desc, const int32_t* mp_off, int n_mp, int32_t* best_idx, int32_t* best_median,
+                                       uint8_t* out_desc);
+
 /* Object::ComputeBow (src/Object.cpp:238-247): DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
  * (modules/DBow3/src/Vocabulary.cpp:572-672). The vocabulary is handed over once as flat arrays — what a maintainer gets by
  * walking DBoW3's m_nodes after Vocabulary::load: child_off [n_nodes+1] / child_ids = m_nodes[i].children in stored order

@@ -31,7 +31,7 @@ EXPORTS = [
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
     "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_set_input_channels", "mcv_orb_set_input_channels", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
-    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
+    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_distinctive_descriptors", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
 ]
 
@@ -105,6 +105,7 @@ def lib():
         L.mcv_project_match.argtypes = [vp, vp, i, i, i, vp, i, vp, vp, vp, vp, vp, vp, i, f, vp, vp, C.POINTER(i)]
         L.mcv_fuse_match.argtypes = [vp, vp, i, i, i, vp, vp, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, i, vp, vp, C.POINTER(i)]
         L.mcv_wnd_track.argtypes = [vp, vp, i, vp, i, vp, vp, i, i, i, vp, vp, vp, C.POINTER(i)]
+        L.mcv_distinctive_descriptors.argtypes = [vp, vp, i, vp, vp, vp]
         L.mcv_voc_create.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(vp)]
         L.mcv_voc_destroy.argtypes = [vp]
         L.mcv_voc_destroy.restype = None
@@ -401,6 +402,17 @@ def WndTrack(kps1, desps1, q_idx, kps2, desps2, w, h):
     _check(lib().mcv_wnd_track(_p(kps1), _p(desps1), len(kps1), _p(q), len(q), _p(kps2), _p(desps2), len(kps2), w, h, _p(oi), _p(ob), _p(od),
                                C.byref(cnt)))
     return cnt.value, oi, ob, od
+
+
+def ComputeDistinctiveDescriptors(desps, off):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150) for a batch of MapPoints: rows [off[m], off[m+1]) of
+    `desps` are the descriptors point m was observed with. Returns (best_idx, best_median, desp [n_mp, 32]); best_idx = -1 and a
+    zero row where a point has no observation (the reference leaves such a point untouched)."""
+    desps = _u8(desps); off = np.ascontiguousarray(off, np.int32)
+    n_mp = len(off) - 1
+    bi = np.full(n_mp, -1, np.int32); bm = np.full(n_mp, -1, np.int32); od = np.zeros((n_mp, 32), np.uint8)
+    _check(lib().mcv_distinctive_descriptors(_p(desps), _p(off), n_mp, _p(bi), _p(bm), _p(od)))
+    return bi, bm, od
 
 
 class Vocabulary:

@@ -20,6 +20,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # --fmad=false: the parity-critical float code uses explicit _rn intrinsics; this is the safety net for everything else.
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]
+# tuning experiments: MCV_NVCC_EXTRA="-DFS_MINB=6" python -m mcvslam_b200.build --force
+FLAGS += os.environ.get("MCV_NVCC_EXTRA", "").split()
 
 
 def _deps():

@@ -217,7 +217,9 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
     const Plan& P = h->plan;
     if (n_images > h->cap_images) {
         mcv_status st;
-        if ((st = h->pyr.reserve((size_t)P.pyr_bytes * n_images + 256))) return st;   // + spare bytes: k_resize_march reads whole words past a row end
+        // + spare bytes: k_resize_march reads whole words past a row end, and k_fast_score prefetches up to FS_ROWS + 6 rows past the
+        // end of a level (rows that feed no output) without clamping
+        if ((st = h->pyr.reserve((size_t)P.pyr_bytes * n_images + 256 + (size_t)(FS_ROWS + 8) * P.lv[0].pitch))) return st;
         if ((st = h->blur.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->score.reserve((size_t)P.pyr_bytes * n_images))) return st;
         if ((st = h->cell_pts.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
@@ -751,6 +753,38 @@ mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1,
     MCV_CUDA(cudaMemcpyAsync(out_dist, b_od.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaStreamSynchronize(s));
     if (n_matched) { int c = 0; for (int q = 0; q < n_q; ++q) c += out_idx[q] >= 0; *n_matched = c; }
+    return MCV_OK;
+}
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150), batched over MapPoints ----
+mcv_status mcv_distinctive_descriptors(const uint8_t* desc, const int32_t* mp_off, int n_mp, int32_t* best_idx, int32_t* best_median,
+                                       uint8_t* out_desc) {
+    if (n_mp < 0 || (n_mp > 0 && (!mp_off || !best_idx))) return MCV_ERR_BAD_ARG;
+    if (n_mp == 0) return MCV_OK;
+    if (mp_off[0] != 0) return MCV_ERR_BAD_ARG;
+    for (int m = 0; m < n_mp; ++m) if (mp_off[m + 1] < mp_off[m] || mp_off[m + 1] - mp_off[m] >= (1 << 22)) return MCV_ERR_BAD_ARG;
+    const int total = mp_off[n_mp];
+    if (total > 0 && !desc) return MCV_ERR_BAD_ARG;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b_d, b_off, b_bi, b_bm;
+    if ((st = b_d.reserve(std::max<size_t>(32, (size_t)total * 32)))) return st;
+    if ((st = b_off.reserve((size_t)(n_mp + 1) * 4))) return st;
+    if ((st = b_bi.reserve((size_t)n_mp * 4))) return st;
+    if ((st = b_bm.reserve((size_t)n_mp * 4))) return st;
+    if (total) MCV_CUDA(cudaMemcpyAsync(b_d.p, desc, (size_t)total * 32, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(b_off.p, mp_off, (size_t)(n_mp + 1) * 4, cudaMemcpyHostToDevice, s));
+    launch_distinctive(b_d.as<uint8_t>(), b_off.as<int32_t>(), n_mp, b_bi.as<int32_t>(), b_bm.as<int32_t>(), s);
+    MCV_CUDA(cudaGetLastError());
+    std::vector<int32_t> med_tmp;
+    if (!best_median) { med_tmp.resize(n_mp); best_median = med_tmp.data(); }
+    MCV_CUDA(cudaMemcpyAsync(best_idx, b_bi.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(best_median, b_bm.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaStreamSynchronize(s));
+    if (out_desc)   // MapPoint::desp = all_ob_desps[BestIdx].clone(); points without observations keep their row untouched
+        for (int m = 0; m < n_mp; ++m)
+            if (best_idx[m] >= 0) memcpy(out_desc + (size_t)m * 32, desc + (size_t)(mp_off[m] + best_idx[m]) * 32, 32);
     return MCV_OK;
 }
 

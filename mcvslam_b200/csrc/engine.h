@@ -117,6 +117,7 @@ int launch_wnd_track(const mcv_keypoint* d_kps1, const uint8_t* d_desc1, const i
                      const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_idx, int32_t* d_best, int32_t* d_dist, cudaStream_t s);
 int launch_bow_descend(const uint8_t* d_desc, int n, const int32_t* d_child_off, const uint32_t* d_child_ids, const uint8_t* d_node_desc,
                        int nid_level, int max_depth, uint32_t* d_leaf, uint32_t* d_nid, cudaStream_t s);
+int launch_distinctive(const uint8_t* d_desc, const int32_t* d_off, int n_mp, int32_t* d_best_idx, int32_t* d_best_median, cudaStream_t s);
 int launch_debug_sincosf(const float* d_a, int n, float* d_s, float* d_c, cudaStream_t s);
 int launch_debug_atan2(const float* d_y, const float* d_x, int n, float* d_o, cudaStream_t s);
 int launch_popc_peak(int iters, unsigned* d_sink, int blocks, int threads, cudaStream_t s);

@@ -32,7 +32,10 @@
 namespace mcv {
 
 constexpr int FS_WARPS = 4;
-constexpr int FS_QCAP = 32 + 128;
+#ifndef FS_MINB
+#define FS_MINB 5                 // resident CTAs per SM the register allocation aims at (95 registers, no spills)
+#endif
+constexpr int FS_QCAP = 32 + 7 * 128;   // leftover (< 32) + every pixel of a 7-row block
 
 __device__ __noinline__ int fast_score16(const uint8_t* c, int pitch) {
     // Bresenham circle, OpenCV order (fast_score.cpp makeOffsets). Both polarities at once: P[k] = (256 + v - p, 256 + p - v) as
@@ -99,7 +102,7 @@ __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_belo
     return (ln << 8) | qn;
 }
 
-__global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
+__global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
                                                                unsigned* __restrict__ nz_list, int* __restrict__ nz_cnt,
                                                                const __grid_constant__ Plan P, const __grid_constant__ StripTable T, int Tm) {
     __shared__ unsigned s_q[FS_WARPS][FS_QCAP];
@@ -126,30 +129,33 @@ __global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __r
     for (int k = 0; k < 4; ++k) if (x0 + k >= x_lo && x0 + k < x_hi) colmask |= 0x80u << (8 * k);
     const unsigned add = 255u - (unsigned)Tm, add_lo7 = (add & 0x7fu) * 0x01010101u;
     const bool add_hi = (add & 0x80u) != 0;
-    const unsigned lt = (1u << lane) - 1;
     unsigned* q = s_q[warp];
     int qn = 0;                                             // warp-uniform queue fill
 
-    auto row_ptr = [&](int r) { return src + min(y0 - 3 + r, h - 1) * pitch; };   // rows past the image feed nothing
+    // rows past the level's end feed no output row (row_ok is false for them); they are read unclamped — the next level / image
+    // follows in the same buffer and the allocation ends with FS_ROWS + 8 spare rows (enqueue_extract)
     unsigned pw[7], pe[7], ring[7], ering[7];
 #pragma unroll
     for (int d = 0; d < 7; ++d) {
-        const uint8_t* row = row_ptr(d);
+        const uint8_t* row = src + (y0 - 3 + d) * pitch;
         pw[d] = in_row ? __ldg(reinterpret_cast<const unsigned*>(row + x0)) : 0u;
         pe[d] = edge ? __ldg(reinterpret_cast<const unsigned*>(row + ex)) : 0u;
         ring[d] = 0u; ering[d] = 0u;
     }
+    const uint8_t* lp = src + (size_t)(y0 + 4) * pitch + x0;              // input row y0 - 3 + (r + 7) for r = 0
+    const uint8_t* lpe = lp + (ex - x0);
+    uint8_t* sp = dst + (size_t)(y0 - 6) * pitch + x0;                     // output row y0 + r - 6 for r = 0
 #pragma unroll 1
     for (int rb = 0; rb < FS_ROWS + 6; rb += 7) {
+        // candidates of the block's 7 rows: row j's four pass bits (bit 7 of each byte) shifted right by j never collide
+        unsigned acc = 0u;
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
             const int r = rb + j;                           // input row y0 - 3 + r; completes the window of output row y0 + r - 6
             ring[j] = pw[j]; ering[j] = pe[j];
-            {
-                const uint8_t* row = row_ptr(r + 7);
-                pw[j] = in_row ? __ldg(reinterpret_cast<const unsigned*>(row + x0)) : 0u;
-                pe[j] = edge ? __ldg(reinterpret_cast<const unsigned*>(row + ex)) : 0u;
-            }
+            pw[j] = in_row ? __ldg(reinterpret_cast<const unsigned*>(lp)) : 0u;
+            pe[j] = edge ? __ldg(reinterpret_cast<const unsigned*>(lpe)) : 0u;
+            lp += pitch; lpe += pitch;
             const int y = y0 + r - 6;
             const unsigned v4 = ring[(j + 4) % 7], top = ring[(j + 1) % 7], bot = ring[j], we = ering[(j + 4) % 7];
             unsigned w0 = __shfl_up_sync(0xffffffffu, v4, 1), w2 = __shfl_down_sync(0xffffffffu, v4, 1);
@@ -161,20 +167,25 @@ __global__ void __launch_bounds__(32 * FS_WARPS) k_fast_score(const uint8_t* __r
             const bool row_ok = r >= 6 && r < FS_ROWS + 6 && y < y_hi;   // warp-uniform; every row belongs to exactly one strip
                                                                          // (a pixel listed twice would survive NMS twice)
             const unsigned pass = row_ok ? ((mt | mb) & (ml | mr) & colmask) : 0u;
-            if (row_ok && colmask) *reinterpret_cast<unsigned*>(dst + y * pitch + x0) = 0u;   // zero first; scores land later
-            if (__any_sync(0xffffffffu, pass != 0)) {
-                // queue position of (lane, k): entries of byte k of all lanes, then byte k + 1, ...
-                int base = qn;
+            if (row_ok && colmask) *reinterpret_cast<unsigned*>(sp) = 0u;   // zero first; scores land later
+            sp += pitch;
+            acc |= pass >> j;
+        }
+        if (__any_sync(0xffffffffu, acc != 0u)) {
+            // one compaction per block: exclusive scan of the lanes' counts, then every lane appends its own entries
+            const int cnt = __popc(acc);
+            int incl = cnt;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool pk = (pass >> (8 * k + 7)) & 1u;
-                    const unsigned m = __ballot_sync(0xffffffffu, pk);
-                    if (pk) q[base + __popc(m & lt)] = (unsigned)(x0 + k) | ((unsigned)y << 16);
-                    base += __popc(m);
-                }
-                qn = base;
-                if (qn >= 32) { const int r2 = drain_queue(q, qn, 31, src, dst, pitch, Tm, list, ln); qn = r2 & 0xff; ln = r2 >> 8; }
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+            int pos = qn + incl - cnt;
+            qn += __shfl_sync(0xffffffffu, incl, 31);
+            const int yb = y0 + rb - 6 + 7;                 // bit b: column byte b >> 3, row j = 7 - (b & 7)
+            while (acc) {
+                const int b = __ffs(acc) - 1;
+                acc &= acc - 1u;
+                q[pos++] = (unsigned)(x0 + (b >> 3)) | ((unsigned)(yb - (b & 7)) << 16);
             }
+            if (qn >= 32) { const int r2 = drain_queue(q, qn, 31, src, dst, pitch, Tm, list, ln); qn = r2 & 0xff; ln = r2 >> 8; }
         }
     }
     ln = drain_queue(q, qn, 0, src, dst, pitch, Tm, list, ln) >> 8;

@@ -394,6 +394,75 @@ int launch_bow_descend(const uint8_t* d_desc, int n, const int32_t* d_child_off,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150) for a batch of MapPoints: the observed descriptors of
+// point m are rows [off[m], off[m + 1]) of `desc`. Per point: all-pairs Hamming distances (diagonal 0), every row sorted, its
+// median = row[(size_t)(0.5 * (N - 1))], and the FIRST row with the smallest median wins (strict '<' against INT_MAX).
+// One CTA per point, one warp per row: distances go into a 257-bin shared-memory histogram (a sorted row is only ever read at
+// one rank, so counting replaces std::sort), the rank is located with a warp scan over 9-bin slices, and the point's winner is
+// the minimum of the packed key median << 22 | row.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DD_WARPS = 8;
+constexpr int DD_BINS = 288;                     // 257 distances rounded up to 32 lanes x 9 bins
+
+__global__ void __launch_bounds__(32 * DD_WARPS) k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ off, int n_mp,
+                                                                 int32_t* __restrict__ best_idx, int32_t* __restrict__ best_median) {
+    __shared__ unsigned s_hist[DD_WARPS][DD_BINS];
+    __shared__ unsigned s_best;
+    const int m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (m >= n_mp) return;
+    const int lo = off[m], N = off[m + 1] - lo;
+    if (threadIdx.x == 0) s_best = 0xffffffffu;
+    __syncthreads();
+    if (N > 0) {
+        const int k = (N - 1) >> 1;              // (size_t)(0.5 * (N - 1))
+        unsigned* hist = s_hist[warp];
+        unsigned mine = 0xffffffffu;
+        for (int i = warp; i < N; i += DD_WARPS) {
+#pragma unroll
+            for (int b = 0; b < DD_BINS / 32; ++b) hist[b * 32 + lane] = 0u;
+            __syncwarp();
+            const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(lo + i) * 32));
+            const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(lo + i) * 32 + 16));
+            for (int j = lane; j < N; j += 32) {
+                const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(lo + j) * 32));
+                const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(lo + j) * 32 + 16));
+                atomicAdd(&hist[j == i ? 0 : hamming256(a0, a1, b0, b1)], 1u);   // the buffer's diagonal stays 0 (src/MapPoint.cpp:123)
+            }
+            __syncwarp();
+            unsigned c[9], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 9; ++b) { c[b] = hist[lane * 9 + b]; sum += c[b]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            // the lane whose slice holds rank k: exclusive prefix <= k < inclusive prefix
+            unsigned before = incl - sum;
+            int med = -1;
+            if (before <= (unsigned)k && (unsigned)k < incl) {
+#pragma unroll
+                for (int b = 0; b < 9; ++b) { if (med < 0 && before + c[b] > (unsigned)k) med = lane * 9 + b; before += c[b]; }
+            }
+            const unsigned who = __ballot_sync(0xffffffffu, med >= 0);
+            med = __shfl_sync(0xffffffffu, med, __ffs(who) - 1);
+            mine = min(mine, ((unsigned)med << 22) | (unsigned)i);
+            __syncwarp();
+        }
+        if (lane == 0) atomicMin(&s_best, mine);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        best_idx[m] = N > 0 ? (int)(s_best & 0x3fffffu) : -1;
+        best_median[m] = N > 0 ? (int)(s_best >> 22) : -1;
+    }
+}
+
+int launch_distinctive(const uint8_t* d_desc, const int32_t* d_off, int n_mp, int32_t* d_best_idx, int32_t* d_best_median, cudaStream_t s) {
+    if (n_mp <= 0) return 0;
+    k_distinctive<<<n_mp, 32 * DD_WARPS, 0, s>>>(d_desc, d_off, n_mp, d_best_idx, d_best_median);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // test taps + integer-pipe peak
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_debug_sincosf(const float* a, int n, float* s, float* c) {

@@ -505,6 +505,22 @@ inline uint Wnd_Track(const Object& obj1, const std::vector<int>& mp_kp_idxs, co
     if (matched_dist) matched_dist->assign(od.begin(), od.begin() + nq);
     return (uint)cnt;
 }
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150) on the descriptors the point was observed with
+// (`all_ob_desps`, the vector the reference builds at :108-115). Returns what the reference assigns to MapPoint::desp — a
+// clone of the row with the least median distance to the others — or an empty Mat where the reference returns early.
+inline cv::Mat ComputeDistinctiveDescriptors(const std::vector<cv::Mat>& all_ob_desps, int* best_idx_out = nullptr, int* best_median_out = nullptr) {
+    if (best_idx_out) *best_idx_out = -1;
+    if (all_ob_desps.empty()) return cv::Mat();
+    std::vector<uint8_t> rows((size_t)all_ob_desps.size() * 32);
+    for (size_t i = 0; i < all_ob_desps.size(); ++i) memcpy(rows.data() + i * 32, all_ob_desps[i].data, 32);
+    const int32_t off[2] = {0, (int32_t)all_ob_desps.size()};
+    int32_t bi = -1, bm = -1;
+    const mcv_status st = mcv_distinctive_descriptors(rows.data(), off, 1, &bi, &bm, nullptr);
+    if (st != MCV_OK) throw std::runtime_error(std::string("ComputeDistinctiveDescriptors: ") + mcv_last_error());
+    if (best_idx_out) *best_idx_out = bi;
+    if (best_median_out) *best_median_out = bm;
+    return all_ob_desps[(size_t)bi].clone();
+}
 using ObjectRef = std::shared_ptr<Object>;
 
 class Frame {

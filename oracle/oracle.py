@@ -283,6 +283,19 @@ def wnd_track(kps1, desc1, q_idx, kps2, desc2, W, H):
     return cnt, oi, ob, od
 
 
+def distinctive(desc, off):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150) for a batch: rows [off[m], off[m+1]) of desc are the
+    observations of point m. Returns (best_idx, best_median), -1 for points without observations."""
+    desc = _u8(desc); off = np.ascontiguousarray(off, np.int32)
+    n_mp = len(off) - 1
+    bi = np.empty(n_mp, np.int32); bm = np.empty(n_mp, np.int32)
+    L = lib()
+    L.ora_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ora_distinctive.restype = None
+    L.ora_distinctive(_p(desc), _p(off), n_mp, _p(bi), _p(bm))
+    return bi, bm
+
+
 def bow_transform(desc, voc, levelsup=4):
     """DBoW3::Vocabulary::transform (modules/DBow3/src/Vocabulary.cpp:572-672) as Object::ComputeBow calls it. `voc` = dict of the
     flat vocabulary arrays (mcvslam_b200.synth.random_vocabulary layout). Returns dict(word, weight, nid, bow_ids, bow_vals,

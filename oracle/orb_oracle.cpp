@@ -743,6 +743,33 @@ int ora_wnd_track(const KeyPoint* kps1, const uint8_t* desc1, const int* q_idx, 
     return cnt;
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150), one call per MapPoint in a batch. desc rows
+// [off[m], off[m + 1]) = all_ob_desps of point m (:108-115). Literal restatement: N x N int buffer with a zero diagonal (:120-128),
+// std::sort of every row, median = row[0.5 * (N - 1)] (double product converted to the index type), strict '<' against INT_MAX
+// (:131-141). best_idx = -1 where the reference returns early (:104,117).
+void ora_distinctive(const uint8_t* desc, const int* off, int n_mp, int* best_idx, int* best_median) {
+    for (int m = 0; m < n_mp; ++m) {
+        const uint8_t* d = desc + (size_t)off[m] * 32;
+        const size_t N = (size_t)(off[m + 1] - off[m]);
+        best_idx[m] = -1; best_median[m] = -1;
+        if (N == 0) continue;
+        vector<vector<int>> buf(N, vector<int>(N, 0));
+        for (size_t i = 0; i < N; i++)
+            for (size_t j = i + 1; j < N; j++) {
+                const int distij = (int)hamming256(d + i * 32, d + j * 32);
+                buf[i][j] = distij;
+                buf[j][i] = distij;
+            }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (size_t i = 0; i < N; i++) {
+            sort(buf[i].begin(), buf[i].end());
+            const int median = buf[i][0.5 * (N - 1)];
+            if (median < BestMedian) { BestMedian = median; BestIdx = (int)i; }
+        }
+        best_idx[m] = BestIdx; best_median[m] = BestMedian;
+    }
+}
+
 // ---- Object::ComputeBow (src/Object.cpp:238-247) = DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
 // (modules/DBow3/src/Vocabulary.cpp:572-633) on a vocabulary passed as flat arrays: child_off/child_ids = m_nodes[i].children in
 // stored order, node_desc = m_nodes[i].descriptor (32 B), word_id / weight = leaf fields, L = m_L. Per feature the tree descent

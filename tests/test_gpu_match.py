@@ -242,3 +242,24 @@ def test_bow_transform(api, oracle, weighting, norm, K, L, levelsup):
     assert len(r.knn) > 100
     assert V.transform(d[:0], levelsup)["bow_ids"].size == 0
     V.close()
+
+
+@pytest.mark.parametrize("sizes", [[0, 1, 2, 3, 4, 5, 8, 33, 64, 100, 0, 7], [700], [1] * 50 + [2] * 50, list(range(0, 70))])
+def test_distinctive_descriptors(api, oracle, sizes):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150) batched: BestIdx, BestMedian and the cloned row."""
+    from test_oracle_golden import _ragged_observations
+    desc, off = _ragged_observations(len(sizes), sizes)
+    bi, bm, od = api.ComputeDistinctiveDescriptors(desc, off)
+    bio, bmo = oracle.distinctive(desc, off)
+    assert np.array_equal(bi, bio) and np.array_equal(bm, bmo)
+    for m in range(len(sizes)):
+        assert np.array_equal(od[m], desc[off[m] + bi[m]] if bi[m] >= 0 else np.zeros(32, np.uint8))
+
+
+def test_distinctive_descriptors_ties(api, oracle):
+    """Identical observations: every median is 0 and the first row wins; an empty batch is a no-op."""
+    desc = np.tile(synth.descriptors(1, 5), (9, 1))
+    bi, bm, od = api.ComputeDistinctiveDescriptors(desc, [0, 4, 9])
+    assert bi.tolist() == [0, 0] and bm.tolist() == [0, 0]
+    bi, bm, od = api.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), [0])
+    assert len(bi) == 0
