@@ -7,6 +7,8 @@
 //     lane i produces descriptor byte i;
 //   * the level-major assembly of operator() (ORBextractor.cc:845-897): quadtree keypoints of a level in heap-pop order,
 //     then the caller's pre-seeded keypoints of that octave, pt *= scale for level != 0.
+#include <cuda.h>
+#include <string.h>
 #include "devmath.cuh"
 #include "engine.h"
 
@@ -16,117 +18,252 @@ __constant__ int8_t c_pattern[1024] = {
 #include "rbrief_pattern.inc"
 };
 
-constexpr int DESC_WARPS = 8;
-constexpr int DESC_KPW = 4;      // keypoints per warp (amortises the per-CTA tables and the level lookup)
+constexpr int DESC_WARPS = 4;
+constexpr int DESC_KPW = 4;      // keypoints per warp and round: one per group of 8 lanes
+#ifndef DESC_WAVES
+#define DESC_WAVES 4             // persistent grid: about this many waves of resident CTAs (3 per SM), split evenly over the images
+#endif
+#ifndef DESC_PREFETCH
+#define DESC_PREFETCH 0          // cp.async.bulk.prefetch.tensor of the warp's next round: measured slower (0.78 vs 0.58 ms per 384
+#endif                           // images) — it doubles the row requests the TMA engine has to generate
+
+// Design. A quarter-warp (8 lanes) owns one keypoint, so the scalar part of the work (slot decoding, cv::fastAtan2, sincosf,
+// keypoint assembly) is paid once per FOUR keypoints of a warp instead of once per keypoint, and a lane produces four
+// descriptor bytes. Both pixel neighbourhoods of the keypoint are fetched by the TMA engine (cp.async.bulk.tensor, one
+// instruction per window, issued by the group's first lane, completion on the warp's mbarrier) from per-level 3-D tensor
+// maps (x, y, image) over the pyramid / blurred-pyramid buffers:
+//  * blurred window for rBRIEF: the pattern points lie within radius 18.4 of the centre, so every steered sample falls inside
+//    37 x 37; box 64 x 37 starting at ((cx - 18) & ~15, cy - 18) — the TMA start coordinate of the byte dimension must be a
+//    multiple of 16 (an unaligned one raises "illegal instruction": scripts/exp/tma_probe.cu) — and whatever lies past the
+//    row pitch is zero-filled. The 512 single-byte gathers then hit shared-memory banks instead of ~20 different L1 lines
+//    per warp instruction.
+//  * unblurred 31 x 31 patch for IC_Angle: box 48 x 31 at ((cx - 15) & ~15, cy - 15); lane k funnel-shifts two consecutive
+//    words of a row into patch pixels 4k .. 4k+3.
+// The kernel is persistent per image (a few CTAs per image, tables built once per CTA): a warp loops over rounds of four
+// keypoints; the other resident warps (12 per SM) cover the TMA latency of a round.
+// History (ncu, 384 images, 770 k keypoints): warp-per-keypoint with global gathers 0.83 ms (636 warp-instructions per
+// keypoint, l1tex 96 %); the same with cp.async staging 0.88 ms (810 per keypoint, short-scoreboard bound); quarter-warp + TMA,
+// one CTA per 16 keypoints 0.91 ms (table prologue per CTA, 18 % occupancy); persistent 0.58 ms (424 per keypoint; l1tex 78 %,
+// L2 56 %: what moves is ~3.9 KB of window per keypoint, 3 GB per launch).
+constexpr int TILE_R = 18, TILE_ROWS = 2 * TILE_R + 1, TILE_PITCH = 64;
+constexpr int IC_ROWS = 31, IC_PITCH = 48;
+constexpr int TILE_BYTES = TILE_ROWS * TILE_PITCH;                    // 2368
+constexpr int IC_BYTES = IC_ROWS * IC_PITCH;                          // 1488
+constexpr int BUF_IC_OFF = (TILE_BYTES + 127) & ~127;                 // TMA destinations are 128-byte aligned
+constexpr int BUF_BYTES = BUF_IC_OFF + ((IC_BYTES + 127) & ~127);     // per keypoint
+constexpr int DESC_DYN_SMEM = DESC_WARPS * DESC_KPW * BUF_BYTES;
+
+struct DescMaps {                 // per level: (pitch, h, n_images) u8 tensors over the pyramid and the blurred pyramid
+    CUtensorMap pyr[MAX_LEVELS];
+    CUtensorMap blur[MAX_LEVELS];
+};
 
 __device__ __forceinline__ int dp4a_us(unsigned a, unsigned b_signed, int c) {   // sum of u8(a) * s8(b) + c
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_signed), "r"(c));
     return d;
 }
+__device__ __forceinline__ void tma_load_3d(unsigned dst_smem, const CUtensorMap* map, int c0, int c1, int c2, unsigned mbar_smem) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(mbar_smem) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar_smem, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_smem), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar_smem, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(mbar_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar_smem, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n"
+        "MCV_MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MCV_MBAR_DONE_%=;\n\t"
+        "bra MCV_MBAR_WAIT_%=;\n"
+        "MCV_MBAR_DONE_%=:\n\t"
+        "}" ::"r"(mbar_smem), "r"(parity) : "memory");
+}
 
-__global__ void __launch_bounds__(32 * DESC_WARPS) k_orient_desc(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+__global__ void __launch_bounds__(32 * DESC_WARPS) k_orient_desc(const __grid_constant__ DescMaps maps,
                                                                  const uint32_t* __restrict__ out_pts, const int* __restrict__ out_cnt,
                                                                  const mcv_keypoint* __restrict__ seeds, int n_seeds,
                                                                  mcv_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
                                                                  int* __restrict__ counts, int cap, const __grid_constant__ Plan P) {
-    // pattern transposed into shared memory as floats: s_pat[k][lane] = point (16*lane + k) -> conflict-free per-lane reads
-    __shared__ float2 s_pat[16][32];
-    // IC_Angle weights of the 31x31 circular patch, by row (v + 15) and 4-px word k (u = -15 + 4k ...): byte = u inside the
-    // circle (|u| <= umax[|v|], ORBextractor.cc:444-456), 0 outside; s_one has 1 / 0. Row 31 is all zero.
-    __shared__ unsigned s_wu[32][8], s_one[32][8];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_pat[i & 15][i >> 4] = make_float2((float)c_pattern[2 * i], (float)c_pattern[2 * i + 1]);
-    {
+    extern __shared__ __align__(128) uint8_t s_buf[];                   // [warp][group][BUF_BYTES]
+    // pattern: s_pat[k][l8] = point 64 * l8 + k (the 64 points = 32 pairs = 4 descriptor bytes of lane l8): the 8 lanes of a
+    // group read 8 consecutive float2, the four groups the same ones (broadcast)
+    __shared__ float2 s_pat[64][8];
+    // IC_Angle weights of the 31x31 circular patch, by row (v + 15) and 4-px word k (u = -15 + 4k ...): s_wu = u, s_wv = v
+    // inside the circle (|u| <= umax[|v|], ORBextractor.cc:444-456), 0 outside, as signed bytes for dp4a
+    __shared__ unsigned s_wu[32][8], s_wv[32][8];
+    __shared__ int s_end[MAX_LEVELS + 1], s_nq[MAX_LEVELS], s_ns[MAX_LEVELS];
+    __shared__ __align__(8) unsigned long long s_mbar[DESC_WARPS];
+    const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_pat[i & 63][i >> 6] = make_float2((float)c_pattern[2 * i], (float)c_pattern[2 * i + 1]);
+    for (int e = threadIdx.x; e < 256; e += blockDim.x) {
         constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-        const int row = threadIdx.x >> 3, k = threadIdx.x & 7;          // 256 threads <-> 32 x 8 entries
-        unsigned wu = 0, one = 0;
+        const int row = e >> 3, k = e & 7;
+        unsigned wu = 0, wv = 0;
         if (row < 31) {
             const int v = row - 15, d = UMAX[v < 0 ? -v : v];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int u = -15 + 4 * k + j;
-                if (u >= -d && u <= d) { wu |= (unsigned)(u & 0xff) << (8 * j); one |= 1u << (8 * j); }
+                if (u >= -d && u <= d) { wu |= (unsigned)(u & 0xff) << (8 * j); wv |= (unsigned)(v & 0xff) << (8 * j); }
             }
         }
-        s_wu[row][k] = wu; s_one[row][k] = one;
+        s_wu[row][k] = wu; s_wv[row][k] = wv;
+    }
+    // per-level slot ranges of this image: quadtree keypoints of the level, then the caller's seeds of that octave
+    if (warp == 0) {
+        int my_nq = 0, my_ns = 0;
+        if (lane < P.n_levels) {
+            my_nq = out_cnt[(size_t)img * P.n_levels + lane];
+            for (int s = 0; s < n_seeds; ++s) my_ns += seeds[s].octave == lane;   // n_seeds is 0 on the batch path
+        }
+        int my_end = my_nq + my_ns;                                     // inclusive prefix = first slot after this level
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, my_end, o); if (lane >= o) my_end += v; }
+        if (lane < MAX_LEVELS) { s_end[lane + 1] = my_end; s_nq[lane] = my_nq; s_ns[lane] = my_ns; }
+        if (lane == 0) s_end[0] = 0;
+    }
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar[warp]);
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the init is visible to the TMA engine
     }
     __syncthreads();
-    const int img = blockIdx.y, lane = threadIdx.x & 31;
-    // per-level slot ranges of this image: quadtree keypoints of the level, then the caller's seeds of that octave
-    int my_nq = 0, my_ns = 0;
-    if (lane < P.n_levels) {
-        my_nq = out_cnt[(size_t)img * P.n_levels + lane];
-        for (int s = 0; s < n_seeds; ++s) my_ns += seeds[s].octave == lane;   // n_seeds is 0 on the batch path
-    }
-    int my_end = my_nq + my_ns;                                         // inclusive prefix = first slot after this level
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, my_end, o); if (lane >= o) my_end += v; }
-    const int total = __shfl_sync(0xffffffffu, my_end, 31);
-    const int warp_slot0 = (blockIdx.x * DESC_WARPS + (threadIdx.x >> 5)) * DESC_KPW;
-    if (warp_slot0 == 0 && lane == 0) counts[img] = min(total, cap);
+    const int total = min(s_end[P.n_levels], cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[img] = total;
+    const int grp = lane >> 3, l8 = lane & 7;
+    const unsigned gmask = 0xffu << (8 * grp);
+    uint8_t* buf = s_buf + (size_t)(warp * DESC_KPW + grp) * BUF_BYTES;
+    const unsigned buf_s = (unsigned)__cvta_generic_to_shared(buf);
+    const int n_rounds = (total + DESC_KPW - 1) / DESC_KPW;
+    const int round_stride = gridDim.x * DESC_WARPS;
 
-    for (int q = 0; q < DESC_KPW; ++q) {
-        const int slot = warp_slot0 + q;
-        if (slot >= total || slot >= cap) return;                       // warp-uniform
-        const int level = __popc(__ballot_sync(0xffffffffu, lane < P.n_levels && slot >= my_end));
-        const int lvl_end = __shfl_sync(0xffffffffu, my_end, level);
-        const int n_quad = __shfl_sync(0xffffffffu, my_nq, level), n_sd = __shfl_sync(0xffffffffu, my_ns, level);
-        const int j = slot - (lvl_end - n_quad - n_sd);
-        const LevelGeom& g = P.lv[level];
-        const int pitch = g.pitch;
-        const uint8_t* im = pyr + (size_t)img * P.pyr_bytes + g.img_off;
-        const uint8_t* bl = blur + (size_t)img * P.pyr_bytes + g.img_off;
-
-        mcv_keypoint kp;
-        int cx, cy;
+    // slot -> level, centre. `pt` = packed quadtree point (level coordinates - BORDER); a pre-seeded keypoint is the
+    // (j - n_quad)-th seed of its octave in the caller's order (ORBextractor.cc:845-847)
+    auto decode = [&](int slot, bool& valid, int& level, int& cx, int& cy, int& seed_idx, uint32_t& pt) {
+        valid = slot < total; level = 0; cx = cy = 0; seed_idx = -1; pt = 0;
+        if (!valid) return;
+        while (level + 1 < P.n_levels && slot >= s_end[level + 1]) ++level;
+        const int n_quad = s_nq[level];
+        const int j = slot - s_end[level];
         if (j < n_quad) {
-            const uint32_t p = out_pts[(size_t)img * P.out_per_image + g.out_off + j];
-            cx = pt_x(p) + BORDER; cy = pt_y(p) + BORDER;
-            kp.x = (float)cx; kp.y = (float)cy;
-            kp.size = (float)g.kp_size; kp.response = (float)pt_r(p); kp.octave = level; kp.class_id = -1;
-            // IC_Angle: lane = (row group r4, word k); 8 rounds of 4 rows. The row's 31 patch bytes start at alignment `a` of the
-            // first aligned word (level rows are 4-byte aligned), so lane k funnel-shifts words k, k+1 into its 4 patch pixels.
-            const int r4 = lane >> 3, k = lane & 7;
-            const int a8 = ((cx - 15) & 3) * 8;
-            const uint8_t* p0 = im + (size_t)(cy - 15) * pitch + ((cx - 15) & ~3) + 4 * k;
-            int m10 = 0, m01 = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = 4 * i + r4;
-                const uint8_t* pr = p0 + min(row, 30) * pitch;          // row 31 has zero weights
-                const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(pr)), w1 = __ldg(reinterpret_cast<const unsigned*>(pr + 4));
-                const unsigned w = __funnelshift_r(w0, w1, a8);
-                m10 = dp4a_us(w, s_wu[row][k], m10);
-                m01 += (row - 15) * (int)__dp4a(w, s_one[row][k], 0u);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-            kp.angle = fast_atan2_deg((float)m01, (float)m10);
+            pt = __ldg(out_pts + (size_t)img * P.out_per_image + P.lv[level].out_off + j);
+            cx = pt_x(pt) + BORDER; cy = pt_y(pt) + BORDER;
         } else {
-            // pre-seeded keypoint: the (j - n_quad)-th seed of this octave, in the caller's order (ORBextractor.cc:845-847)
             int k = j - n_quad, s = 0;
             for (; s < n_seeds; ++s) if (seeds[s].octave == level && k-- == 0) break;
-            kp = seeds[s];
-            cx = cv_round_f(kp.x); cy = cv_round_f(kp.y);
+            seed_idx = s;
+            cx = cv_round_f(seeds[s].x); cy = cv_round_f(seeds[s].y);
         }
-        // steered BRIEF
-        const float ang = __fmul_rn(kp.angle, 0.017453292519943295f);  // factorPI = (float)(CV_PI / 180.f)
-        float a, b;
-        sincosf_glibc(ang, &b, &a);  // a = cos, b = sin
-        const uint8_t* center = bl + (size_t)cy * pitch + cx;
-        unsigned val = 0;
+    };
+
+    int round = blockIdx.x * DESC_WARPS + warp;
+    bool valid, valid_n; int level, level_n, cx, cx_n, cy, cy_n, seed_idx, seed_idx_n; uint32_t pt, pt_n;
+    decode(round * DESC_KPW + grp, valid, level, cx, cy, seed_idx, pt);
+    unsigned parity = 0;
+    for (; round < n_rounds; round += round_stride) {                   // warp-uniform
+        const int slot = round * DESC_KPW + grp;
+        const unsigned n_valid = __popc(__ballot_sync(0xffffffffu, valid)) >> 3;   // groups with a keypoint (>= 1 here)
+        if (lane == 0) mbar_expect_tx(mbar, n_valid * (unsigned)(TILE_BYTES + IC_BYTES));
+        __syncwarp();
+        if (valid && l8 == 0) {
+            tma_load_3d(buf_s, &maps.blur[level], (cx - TILE_R) & ~15, cy - TILE_R, img, mbar);
+            tma_load_3d(buf_s + BUF_IC_OFF, &maps.pyr[level], (cx - 15) & ~15, cy - 15, img, mbar);
+        }
+        // the warp's next round: its windows go to L2 now
+        decode(slot + round_stride * DESC_KPW, valid_n, level_n, cx_n, cy_n, seed_idx_n, pt_n);
+        if (DESC_PREFETCH && valid_n && l8 == 0) {
+            tma_prefetch_3d(&maps.blur[level_n], (cx_n - TILE_R) & ~15, cy_n - TILE_R, img);
+            tma_prefetch_3d(&maps.pyr[level_n], (cx_n - 15) & ~15, cy_n - 15, img);
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        if (valid) {                                                    // whole groups; the shuffles below are group-wide
+            const LevelGeom& g = P.lv[level];
+            mcv_keypoint kp;
+            if (seed_idx < 0) {
+                kp.x = (float)cx; kp.y = (float)cy;
+                kp.size = (float)g.kp_size; kp.response = (float)pt_r(pt); kp.octave = level; kp.class_id = -1;
+                // IC_Angle: lane l8 owns patch columns 4 l8 .. 4 l8 + 3 of every row; the row's 31 patch bytes start `ox` bytes
+                // into the staged row. The four groups walk the rows with an offset of grp so that their loads (buffers are
+                // 128-byte aligned) spread over the banks.
+                const int ox = (cx - 15) & 15, a8 = (ox & 3) * 8;
+                const unsigned* ic = reinterpret_cast<const unsigned*>(buf + BUF_IC_OFF) + (ox >> 2) + l8;
+                int m10 = 0, m01 = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float2 q0 = s_pat[2 * k][lane], q1 = s_pat[2 * k + 1][lane];
-            const int r0 = cv_round_f(__fadd_rn(__fmul_rn(q0.x, b), __fmul_rn(q0.y, a))), c0 = cv_round_f(__fsub_rn(__fmul_rn(q0.x, a), __fmul_rn(q0.y, b)));
-            const int r1 = cv_round_f(__fadd_rn(__fmul_rn(q1.x, b), __fmul_rn(q1.y, a))), c1 = cv_round_f(__fsub_rn(__fmul_rn(q1.x, a), __fmul_rn(q1.y, b)));
-            const int t0 = center[r0 * pitch + c0], t1 = center[r1 * pitch + c1];
-            val |= (unsigned)(t0 < t1) << k;
+                for (int i = 0; i < IC_ROWS; ++i) {
+                    int row = i + grp;
+                    row = row >= IC_ROWS ? row - IC_ROWS : row;
+                    const unsigned w = __funnelshift_r(ic[row * (IC_PITCH / 4)], ic[row * (IC_PITCH / 4) + 1], a8);
+                    m10 = dp4a_us(w, s_wu[row][l8], m10);
+                    m01 = dp4a_us(w, s_wv[row][l8], m01);
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) { m10 += __shfl_xor_sync(gmask, m10, o); m01 += __shfl_xor_sync(gmask, m01, o); }
+                kp.angle = fast_atan2_deg((float)m01, (float)m10);
+            } else {
+                kp = seeds[seed_idx];
+            }
+            // steered BRIEF
+            const float ang = __fmul_rn(kp.angle, 0.017453292519943295f);  // factorPI = (float)(CV_PI / 180.f)
+            float a, bs;
+            sincosf_glibc(ang, &bs, &a);  // a = cos, bs = sin
+            // cvRound by the 1.5 * 2^23 trick (round-half-even like cvRound's lrint; |v| < 19): integer = float bits -
+            // 0x4B400000, and that constant, times 65 for row * 64 + column, is folded into the window's base offset (mod 2^32)
+            constexpr float MAGIC = 12582912.0f;
+            const unsigned base = (unsigned)(TILE_R * TILE_PITCH + TILE_R + ((cx - TILE_R) & 15)) - (unsigned)(TILE_PITCH + 1) * 0x4B400000u;
+            unsigned val = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float2 q0 = s_pat[2 * k][l8], q1 = s_pat[2 * k + 1][l8];
+                const unsigned r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q0.x, bs), __fmul_rn(q0.y, a)), MAGIC));
+                const unsigned c0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q0.x, a), __fmul_rn(q0.y, bs)), MAGIC));
+                const unsigned r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q1.x, bs), __fmul_rn(q1.y, a)), MAGIC));
+                const unsigned c1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q1.x, a), __fmul_rn(q1.y, bs)), MAGIC));
+                const int t0 = buf[r0 * TILE_PITCH + c0 + base], t1 = buf[r1 * TILE_PITCH + c1 + base];
+                val |= (unsigned)(t0 < t1) << k;
+            }
+            reinterpret_cast<unsigned*>(desc + ((size_t)img * cap + slot) * 32)[l8] = val;   // bytes 4 l8 .. 4 l8 + 3, little endian
+            if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }
+            if (l8 == 0) kps[(size_t)img * cap + slot] = kp;
         }
-        desc[((size_t)img * cap + slot) * 32 + lane] = (uint8_t)val;
-        if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }
-        if (lane == 0) kps[(size_t)img * cap + slot] = kp;
+        // the buffers are about to be overwritten through the async proxy: order the generic-proxy reads before it
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        valid = valid_n; level = level_n; cx = cx_n; cy = cy_n; seed_idx = seed_idx_n; pt = pt_n;
     }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+static bool encode_level_map(CUtensorMap* m, const uint8_t* base, const Plan& P, int level, int n_images, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const LevelGeom& g = P.lv[level];
+    const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.h, (cuuint64_t)n_images};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)P.pyr_bytes};    // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u}, estr[3] = {1u, 1u, 1u};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base) + g.img_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blur, const uint32_t* d_out_pts, const int* d_out_cnt,
@@ -135,9 +272,19 @@ int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blu
     const int n_seeds = seeds ? seeds->n_seeds : 0;
     const int max_kp = std::max(1, std::min(cap, P.max_quad_kp + n_seeds));
     constexpr int per_cta = DESC_WARPS * DESC_KPW;
-    dim3 grid((max_kp + per_cta - 1) / per_cta, n_images);
-    k_orient_desc<<<grid, 32 * DESC_WARPS, 0, s>>>(d_pyr, d_blur, d_out_pts, d_out_cnt, seeds ? seeds->d_seeds : nullptr, n_seeds, d_kps,
-                                                  d_desc, d_counts, cap, P);
+    const int ctas_per_image = std::max(1, std::min((max_kp + per_cta - 1) / per_cta, (DESC_WAVES * 3 * NUM_SMS + n_images - 1) / n_images));
+    dim3 grid(ctas_per_image, n_images);
+    DescMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int l = 0; l < P.n_levels; ++l)
+        if (!encode_level_map(&maps.pyr[l], d_pyr, P, l, n_images, IC_PITCH, IC_ROWS) ||
+            !encode_level_map(&maps.blur[l], d_blur, P, l, n_images, TILE_PITCH, TILE_ROWS)) {
+            set_error("cuTensorMapEncodeTiled failed for the orientation / descriptor windows");
+            return -1;
+        }
+    cudaFuncSetAttribute(k_orient_desc, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_DYN_SMEM);   // per device; cheap
+    k_orient_desc<<<grid, 32 * DESC_WARPS, DESC_DYN_SMEM, s>>>(maps, d_out_pts, d_out_cnt, seeds ? seeds->d_seeds : nullptr, n_seeds, d_kps,
+                                                              d_desc, d_counts, cap, P);
     return 1;
 }
 

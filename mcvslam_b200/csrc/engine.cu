@@ -267,8 +267,10 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     if (r < 0) { set_error("nfeatures too large for the quadtree kernel's shared-memory heap"); return MCV_ERR_CAPACITY; }
     n += r;
     prof_mark(h, 5);
-    n += launch_orient_desc(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), seeds, d_kps,
-                            d_desc, d_counts, cap, n_images, h->stream);
+    const int rd = launch_orient_desc(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), seeds, d_kps,
+                                      d_desc, d_counts, cap, n_images, h->stream);
+    if (rd < 0) return MCV_ERR_CUDA;
+    n += rd;
     prof_mark(h, 6);
     MCV_CUDA(cudaGetLastError());
     h->last_images = n_images; h->last_cap = cap; h->last_launches = n;
