@@ -80,6 +80,10 @@ struct mcv_orb {
     bool profile = false;
     std::vector<cudaEvent_t> ev;   // PROF_RING calls x (N_STAGES + 1) events
     int prof_calls = 0;
+    // optional: the latency-bound quadtree kernel runs on its own highest-priority stream, fenced by two events, so that its
+    // few-warp CTAs are dispatched ahead of the stencil CTAs of whatever chunk is running beside it (rig slots only)
+    cudaStream_t quad_stream = nullptr;
+    cudaEvent_t quad_in = nullptr, quad_out = nullptr;
 };
 
 constexpr int N_STAGES = 8;   // pyramid, blur, fast_score, nms_cells, quadtree, orient_desc, stereo_match, stereo_median
@@ -262,8 +266,18 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
                            (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 3] : nullptr);
     if (signal_front) MCV_CUDA(cudaEventRecord(signal_front, h->stream));
     prof_mark(h, 4);
+    cudaStream_t qs = h->stream;
+    if (h->quad_stream && !h->profile) {
+        MCV_CUDA(cudaEventRecord(h->quad_in, h->stream));
+        MCV_CUDA(cudaStreamWaitEvent(h->quad_stream, h->quad_in, 0));
+        qs = h->quad_stream;
+    }
     const int r = launch_octree(P, h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->arena_a.as<uint32_t>(), h->arena_b.as<uint32_t>(),
-                                h->oct_idx.as<uint16_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, h->stream);
+                                h->oct_idx.as<uint16_t>(), h->out_pts.as<uint32_t>(), h->out_cnt.as<int>(), n_images, qs);
+    if (qs != h->stream) {
+        MCV_CUDA(cudaEventRecord(h->quad_out, qs));
+        MCV_CUDA(cudaStreamWaitEvent(h->stream, h->quad_out, 0));
+    }
     if (r < 0) { set_error("nfeatures too large for the quadtree kernel's shared-memory heap"); return MCV_ERR_CAPACITY; }
     n += r;
     prof_mark(h, 5);
@@ -315,6 +329,7 @@ void mcv_orb_destroy(mcv_orb* h) {
         b->release();
     h->h_stage.release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->quad_stream) { cudaStreamDestroy(h->quad_stream); cudaEventDestroy(h->quad_in); cudaEventDestroy(h->quad_out); }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -980,8 +995,10 @@ struct mcv_rig {
     int chunk_frames_dev = 128;     // device-resident path: consecutive calls overlap instead (see mcv_rig_process_async)
     int next_slot = 0;              // chunks rotate over the slots across calls
     int use_slots = RIG_SLOTS;      // host path: slots in rotation (env MCV_RIG_SLOTS)
-    int use_slots_dev = 1;          // device-resident path (env MCV_RIG_SLOTS_DEV): measured on B200, running whole batches
-                                    // back to back on ONE stream beats overlapping them (28.8k vs 25.0k frames/s, profiles/)
+    int use_slots_dev = 2;          // device-resident path (env MCV_RIG_SLOTS_DEV): consecutive calls alternate between two
+                                    // streams, so the latency-bound quadtree of one batch runs beside the stencils of the next
+                                    // (B200, current kernels: 34.0k frames/s on one stream, 37.3k on two, 37.3k on three; a
+                                    // dedicated high-priority quadtree stream, MCV_RIG_QUAD_PRIORITY=1, changes nothing)
     cudaEvent_t last_front = nullptr;   // front-half event of the most recently enqueued chunk
     cudaEvent_t ticket[RIG_TICKETS] = {};   // completion of the last RIG_TICKETS mcv_rig_submit calls
     long long submitted = 0;                // number of mcv_rig_submit calls so far (ticket ids start at 1)
@@ -1077,6 +1094,16 @@ mcv_status mcv_rig_create(const mcv_rig_params* p, int device, void* stream, mcv
         if (st) { for (int k = 0; k < i; ++k) mcv_orb_destroy(r->slot[k].orb); delete r; return st; }
         cudaEventCreateWithFlags(&r->slot[i].done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&r->slot[i].front, cudaEventDisableTiming);
+        if (const char* e = getenv("MCV_RIG_QUAD_PRIORITY")) {
+            if (atoi(e) > 0) {
+                int lo = 0, hi = 0;
+                cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
+                mcv_orb* h = r->slot[i].orb;
+                cudaStreamCreateWithPriority(&h->quad_stream, cudaStreamNonBlocking, hi);
+                cudaEventCreateWithFlags(&h->quad_in, cudaEventDisableTiming);
+                cudaEventCreateWithFlags(&h->quad_out, cudaEventDisableTiming);
+            }
+        }
     }
     cudaEventCreateWithFlags(&r->fork, cudaEventDisableTiming);
     if (stream) r->stream = (cudaStream_t)stream;
