@@ -260,6 +260,19 @@ mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1,
 mcv_status mcv_distinctive_descriptors(const uint8_t* desc, const int32_t* mp_off, int n_mp, int32_t* best_idx, int32_t* best_median,
                                        uint8_t* out_desc);
 
+/* KL_Track's optical flow (src/Frame.cpp:52-54): cv::calcOpticalFlowPyrLK(prev, next, pts, next_pts, res, err, Size(10, 10), 1,
+ * TermCriteria(COUNT + EPS, 10, 0.01), 0, 0.001) on two 8-bit gray host images of the same size. pts / next_pts = n (x, y)
+ * pairs, status = res, err = the L1 window residual / 32. Bit-exact with an SSE-baseline x86-64 OpenCV 4 (oracle pinned
+ * against cv2 4.13). */
+mcv_status mcv_lk_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const float* pts, int n, float* next_pts,
+                        uint8_t* status, float* err);
+/* KL_Track (src/Frame.cpp:34-76) without the MapPoint bookkeeping: kps = obj1->kps[GetMapPointIdx(mp)] in the order of
+ * GetMapPointsVector(). ok[i] = res[i] > 0 && err[i] < 1 (:57-58); new_kps[i] (valid where ok[i]) = the keypoint :65-69 pushes
+ * onto obj2->kps: kps[i] with pt = next_pts[i] and octave = 0. With fewer than 10 points nothing is tracked (:41). The caller
+ * keeps the mp2idx map (skip MapPoints already seen, :61-63). */
+mcv_status mcv_kl_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const mcv_keypoint* kps, int n, mcv_keypoint* new_kps,
+                        uint8_t* ok, int* n_ok);
+
 /* Object::ComputeBow (src/Object.cpp:238-247): DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
  * (modules/DBow3/src/Vocabulary.cpp:572-672). The vocabulary is handed over once as flat arrays — what a maintainer gets by
  * walking DBoW3's m_nodes after Vocabulary::load: child_off [n_nodes+1] / child_ids = m_nodes[i].children in stored order

@@ -31,7 +31,7 @@ EXPORTS = [
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
     "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_set_input_channels", "mcv_orb_set_input_channels", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
-    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_distinctive_descriptors", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
+    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_distinctive_descriptors", "mcv_lk_track", "mcv_kl_track", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
 ]
 
@@ -106,6 +106,8 @@ def lib():
         L.mcv_fuse_match.argtypes = [vp, vp, i, i, i, vp, vp, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, i, vp, vp, C.POINTER(i)]
         L.mcv_wnd_track.argtypes = [vp, vp, i, vp, i, vp, vp, i, i, i, vp, vp, vp, C.POINTER(i)]
         L.mcv_distinctive_descriptors.argtypes = [vp, vp, i, vp, vp, vp]
+        L.mcv_lk_track.argtypes = [vp, vp, i, i, C.c_size_t, vp, i, vp, vp, vp]
+        L.mcv_kl_track.argtypes = [vp, vp, i, i, C.c_size_t, vp, i, vp, vp, C.POINTER(i)]
         L.mcv_voc_create.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(vp)]
         L.mcv_voc_destroy.argtypes = [vp]
         L.mcv_voc_destroy.restype = None
@@ -413,6 +415,26 @@ def ComputeDistinctiveDescriptors(desps, off):
     bi = np.full(n_mp, -1, np.int32); bm = np.full(n_mp, -1, np.int32); od = np.zeros((n_mp, 32), np.uint8)
     _check(lib().mcv_distinctive_descriptors(_p(desps), _p(off), n_mp, _p(bi), _p(bm), _p(od)))
     return bi, bm, od
+
+
+def LkTrack(prev, nxt, pts):
+    """cv::calcOpticalFlowPyrLK as KL_Track calls it (src/Frame.cpp:52-54). Returns (next_pts [n, 2], status, err)."""
+    prev = _u8(prev); nxt = _u8(nxt)
+    assert prev.shape == nxt.shape and prev.ndim == 2
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); n = len(pts)
+    out = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+    _check(lib().mcv_lk_track(_p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(pts), n, _p(out), _p(st), _p(err)))
+    return out, st, err
+
+
+def KL_Track(prev, nxt, kps):
+    """KL_Track (src/Frame.cpp:34-76) without the MapPoint map. Returns (cnt, new_kps, ok)."""
+    prev = _u8(prev); nxt = _u8(nxt)
+    assert prev.shape == nxt.shape and prev.ndim == 2
+    kps = np.ascontiguousarray(kps, KP_DTYPE); n = len(kps)
+    new = np.zeros(n, KP_DTYPE); ok = np.zeros(n, np.uint8); cnt = C.c_int(0)
+    _check(lib().mcv_kl_track(_p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(kps), n, _p(new), _p(ok), C.byref(cnt)))
+    return cnt.value, new, ok
 
 
 class Vocabulary:

@@ -805,6 +805,59 @@ mcv_status mcv_distinctive_descriptors(const uint8_t* desc, const int32_t* mp_of
     return MCV_OK;
 }
 
+// ---- KL_Track (src/Frame.cpp:34-76): cv::calcOpticalFlowPyrLK with the reference's fixed arguments ----
+mcv_status mcv_lk_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const float* pts, int n, float* next_pts,
+                        uint8_t* status, float* err) {
+    if (!prev || !next || n < 0 || (n > 0 && (!pts || !next_pts || !status || !err))) return MCV_ERR_BAD_ARG;
+    if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
+    if (stride < (size_t)w) return MCV_ERR_BAD_ARG;
+    cudaStream_t s;
+    mcv_status st = match_stream(&s);
+    if (st) return st;
+    static DevBuf b_img, b_ws, b_pts, b_out, b_st, b_err;
+    const size_t img_bytes = (size_t)w * hgt;
+    if ((st = b_img.reserve(2 * img_bytes))) return st;
+    if ((st = b_ws.reserve(lk_workspace_bytes(w, hgt)))) return st;
+    if ((st = b_pts.reserve(std::max<size_t>(8, (size_t)n * 8)))) return st;
+    if ((st = b_out.reserve(std::max<size_t>(8, (size_t)n * 8)))) return st;
+    if ((st = b_st.reserve(std::max<size_t>(4, (size_t)n)))) return st;
+    if ((st = b_err.reserve(std::max<size_t>(4, (size_t)n * 4)))) return st;
+    MCV_CUDA(cudaMemcpy2DAsync(b_img.p, w, prev, stride, w, hgt, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpy2DAsync(b_img.as<uint8_t>() + img_bytes, w, next, stride, w, hgt, cudaMemcpyHostToDevice, s));
+    if (n) MCV_CUDA(cudaMemcpyAsync(b_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    launch_lk_track(b_img.as<uint8_t>(), b_img.as<uint8_t>() + img_bytes, w, hgt, w, b_ws.p, b_pts.as<float>(), n, b_out.as<float>(), b_st.as<uint8_t>(),
+                    b_err.as<float>(), s);
+    MCV_CUDA(cudaGetLastError());
+    if (n) {
+        MCV_CUDA(cudaMemcpyAsync(next_pts, b_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MCV_CUDA(cudaMemcpyAsync(status, b_st.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+        MCV_CUDA(cudaMemcpyAsync(err, b_err.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    MCV_CUDA(cudaStreamSynchronize(s));
+    return MCV_OK;
+}
+
+mcv_status mcv_kl_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const mcv_keypoint* kps, int n, mcv_keypoint* new_kps,
+                        uint8_t* ok, int* n_ok) {
+    if (n < 0 || (n > 0 && (!kps || !new_kps || !ok))) return MCV_ERR_BAD_ARG;
+    if (n_ok) *n_ok = 0;
+    for (int i = 0; i < n; ++i) ok[i] = 0;
+    if (n < 10) return (!prev || !next) ? MCV_ERR_BAD_ARG : MCV_OK;     // src/Frame.cpp:41
+    std::vector<float> pts((size_t)2 * n), nxt((size_t)2 * n), err((size_t)n);
+    std::vector<uint8_t> status((size_t)n);
+    for (int i = 0; i < n; ++i) { pts[2 * i] = kps[i].x; pts[2 * i + 1] = kps[i].y; }
+    mcv_status st = mcv_lk_track(prev, next, w, hgt, stride, pts.data(), n, nxt.data(), status.data(), err.data());
+    if (st) return st;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i)
+        if (status[i] > 0 && err[i] < 1) {                                 // src/Frame.cpp:57-58
+            ok[i] = 1; ++cnt;
+            new_kps[i] = kps[i]; new_kps[i].x = nxt[2 * i]; new_kps[i].y = nxt[2 * i + 1]; new_kps[i].octave = 0;   // :65-68
+        }
+    if (n_ok) *n_ok = cnt;
+    return MCV_OK;
+}
+
 // ---- Object::ComputeBow: DBoW3 vocabulary on the device + Vocabulary::transform ----
 struct mcv_voc {
     int device = 0, n_nodes = 0, L = 0, weighting = 0, norm = 1;

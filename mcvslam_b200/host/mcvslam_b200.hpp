@@ -505,6 +505,33 @@ inline uint Wnd_Track(const Object& obj1, const std::vector<int>& mp_kp_idxs, co
     if (matched_dist) matched_dist->assign(od.begin(), od.begin() + nq);
     return (uint)cnt;
 }
+// KL_Track(obj1, obj2, mp2idx) (src/Frame.cpp:34-76). MapPoints are opaque to this layer: mp_kp_idxs[i] =
+// obj1->GetMapPointIdx(mps[i]) in the order of obj1->GetMapPointsVector(), seen[i] = mp2idx.count(mps[i]) on entry (updated
+// like mp2idx[mps[i]] = ... at :65). Appends the tracked keypoints to obj2.kps exactly like :65-69 (pt = next_pts[i],
+// octave = 0), new_idx[i] = the index the reference stores in mp2idx, or -1. Returns cnt.
+inline uint KL_Track(const Object& obj1, const std::vector<int>& mp_kp_idxs, Object& obj2, std::vector<uint8_t>& seen, std::vector<int>& new_idx) {
+    const int n = (int)mp_kp_idxs.size();
+    new_idx.assign((size_t)n, -1);
+    seen.resize((size_t)n, 0);
+    if (n < 10) return 0;                                                  // :41
+    std::vector<cv::KeyPoint> kps((size_t)n), nk((size_t)n);
+    for (int i = 0; i < n; ++i) kps[(size_t)i] = obj1.kps[(size_t)mp_kp_idxs[(size_t)i]];
+    std::vector<uint8_t> ok((size_t)n);
+    int n_ok = 0;
+    const cv::Mat a = obj1.img.isContinuous() ? obj1.img : obj1.img.clone(), b = obj2.img.isContinuous() ? obj2.img : obj2.img.clone();
+    const mcv_status st = mcv_kl_track(a.data, b.data, a.cols, a.rows, (size_t)a.cols, mcv_host::kp_ptr(kps), n, mcv_host::kp_ptr(nk), ok.data(), &n_ok);
+    if (st != MCV_OK) throw std::runtime_error(std::string("KL_Track: ") + mcv_last_error());
+    uint cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!ok[(size_t)i] || seen[(size_t)i]) continue;                   // :57-63
+        seen[(size_t)i] = 1;
+        new_idx[(size_t)i] = (int)obj2.kps.size();
+        obj2.kps.push_back(nk[(size_t)i]);
+        cnt++;
+    }
+    return cnt;
+}
+
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cpp:101-150) on the descriptors the point was observed with
 // (`all_ob_desps`, the vector the reference builds at :108-115). Returns what the reference assigns to MapPoint::desp — a
 // clone of the row with the least median distance to the others — or an empty Mat where the reference returns early.

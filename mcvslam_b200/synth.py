@@ -84,3 +84,17 @@ def random_vocabulary(seed, K=10, L=4, weighting=0, norm=1, stop_fraction=0.02, 
     weight[leaves] = w if weighting in (0, 2) else np.where(w > 0, 1.0, 0.0)
     return dict(child_off=child_off, child_ids=np.array(ids, np.uint32), node_desc=np.stack(desc), word_id=word_id, weight=weight, L=L, K=K,
                 weighting=weighting, norm=norm)
+
+
+def shifted(img, dx, dy, seed, noise=3):
+    """`img` translated by the fractional offset (dx, dy) (pure-numpy bilinear blend of four integer shifts, edges wrap) plus
+    fresh +-`noise` noise: the second frame of a synthetic optical-flow pair."""
+    fx, fy = int(np.floor(dx)), int(np.floor(dy))
+    ax, ay = float(dx - fx), float(dy - fy)
+    f = img.astype(np.float64)
+    s00 = np.roll(f, (fy, fx), (0, 1)); s01 = np.roll(f, (fy, fx + 1), (0, 1))
+    s10 = np.roll(f, (fy + 1, fx), (0, 1)); s11 = np.roll(f, (fy + 1, fx + 1), (0, 1))
+    out = (1 - ay) * ((1 - ax) * s00 + ax * s01) + ay * ((1 - ax) * s10 + ax * s11)
+    rng = np.random.default_rng(seed)
+    out = np.rint(out) + (rng.integers(-noise, noise + 1, img.shape) if noise > 0 else 0)
+    return np.clip(out, 0, 255).astype(np.uint8)

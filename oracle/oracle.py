@@ -19,7 +19,7 @@ assert KP_DTYPE.itemsize == 28 and DM_DTYPE.itemsize == 16
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "ora_primitives.hpp", "ora_pattern.inc", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "ora_primitives.hpp", "ora_lk.hpp", "ora_pattern.inc", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
     return _SO
@@ -294,6 +294,30 @@ def distinctive(desc, off):
     L.ora_distinctive.restype = None
     L.ora_distinctive(_p(desc), _p(off), n_mp, _p(bi), _p(bm))
     return bi, bm
+
+
+def lk_track(prev, nxt, pts):
+    """cv::calcOpticalFlowPyrLK as KL_Track calls it (src/Frame.cpp:52-54). pts [n, 2] float32. Returns (next_pts, status, err)."""
+    prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); n = len(pts)
+    out = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+    L = lib()
+    L.ora_lk_track.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ora_lk_track.restype = None
+    L.ora_lk_track(_p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(pts), n, _p(out), _p(st), _p(err))
+    return out, st, err
+
+
+def kl_track(prev, nxt, kps):
+    """KL_Track (src/Frame.cpp:34-76) without the MapPoint map: returns (cnt, new_kps, ok, next_pts, status, err)."""
+    prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
+    kps = np.ascontiguousarray(kps, KP_DTYPE); n = len(kps)
+    new = np.zeros(n, KP_DTYPE); ok = np.zeros(n, np.uint8)
+    out = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+    L = lib()
+    L.ora_kl_track.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    cnt = L.ora_kl_track(_p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(kps), n, _p(new), _p(ok), _p(out), _p(st), _p(err))
+    return cnt, new, ok, out, st, err
 
 
 def bow_transform(desc, voc, levelsup=4):

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "ora_primitives.hpp"
+#include "ora_lk.hpp"
 
 using namespace std;  // as the reference does (ORBextractor.cc:67) — this is what makes cos(float) resolve to cosf
 
@@ -768,6 +769,33 @@ void ora_distinctive(const uint8_t* desc, const int* off, int n_mp, int* best_id
         }
         best_idx[m] = BestIdx; best_median[m] = BestMedian;
     }
+}
+
+// ---- KL_Track's optical flow (src/Frame.cpp:52-54): cv::calcOpticalFlowPyrLK with the reference's fixed arguments; see
+// ora_lk.hpp for the restatement and how it is pinned. pts / next_pts are (x, y) pairs.
+void ora_lk_track(const uint8_t* prev, const uint8_t* next, int w, int h, int stride, const float* pts, int n, float* next_pts, uint8_t* status,
+                  float* err) {
+    ora_lk::calc_lk(prev, next, w, h, stride, pts, n, next_pts, status, err);
+}
+// KL_Track (src/Frame.cpp:34-76) minus the MapPoint bookkeeping: kps = obj1->kps[GetMapPointIdx(mp)] in the order of
+// GetMapPointsVector(). ok[i] = res[i] > 0 && err[i] < 1 (:57-58); new_kps[i] = what :65-69 would push onto obj2->kps (kps[i]
+// with pt = next_pts[i], octave = 0), valid where ok[i]. The "fewer than 10 MapPoints -> return 0" gate (:41) applies: returns
+// 0 and clears ok. Returns the number of ok points (the caller still skips MapPoints it has already seen, :61-63).
+int ora_kl_track(const uint8_t* prev, const uint8_t* next, int w, int h, int stride, const KeyPoint* kps, int n, KeyPoint* new_kps, uint8_t* ok,
+                 float* next_pts, uint8_t* status, float* err) {
+    for (int i = 0; i < n; ++i) ok[i] = 0;
+    if (n < 10) return 0;
+    vector<float> pts((size_t)2 * n);
+    for (int i = 0; i < n; ++i) { pts[2 * i] = kps[i].x; pts[2 * i + 1] = kps[i].y; }
+    ora_lk::calc_lk(prev, next, w, h, stride, pts.data(), n, next_pts, status, err);
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        if (status[i] > 0 && err[i] < 1) {
+            ok[i] = 1; ++cnt;
+            new_kps[i] = kps[i]; new_kps[i].x = next_pts[2 * i]; new_kps[i].y = next_pts[2 * i + 1]; new_kps[i].octave = 0;
+        }
+    }
+    return cnt;
 }
 
 // ---- Object::ComputeBow (src/Object.cpp:238-247) = DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
