@@ -34,6 +34,9 @@ int ora_fuse_match(const cv::KeyPoint* kps, const uint8_t* desc, int n, int W, i
                    const uint8_t* mp_desc, const int* mp_level, int n_mp, int* out_idx, int* out_dist);
 int ora_wnd_track(const cv::KeyPoint* kps1, const uint8_t* desc1, const int* q_idx, int n_q, const cv::KeyPoint* kps2, const uint8_t* desc2, int n2, int W,
                   int H, int* out_idx, int* out_best, int* out_dist);
+void ora_distinctive(const uint8_t* desc, const int* off, int n_mp, int* best_idx, int* best_median);
+int ora_kl_track(const uint8_t* prev, const uint8_t* next, int w, int h, int stride, const cv::KeyPoint* kps, int n, cv::KeyPoint* new_kps, uint8_t* ok,
+                 float* next_pts, uint8_t* status, float* err);
 int ora_distribute_octree(const cv::KeyPoint* in, int n, int minX, int maxX, int minY, int maxY, int N, cv::KeyPoint* out, int cap);
 }
 
@@ -292,6 +295,37 @@ int main(int argc, char** argv) {
             const int wref = ora_wnd_track(ol.kps.data(), ol.desc.data(), q.data(), (int)q.size(), orr.kps.data(), orr.desc.data(), (int)orr.kps.size(), 640, 480,
                                            wi.data(), wb.data(), wdd.data());
             CHECK((int)wcnt == wref && wm == wi && wd == wdd, "Wnd_Track: %u vs %d", wcnt, wref);
+        }
+
+        // ---- MapPoint::ComputeDistinctiveDescriptors on a MapPoint observed by every 40th LEFT keypoint; KL_Track LEFT -> RIGHT ----
+        {
+            std::vector<cv::Mat> obs;
+            std::vector<uint8_t> rows;
+            for (int i = 0; i < nl; i += 40) { obs.push_back(frame.LEFT->desps.row(i)); rows.insert(rows.end(), ol.desc.begin() + (size_t)i * 32, ol.desc.begin() + (size_t)i * 32 + 32); }
+            int bi = -1, bm = -1, rbi = -1, rbm = -1;
+            const cv::Mat best = ComputeDistinctiveDescriptors(obs, &bi, &bm);
+            const int off[2] = {0, (int)obs.size()};
+            ora_distinctive(rows.data(), off, 1, &rbi, &rbm);
+            CHECK(bi == rbi && bm == rbm && memcmp(best.data, rows.data() + (size_t)bi * 32, 32) == 0, "ComputeDistinctiveDescriptors: %d/%d vs %d/%d", bi, bm, rbi, rbm);
+            std::vector<int> q;
+            for (int i = 0; i < nl; i += 4) q.push_back(i);
+            std::vector<cv::KeyPoint> sel(q.size()), rk(q.size());
+            for (size_t i = 0; i < q.size(); ++i) sel[i] = ol.kps[(size_t)q[i]];
+            std::vector<uint8_t> seen(q.size(), 0), rok(q.size()), rst(q.size());
+            seen[3] = 1;                                                  // a MapPoint an earlier frame already tracked (src/Frame.cpp:61-63)
+            std::vector<float> rnx(2 * q.size()), rerr(q.size());
+            ora_kl_track(left.data, right.data, 640, 480, 640, sel.data(), (int)q.size(), rk.data(), rok.data(), rnx.data(), rst.data(), rerr.data());
+            Object target(right, nullptr);
+            target.kps = orr.kps;
+            std::vector<int> new_idx;
+            const uint kcnt = KL_Track(*frame.LEFT, q, target, seen, new_idx);
+            uint want = 0; bool same = true; size_t at = orr.kps.size();
+            for (size_t i = 0; i < q.size(); ++i) {
+                if (!rok[i] || i == 3) { same &= new_idx[i] == -1; continue; }
+                same &= new_idx[i] == (int)at && memcmp(&target.kps[at], &rk[i], 28) == 0;
+                ++at; ++want;
+            }
+            CHECK(kcnt == want && same && target.kps.size() == at, "KL_Track: %u vs %u", kcnt, want);
         }
 
         // ---- batched rig == per-frame Frame ----
