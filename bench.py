@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matching", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="e2e leg: steps kept in flight through mcv_rig_submit (<= 8)")
     ap.add_argument("--chunk", type=int, default=None, help="frames per pipelined chunk inside the engine (default: engine default 32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -222,7 +223,8 @@ def main():
     d_ur = torch.empty(B * cap, dtype=torch.float32, device=dev); d_dp = torch.empty(B * cap, dtype=torch.float32, device=dev)
     # two sets of pinned result buffers: the e2e leg keeps two steps in flight (step k's results are read while step k+1 runs)
     h_out = []
-    for _ in range(2):
+    NF = max(1, min(8, args.inflight))
+    for _ in range(NF):
         h_out.append(dict(kps=torch.empty(kp_bytes, dtype=torch.uint8).pin_memory(), desc=torch.empty(B * 3 * cap * 32, dtype=torch.uint8).pin_memory(),
                           cnt=torch.zeros(B * 3, dtype=torch.int32).pin_memory(), ur=torch.empty(B * cap, dtype=torch.float32).pin_memory(),
                           dp=torch.empty(B * cap, dtype=torch.float32).pin_memory()))
@@ -246,13 +248,13 @@ def main():
         (its keypoint counts are read)."""
         tickets, total_kp = [], 0
         for k in range(n_steps):
-            o = h_out[k & 1]
-            if k >= 2:
-                rig.wait(tickets[k - 2]); total_kp += int(o["cnt"][0])
+            o = h_out[k % NF]
+            if k >= NF:
+                rig.wait(tickets[k - NF]); total_kp += int(o["cnt"][0])
             tickets.append(rig.submit(h_imgs.data_ptr(), B, W, H, o["kps"].data_ptr(), o["desc"].data_ptr(), o["cnt"].data_ptr(),
                                       o["ur"].data_ptr(), o["dp"].data_ptr()))
-        for k in range(max(0, n_steps - 2), n_steps):
-            rig.wait(tickets[k]); total_kp += int(h_out[k & 1]["cnt"][0])
+        for k in range(max(0, n_steps - NF), n_steps):
+            rig.wait(tickets[k]); total_kp += int(h_out[k % NF]["cnt"][0])
         return total_kp
 
     def barrier():
@@ -351,7 +353,7 @@ def main():
                        "collective": "all_gather of per-image keypoint counts per step (N>1 only)"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h_imgs.numel()),
                     "d2h_bytes_per_step": int(h_kps.numel() + h_desc.numel() + h_cnt.numel() * 4 + h_ur.numel() * 4 + h_dp.numel() * 4),
-                    "steps": args.steps, "how": "mcv_rig_submit / mcv_rig_wait on pinned host buffers, two steps in flight, wall clock; every "
+                    "steps": args.steps, "how": "mcv_rig_submit / mcv_rig_wait on pinned host buffers, %d steps in flight, wall clock; every " % NF +
                                                 "step's H2D and D2H inside the region",
                     "sync_call_value": e2e_sync_v, "sync_call_how": "one synchronous mcv_rig_process call per step (%d steps)" % e2e_steps},
             "gpu_launches": launches,
