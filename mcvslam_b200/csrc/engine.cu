@@ -261,9 +261,11 @@ static mcv_status enqueue_extract(mcv_orb* h, const uint8_t* d_imgs, size_t src_
     prof_mark(h, 1);
     n += launch_blur(P, h->pyr.as<uint8_t>(), h->blur.as<uint8_t>(), n_images, h->stream);
     prof_mark(h, 2);
-    n += launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->nz_list.as<unsigned>(), h->nz_cnt.as<int>(), h->cell_raw.as<uint32_t>(),
+    const int rf = launch_fast_cells(P, h->pyr.as<uint8_t>(), h->score.as<uint8_t>(), h->nz_list.as<unsigned>(), h->nz_cnt.as<int>(), h->cell_raw.as<uint32_t>(),
                            h->cell_pts.as<uint32_t>(), h->cell_cnt.as<int>(), h->fallback.as<int>(), n_images, h->stream,
                            (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 3] : nullptr);
+    if (rf < 0) return MCV_ERR_CUDA;
+    n += rf;
     if (signal_front) MCV_CUDA(cudaEventRecord(signal_front, h->stream));
     prof_mark(h, 4);
     cudaStream_t qs = h->stream;

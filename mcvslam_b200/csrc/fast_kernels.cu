@@ -27,7 +27,9 @@
 //
 // Candidate order over the level (cell-row-major, then row-major inside the cell) is rebuilt by the quadtree kernel from the
 // per-cell counts, so it matches vToDistributeKeys of the reference.
+#include <string.h>
 #include "engine.h"
+#include "tma.cuh"
 
 namespace mcv {
 
@@ -195,15 +197,20 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
 // ---------------------------------------------------------------------------------------------------------
 // sparse NMS: one warp per strip (same strip table as k_fast_score).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int NMS_WARPS = 8;
-constexpr int NMS_TW = 34;                      // tile words per row: the strip's 32 words + one word left and right
+constexpr int NMS_WARPS = 4;
+constexpr int NMS_TP = 128 + 32;                // tile pitch in bytes: the strip's 128 px + 16 on either side (TMA boxes start 16-byte aligned)
 constexpr int NMS_TR = FS_ROWS + 2;             // tile rows: the strip's rows + one above and below
+constexpr int NMS_TILE_BYTES = NMS_TR * NMS_TP;
+constexpr int NMS_TILE_STRIDE = (NMS_TILE_BYTES + 127) & ~127;
 
-__global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __restrict__ score, const unsigned* __restrict__ nz_list,
+struct LevelMaps { CUtensorMap m[MAX_LEVELS]; };   // per level: (pitch, h, n_images) u8 view of the score map, box NMS_TP x NMS_TR
+
+__global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const __grid_constant__ LevelMaps maps, const unsigned* __restrict__ nz_list,
                                                                const int* __restrict__ nz_cnt, uint32_t* __restrict__ cell_raw,
                                                                int* __restrict__ cell_cnt, const __grid_constant__ Plan P,
                                                                const __grid_constant__ StripTable T) {
-    __shared__ unsigned s_tile[NMS_WARPS][NMS_TR * NMS_TW];
+    __shared__ __align__(128) uint8_t s_tile[NMS_WARPS][NMS_TILE_STRIDE];
+    __shared__ __align__(8) unsigned long long s_mbar[NMS_WARPS];
     const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sid = blockIdx.x * NMS_WARPS + warp;
     if (sid >= P.n_fast_strips) return;
@@ -213,39 +220,28 @@ __global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __
     while (level + 1 < P.n_levels && sid >= T.first[level + 1]) ++level;
     const LevelGeom& g = P.lv[level];
     const int t = sid - T.first[level];
-    const int tx0 = BORDER + (t % T.strips_x[level]) * 128 - 4;           // level x of tile byte 0 (a multiple of 4)
+    const int tx0 = BORDER + (t % T.strips_x[level]) * 128 - 16;          // level x of tile byte 0 (a multiple of 16)
     const int ty0 = EDGE_THRESHOLD + (t / T.strips_x[level]) * FS_ROWS - 1;   // level y of tile row 0
-    const int pitch = g.pitch;
-    const uint8_t* S = score + (size_t)img * P.pyr_bytes + g.img_off;
-    unsigned* tile = s_tile[warp];
-    // stage the window: rows ty0 .. ty0 + NMS_TR - 1, words tx0/4 .. tx0/4 + 33. Bytes outside the level's detection region
-    // may hold anything (the dense map is only written inside it); the test below never reads them.
-    // (fully unrolled: all loads of a batch are in flight before the first store needs its data)
-    constexpr int TILE_ITERS = (NMS_TR * NMS_TW + 31) / 32;
-#pragma unroll
-    for (int k0 = 0; k0 < TILE_ITERS; k0 += 8) {
-        unsigned v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = (k0 + k) * 32 + lane;
-            const int r = i / NMS_TW, w = i - r * NMS_TW;
-            const int y = ty0 + r, x = tx0 + 4 * w;
-            v[k] = (k0 + k < TILE_ITERS && i < NMS_TR * NMS_TW && y < g.h && x + 4 <= pitch) ? __ldg(reinterpret_cast<const unsigned*>(S + (size_t)y * pitch + x)) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = (k0 + k) * 32 + lane;
-            if (k0 + k < TILE_ITERS && i < NMS_TR * NMS_TW) tile[i] = v[k];
-        }
+    // stage the window with ONE TMA box load: rows ty0 .. ty0 + NMS_TR - 1, bytes tx0 .. tx0 + 159; whatever lies outside the
+    // level comes back as zeros. Bytes outside the level's detection region may hold anything (the dense map is only written
+    // inside it); the test below never reads them. (The previous version staged the tile with 41 rounds of 32-bit loads per
+    // warp: 41 % of the kernel's instructions and nearly all of its long-scoreboard stalls.)
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar[warp]);
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(mbar, NMS_TILE_BYTES);
+        tma_load_3d((unsigned)__cvta_generic_to_shared(s_tile[warp]), &maps.m[level], tx0, ty0, img, mbar);
     }
     __syncwarp();
-    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+    mbar_wait(mbar, 0);
+    const uint8_t* tb = s_tile[warp];
     const unsigned* list = nz_list + ((size_t)img * P.n_fast_strips + sid) * FS_SEG;
     int* cnts = cell_cnt + (size_t)img * P.cells_per_image + g.cell_base;
     uint32_t* cells = cell_raw + (size_t)img * P.cand_per_image + g.cand_off;
     const float inv_wc = 1.0f / (float)g.w_cell, inv_hc = 1.0f / (float)g.h_cell;
     const int x_hi = g.w - EDGE_THRESHOLD, y_hi = g.h - EDGE_THRESHOLD;
-    constexpr int TP = NMS_TW * 4;                                        // tile pitch in bytes
+    constexpr int TP = NMS_TP;                                            // tile pitch in bytes
     for (int i0 = lane; i0 < count; i0 += 128) {
         unsigned ent[4];
 #pragma unroll
@@ -443,8 +439,13 @@ int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, uns
         k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_score, d_nz_list, d_nz_cnt, P, T,
                                                                                              two_pass ? P.ini_th : P.min_th);
     if (after_score) cudaEventRecord(after_score, s);   // stage boundary for mcv_rig_stage_ms
-    if (n > 0)
-        k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(d_score, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
+    if (n > 0) {
+        LevelMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        for (int l = 0; l < P.n_levels; ++l)
+            if (!encode_level_map(&maps.m[l], d_score, P, l, n_images, NMS_TP, NMS_TR)) { set_error("cuTensorMapEncodeTiled failed for the NMS tiles"); return -1; }
+        k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(maps, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
+    }
     k_cell_order<<<dim3((P.cells_per_image + ORD_WARPS - 1) / ORD_WARPS, n_images), 32 * ORD_WARPS, 0, s>>>(d_cell_raw, d_cell_pts, d_cell_cnt, P,
                                                                                                           two_pass ? d_fallback : nullptr);
     if (!two_pass) return 3;
