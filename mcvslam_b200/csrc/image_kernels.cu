@@ -128,7 +128,10 @@ constexpr int RS_ROWS = 16;   // output rows per warp (<= 32: lane j holds row j
 constexpr int RS_WARPS = 4;
 constexpr int RS_PREF = 4;    // source rows in flight per lane
 
-__global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
+#ifndef RS_MINB
+#define RS_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * RS_WARPS, RS_MINB) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
                                                                  int sw, int sh, int spitch, int soff, int dw, int dh, int dpitch, int doff,
                                                                  int strips_x, int n_strips) {
     const int img = blockIdx.y, lane = threadIdx.x & 31;
@@ -282,7 +285,10 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-__global__ void __launch_bounds__(32 * GB_WARPS) k_gauss7(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+#ifndef GB_MINB
+#define GB_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
                                                            const __grid_constant__ Plan P, const __grid_constant__ StripTable T) {
     const int img = blockIdx.y, lane = threadIdx.x & 31;
     const int sid = blockIdx.x * GB_WARPS + (threadIdx.x >> 5);

@@ -36,7 +36,8 @@ def test_flat_and_crowded_images(api, oracle):
 
 
 @pytest.mark.parametrize("w,h,prm", [(641, 479, (1200, 1.2, 8, 28, 15)), (1000, 333, (1500, 1.2, 5, 20, 7)), (250, 200, (300, 1.1, 3, 20, 7)),
-                                      (768, 576, (2000, 1.5, 4, 28, 15)), (512, 512, (2000, 1.2, 1, 28, 15))])
+                                      (768, 576, (2000, 1.5, 4, 28, 15)), (512, 512, (2000, 1.2, 1, 28, 15)),
+                                      (330, 250, (500, 1.2, 8, 20, 7))])   # last: level pitches below the 160-byte NMS / 64-byte rBRIEF TMA boxes
 def test_odd_geometries(api, oracle, w, h, prm):
     img = synth.scene(w * 7 + h, w, h)
     E = api.ORB(*prm); O = oracle.Orb(*prm)
