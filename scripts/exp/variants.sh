@@ -1,8 +1,6 @@
 run() { MCV_NVCC_EXTRA="$1" python -m mcvslam_b200.build --force > /dev/null 2>&1; timeout 200 python bench.py --steps 20 --no-cpu-baseline --no-matching $2 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['stage_ms_per_step']; print('$1 $2', round(d['value']), 'blur', round(s['blur'],3), 'pyr', round(s['pyramid'],3))"; }
-run "-DGB_MINB=1" ""
-run "-DGB_MINB=6" ""
-run "-DGB_MINB=7" ""
-run "-DGB_MINB=8" ""
-run "-DRS_MINB=10" ""
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['stage_ms_per_step']; print('$1 $2', round(d['value']), 'fast', round(s['fast_score'],3), 'nms', round(s['nms_cells'],3))"; }
+run "-DFS_MINB=5" ""
+run "-DFS_MINB=4" ""
+run "-DFS_MINB=6" ""
