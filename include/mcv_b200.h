@@ -266,6 +266,11 @@ mcv_status mcv_distinctive_descriptors(const uint8_t* desc, const int32_t* mp_of
  * against cv2 4.13). */
 mcv_status mcv_lk_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const float* pts, int n, float* next_pts,
                         uint8_t* status, float* err);
+/* The same for n_pairs image pairs in one call (the Frame constructor runs KL_Track once per earlier frame and camera,
+ * src/Frame.cpp:89-103): prev / next hold n_pairs images back to back (rows `stride` bytes apart, image k starts at row k * hgt),
+ * the points of pair k are pts[pt_off[k] .. pt_off[k + 1]). All pairs' points are tracked concurrently. */
+mcv_status mcv_lk_track_batch(const uint8_t* prev, const uint8_t* next, int n_pairs, int w, int hgt, size_t stride, const float* pts,
+                              const int32_t* pt_off, float* next_pts, uint8_t* status, float* err);
 /* KL_Track (src/Frame.cpp:34-76) without the MapPoint bookkeeping: kps = obj1->kps[GetMapPointIdx(mp)] in the order of
  * GetMapPointsVector(). ok[i] = res[i] > 0 && err[i] < 1 (:57-58); new_kps[i] (valid where ok[i]) = the keypoint :65-69 pushes
  * onto obj2->kps: kps[i] with pt = next_pts[i] and octave = 0. With fewer than 10 points nothing is tracked (:41). The caller

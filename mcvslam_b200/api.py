@@ -31,7 +31,7 @@ EXPORTS = [
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
     "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_set_input_channels", "mcv_orb_set_input_channels", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
-    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_distinctive_descriptors", "mcv_lk_track", "mcv_kl_track", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
+    "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_distinctive_descriptors", "mcv_lk_track", "mcv_lk_track_batch", "mcv_kl_track", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
     "mcv_debug_download_blurred", "mcv_debug_popc_peak", "mcv_debug_octree_clocks",
 ]
 
@@ -107,6 +107,7 @@ def lib():
         L.mcv_wnd_track.argtypes = [vp, vp, i, vp, i, vp, vp, i, i, i, vp, vp, vp, C.POINTER(i)]
         L.mcv_distinctive_descriptors.argtypes = [vp, vp, i, vp, vp, vp]
         L.mcv_lk_track.argtypes = [vp, vp, i, i, C.c_size_t, vp, i, vp, vp, vp]
+        L.mcv_lk_track_batch.argtypes = [vp, vp, i, i, i, C.c_size_t, vp, vp, vp, vp, vp]
         L.mcv_kl_track.argtypes = [vp, vp, i, i, C.c_size_t, vp, i, vp, vp, C.POINTER(i)]
         L.mcv_voc_create.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(vp)]
         L.mcv_voc_destroy.argtypes = [vp]
@@ -425,6 +426,20 @@ def LkTrack(prev, nxt, pts):
     out = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
     _check(lib().mcv_lk_track(_p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(pts), n, _p(out), _p(st), _p(err)))
     return out, st, err
+
+
+def LkTrackBatch(prev, nxt, pts_list):
+    """mcv_lk_track_batch: prev / nxt [n_pairs, h, w] u8, pts_list = one [n_k, 2] array per pair. Returns lists (next_pts, status, err)."""
+    prev = _u8(prev); nxt = _u8(nxt)
+    assert prev.shape == nxt.shape and prev.ndim == 3 and len(pts_list) == prev.shape[0]
+    off = np.zeros(len(pts_list) + 1, np.int32)
+    off[1:] = np.cumsum([len(p) for p in pts_list])
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 2) for p in pts_list]) if off[-1] else np.zeros((0, 2), np.float32))
+    n = int(off[-1])
+    out = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+    _check(lib().mcv_lk_track_batch(_p(prev), _p(nxt), prev.shape[0], prev.shape[2], prev.shape[1], prev.strides[1], _p(pts), _p(off), _p(out), _p(st), _p(err)))
+    sl = [slice(off[k], off[k + 1]) for k in range(len(pts_list))]
+    return [out[s] for s in sl], [st[s] for s in sl], [err[s] for s in sl]
 
 
 def KL_Track(prev, nxt, kps):

@@ -808,35 +808,56 @@ mcv_status mcv_distinctive_descriptors(const uint8_t* desc, const int32_t* mp_of
 }
 
 // ---- KL_Track (src/Frame.cpp:34-76): cv::calcOpticalFlowPyrLK with the reference's fixed arguments ----
-mcv_status mcv_lk_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const float* pts, int n, float* next_pts,
-                        uint8_t* status, float* err) {
-    if (!prev || !next || n < 0 || (n > 0 && (!pts || !next_pts || !status || !err))) return MCV_ERR_BAD_ARG;
+mcv_status mcv_lk_track_batch(const uint8_t* prev, const uint8_t* next, int n_pairs, int w, int hgt, size_t stride, const float* pts,
+                              const int32_t* pt_off, float* next_pts, uint8_t* status, float* err) {
+    if (!prev || !next || n_pairs <= 0 || !pt_off) return MCV_ERR_BAD_ARG;
     if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
-    if (stride < (size_t)w) return MCV_ERR_BAD_ARG;
+    if (stride < (size_t)w || pt_off[0] != 0) return MCV_ERR_BAD_ARG;
+    for (int k = 0; k < n_pairs; ++k) if (pt_off[k + 1] < pt_off[k]) return MCV_ERR_BAD_ARG;
+    const int n = pt_off[n_pairs];
+    if (n > 0 && (!pts || !next_pts || !status || !err)) return MCV_ERR_BAD_ARG;
     cudaStream_t s;
     mcv_status st = match_stream(&s);
     if (st) return st;
-    static DevBuf b_img, b_ws, b_pts, b_out, b_st, b_err;
+    static DevBuf b_img, b_ws, b_pts, b_pair, b_out, b_st, b_err;
     const size_t img_bytes = (size_t)w * hgt;
-    if ((st = b_img.reserve(2 * img_bytes))) return st;
-    if ((st = b_ws.reserve(lk_workspace_bytes(w, hgt)))) return st;
+    if ((st = b_img.reserve(2 * img_bytes * n_pairs))) return st;
+    if ((st = b_ws.reserve(lk_workspace_bytes(w, hgt) * n_pairs))) return st;
     if ((st = b_pts.reserve(std::max<size_t>(8, (size_t)n * 8)))) return st;
+    if ((st = b_pair.reserve(std::max<size_t>(4, (size_t)n * 4)))) return st;
     if ((st = b_out.reserve(std::max<size_t>(8, (size_t)n * 8)))) return st;
     if ((st = b_st.reserve(std::max<size_t>(4, (size_t)n)))) return st;
     if ((st = b_err.reserve(std::max<size_t>(4, (size_t)n * 4)))) return st;
-    MCV_CUDA(cudaMemcpy2DAsync(b_img.p, w, prev, stride, w, hgt, cudaMemcpyHostToDevice, s));
-    MCV_CUDA(cudaMemcpy2DAsync(b_img.as<uint8_t>() + img_bytes, w, next, stride, w, hgt, cudaMemcpyHostToDevice, s));
-    if (n) MCV_CUDA(cudaMemcpyAsync(b_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    launch_lk_track(b_img.as<uint8_t>(), b_img.as<uint8_t>() + img_bytes, w, hgt, w, b_ws.p, b_pts.as<float>(), n, b_out.as<float>(), b_st.as<uint8_t>(),
-                    b_err.as<float>(), s);
+    uint8_t* d_prev = b_img.as<uint8_t>();
+    uint8_t* d_next = d_prev + img_bytes * n_pairs;
+    MCV_CUDA(cudaMemcpy2DAsync(d_prev, w, prev, stride, w, (size_t)hgt * n_pairs, cudaMemcpyHostToDevice, s));   // images back to back: one 2-D copy
+    MCV_CUDA(cudaMemcpy2DAsync(d_next, w, next, stride, w, (size_t)hgt * n_pairs, cudaMemcpyHostToDevice, s));
+    std::vector<int32_t> pair_of;
+    if (n) {
+        MCV_CUDA(cudaMemcpyAsync(b_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        if (n_pairs > 1) {
+            pair_of.resize((size_t)n);
+            for (int k = 0; k < n_pairs; ++k) std::fill(pair_of.begin() + pt_off[k], pair_of.begin() + pt_off[k + 1], k);
+            MCV_CUDA(cudaMemcpyAsync(b_pair.p, pair_of.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        }
+    }
+    launch_lk_track(d_prev, d_next, n_pairs, w, hgt, w, img_bytes, b_ws.p, b_pts.as<float>(), n_pairs > 1 ? b_pair.as<int>() : nullptr, n, b_out.as<float>(),
+                    b_st.as<uint8_t>(), b_err.as<float>(), s);
     MCV_CUDA(cudaGetLastError());
     if (n) {
         MCV_CUDA(cudaMemcpyAsync(next_pts, b_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
         MCV_CUDA(cudaMemcpyAsync(status, b_st.p, (size_t)n, cudaMemcpyDeviceToHost, s));
         MCV_CUDA(cudaMemcpyAsync(err, b_err.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     }
-    MCV_CUDA(cudaStreamSynchronize(s));
+    MCV_CUDA(cudaStreamSynchronize(s));   // (also keeps pair_of alive until its copy is done)
     return MCV_OK;
+}
+
+mcv_status mcv_lk_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const float* pts, int n, float* next_pts,
+                        uint8_t* status, float* err) {
+    if (n < 0) return MCV_ERR_BAD_ARG;
+    const int32_t off[2] = {0, n};
+    return mcv_lk_track_batch(prev, next, 1, w, hgt, stride, pts, off, next_pts, status, err);
 }
 
 mcv_status mcv_kl_track(const uint8_t* prev, const uint8_t* next, int w, int hgt, size_t stride, const mcv_keypoint* kps, int n, mcv_keypoint* new_kps,

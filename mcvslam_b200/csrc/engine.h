@@ -119,8 +119,8 @@ int launch_bow_descend(const uint8_t* d_desc, int n, const int32_t* d_child_off,
                        int nid_level, int max_depth, uint32_t* d_leaf, uint32_t* d_nid, cudaStream_t s);
 int launch_distinctive(const uint8_t* d_desc, const int32_t* d_off, int n_mp, int32_t* d_best_idx, int32_t* d_best_median, cudaStream_t s);
 size_t lk_workspace_bytes(int w, int h);
-int launch_lk_track(const uint8_t* d_prev, const uint8_t* d_next, int w, int h, int src_pitch, void* d_ws, const float* d_pts, int n, float* d_next_pts,
-                    uint8_t* d_status, float* d_err, cudaStream_t s);
+int launch_lk_track(const uint8_t* d_prev, const uint8_t* d_next, int n_pairs, int w, int h, int src_pitch, size_t img_stride, void* d_ws,
+                    const float* d_pts, const int* d_pair_of, int n, float* d_next_pts, uint8_t* d_status, float* d_err, cudaStream_t s);
 int launch_debug_sincosf(const float* d_a, int n, float* d_s, float* d_c, cudaStream_t s);
 int launch_debug_atan2(const float* d_y, const float* d_x, int n, float* d_o, cudaStream_t s);
 int launch_popc_peak(int iters, unsigned* d_sink, int blocks, int threads, cudaStream_t s);

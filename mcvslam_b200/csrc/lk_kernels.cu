@@ -25,10 +25,13 @@ __host__ __device__ inline int lk_reflect101(int p, int len) {
     return p;
 }
 
-__global__ void k_lk_level0(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next, int w, int h, int src_pitch, uint8_t* __restrict__ I0,
-                            uint8_t* __restrict__ J0, int stride) {
+// Every preparation kernel takes the pair index in blockIdx.z: images of consecutive pairs are `img_stride` bytes apart, their
+// workspaces `ws_stride` bytes.
+__global__ void k_lk_level0(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next, int w, int h, int src_pitch, size_t img_stride,
+                            uint8_t* __restrict__ I0, uint8_t* __restrict__ J0, int stride, size_t ws_stride) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= stride) return;
+    prev += blockIdx.z * img_stride; next += blockIdx.z * img_stride; I0 += blockIdx.z * ws_stride; J0 += blockIdx.z * ws_stride;
     if (y == h + 2 * LK_WIN) { I0[(size_t)y * stride + x] = 0; J0[(size_t)y * stride + x] = 0; return; }   // spare row (see ora_lk.hpp)
     const int sx = lk_reflect101(x - LK_WIN, w), sy = lk_reflect101(y - LK_WIN, h);
     I0[(size_t)y * stride + x] = prev[(size_t)sy * src_pitch + sx];
@@ -49,10 +52,11 @@ __device__ __forceinline__ int lk_pyrdown_px(const uint8_t* __restrict__ src, in
     return (acc + 128) >> 8;
 }
 
-__global__ void k_lk_level1(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next, int w, int h, int src_pitch, int w1, int h1,
-                            uint8_t* __restrict__ I1, uint8_t* __restrict__ J1, int stride1) {
+__global__ void k_lk_level1(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next, int w, int h, int src_pitch, size_t img_stride, int w1,
+                            int h1, uint8_t* __restrict__ I1, uint8_t* __restrict__ J1, int stride1, size_t ws_stride) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= stride1) return;
+    prev += blockIdx.z * img_stride; next += blockIdx.z * img_stride; I1 += blockIdx.z * ws_stride; J1 += blockIdx.z * ws_stride;
     if (y == h1 + 2 * LK_WIN) { I1[(size_t)y * stride1 + x] = 0; J1[(size_t)y * stride1 + x] = 0; return; }
     const int sx = lk_reflect101(x - LK_WIN, w1), sy = lk_reflect101(y - LK_WIN, h1);
     I1[(size_t)y * stride1 + x] = (uint8_t)lk_pyrdown_px(prev, w, h, src_pitch, sx, sy);
@@ -60,9 +64,10 @@ __global__ void k_lk_level1(const uint8_t* __restrict__ prev, const uint8_t* __r
 }
 
 // img = bordered level (origin at (LK_WIN, LK_WIN)); the reflect-101 ring IS what calcScharrDeriv's border rules read
-__global__ void k_lk_scharr(const uint8_t* __restrict__ img, int w, int h, int stride, short2* __restrict__ deriv) {
+__global__ void k_lk_scharr(const uint8_t* __restrict__ img, int w, int h, int stride, short2* __restrict__ deriv, size_t ws_stride) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= stride) return;
+    img += blockIdx.z * ws_stride; deriv = reinterpret_cast<short2*>(reinterpret_cast<uint8_t*>(deriv) + blockIdx.z * ws_stride);
     const int ix = x - LK_WIN, iy = y - LK_WIN;
     short2 d = make_short2(0, 0);
     if (ix >= 0 && ix < w && iy >= 0 && iy < h) {
@@ -92,10 +97,16 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 }
 __device__ __forceinline__ float lk_reduce4(const float* q) { return __fadd_rn(__fadd_rn(q[0], q[2]), __fadd_rn(q[1], q[3])); }
 
-__global__ void __launch_bounds__(64) k_lk_track(LkLevel L0, LkLevel L1, int max_level, const float* __restrict__ pts, int n, float* __restrict__ next_pts,
-                                                 uint8_t* __restrict__ status_out, float* __restrict__ err_out) {
+__global__ void __launch_bounds__(64) k_lk_track(LkLevel L0, LkLevel L1, int max_level, size_t ws_stride, const float* __restrict__ pts,
+                                                 const int* __restrict__ pair_of, int n, float* __restrict__ next_pts, uint8_t* __restrict__ status_out,
+                                                 float* __restrict__ err_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    {   // this point's pair: every level buffer of pair k lies k * ws_stride bytes after pair 0's
+        const size_t o = (size_t)(pair_of ? pair_of[i] : 0) * ws_stride;
+        L0.I += o; L0.J += o; L0.D = reinterpret_cast<const short2*>(reinterpret_cast<const uint8_t*>(L0.D) + o);
+        L1.I += o; L1.J += o; L1.D = reinterpret_cast<const short2*>(reinterpret_cast<const uint8_t*>(L1.D) + o);
+    }
     const float px = pts[2 * i], py = pts[2 * i + 1];
     float nx = 0.f, ny = 0.f, err = 0.f;
     int status = 1;
@@ -224,17 +235,19 @@ size_t lk_workspace_bytes(int w, int h) {
     const size_t l0 = (size_t)(w + 2 * LK_WIN) * (h + 2 * LK_WIN + 1), l1 = (size_t)(w1 + 2 * LK_WIN) * (h1 + 2 * LK_WIN + 1);
     // per level: I, J (u8), D (short2), each rounded up to 256 bytes
     auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return 2 * r(l0) + r(l0 * 4) + 2 * r(l1) + r(l1 * 4);
+    return 2 * r(l0) + r(l0 * 4) + 2 * r(l1) + r(l1 * 4);   // a multiple of 256: per-pair workspaces stay aligned
 }
 
-// prev / next: device images (pitch src_pitch); d_ws: lk_workspace_bytes(w, h). Returns the launch count.
-int launch_lk_track(const uint8_t* d_prev, const uint8_t* d_next, int w, int h, int src_pitch, void* d_ws, const float* d_pts, int n, float* d_next_pts,
-                    uint8_t* d_status, float* d_err, cudaStream_t s) {
+// prev / next: n_pairs device images each (rows src_pitch apart, images img_stride apart); d_ws: n_pairs * lk_workspace_bytes(w, h);
+// d_pair_of[i] = pair of point i (NULL: one pair). Returns the launch count.
+int launch_lk_track(const uint8_t* d_prev, const uint8_t* d_next, int n_pairs, int w, int h, int src_pitch, size_t img_stride, void* d_ws,
+                    const float* d_pts, const int* d_pair_of, int n, float* d_next_pts, uint8_t* d_status, float* d_err, cudaStream_t s) {
     const int w1 = (w + 1) / 2, h1 = (h + 1) / 2;
     const int max_level = (w1 <= LK_WIN || h1 <= LK_WIN) ? 0 : 1;     // buildOpticalFlowPyramid stops before a level <= winSize
     const int s0 = w + 2 * LK_WIN, s1 = w1 + 2 * LK_WIN;
     const size_t l0 = (size_t)s0 * (h + 2 * LK_WIN + 1), l1 = (size_t)s1 * (h1 + 2 * LK_WIN + 1);
     auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t ws_stride = lk_workspace_bytes(w, h);
     uint8_t* p = reinterpret_cast<uint8_t*>(d_ws);
     uint8_t* I0 = p; p += r(l0);
     uint8_t* J0 = p; p += r(l0);
@@ -243,15 +256,15 @@ int launch_lk_track(const uint8_t* d_prev, const uint8_t* d_next, int w, int h, 
     uint8_t* J1 = p; p += r(l1);
     short2* D1 = reinterpret_cast<short2*>(p);
     int launches = 0;
-    k_lk_level0<<<dim3((s0 + 255) / 256, h + 2 * LK_WIN + 1), 256, 0, s>>>(d_prev, d_next, w, h, src_pitch, I0, J0, s0); ++launches;
-    k_lk_scharr<<<dim3((s0 + 255) / 256, h + 2 * LK_WIN + 1), 256, 0, s>>>(I0, w, h, s0, D0); ++launches;
+    k_lk_level0<<<dim3((s0 + 255) / 256, h + 2 * LK_WIN + 1, n_pairs), 256, 0, s>>>(d_prev, d_next, w, h, src_pitch, img_stride, I0, J0, s0, ws_stride); ++launches;
+    k_lk_scharr<<<dim3((s0 + 255) / 256, h + 2 * LK_WIN + 1, n_pairs), 256, 0, s>>>(I0, w, h, s0, D0, ws_stride); ++launches;
     if (max_level == 1) {
-        k_lk_level1<<<dim3((s1 + 255) / 256, h1 + 2 * LK_WIN + 1), 256, 0, s>>>(d_prev, d_next, w, h, src_pitch, w1, h1, I1, J1, s1); ++launches;
-        k_lk_scharr<<<dim3((s1 + 255) / 256, h1 + 2 * LK_WIN + 1), 256, 0, s>>>(I1, w1, h1, s1, D1); ++launches;
+        k_lk_level1<<<dim3((s1 + 255) / 256, h1 + 2 * LK_WIN + 1, n_pairs), 256, 0, s>>>(d_prev, d_next, w, h, src_pitch, img_stride, w1, h1, I1, J1, s1, ws_stride); ++launches;
+        k_lk_scharr<<<dim3((s1 + 255) / 256, h1 + 2 * LK_WIN + 1, n_pairs), 256, 0, s>>>(I1, w1, h1, s1, D1, ws_stride); ++launches;
     }
     if (n > 0) {
         const LkLevel L0{I0, J0, D0, w, h, s0}, L1{I1, J1, D1, w1, h1, s1};
-        k_lk_track<<<(n + 63) / 64, 64, 0, s>>>(L0, L1, max_level, d_pts, n, d_next_pts, d_status, d_err); ++launches;
+        k_lk_track<<<(n + 63) / 64, 64, 0, s>>>(L0, L1, max_level, ws_stride, d_pts, d_pair_of, n, d_next_pts, d_status, d_err); ++launches;
     }
     return launches;
 }

@@ -59,3 +59,15 @@ def test_kl_track(api, oracle):
     assert (new["octave"][ok == 1] == 0).all() and np.array_equal(new["angle"][ok == 1], sel["angle"][ok == 1])
     cnt, new, ok = api.KL_Track(a, b, sel[:9])
     assert cnt == 0 and not ok.any()
+
+
+def test_lk_track_batch(api, oracle):
+    """mcv_lk_track_batch: the four 640x480 fixture pairs (ragged point lists, one of them empty) in one call == one oracle call per pair."""
+    cases = [c for c in _lk_cases() if c[1].shape == (480, 640)]
+    prev = np.stack([c[1] for c in cases]); nxt = np.stack([c[2] for c in cases])
+    pts = [c[3][:1500 - 211 * k] for k, c in enumerate(cases)]
+    pts[2] = pts[2][:0]
+    o, st, err = api.LkTrackBatch(prev, nxt, pts)
+    for k, c in enumerate(cases):
+        ro, rs, re = oracle.lk_track(c[1], c[2], pts[k])
+        assert np.array_equal(st[k], rs) and _same(o[k], ro) and _same(err[k], re), k
