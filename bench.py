@@ -171,6 +171,29 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def pin_to_gpu_numa(local_rank):
+    """Binds this rank to the CPUs NVML reports as local to its GPU, BEFORE the pinned host buffers are allocated (first touch
+    puts them on that NUMA node), so that the host-in/host-out leg of N ranks does not cross sockets. Returns the CPU list or
+    None when NVML has nothing to say (or the cgroup leaves no such CPU)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in allowed if (words[c // 64] >> (c % 64)) & 1)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,6 +221,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa(local_rank) if os.environ.get("MCV_BENCH_NUMA", "1") != "0" else None
     dev = torch.device("cuda", local_rank)
     # NCCL prints its version banner on stdout at the first collective; rank 0's stdout must carry ONE JSON line, so fd 1
     # points at stderr until the line is printed
@@ -350,7 +374,8 @@ def main():
             "config": {"workload": "configs[1]: 3-camera rig triplet (left/right/wide) 640x480, 2000 ORB x 8 levels x 1.2, FAST 28/15, "
                                    "extract + L/R stereo match", "frames_per_step_per_gpu": B, "keypoints_per_frame": n_kp / B,
                        "l2": "inputs larger than L2: %d MB of images + %d MB of pyramids per step" % (B * 3 * W * H >> 20, B * 3 * PYR_BYTES_PER_IMAGE >> 20),
-                       "collective": "all_gather of per-image keypoint counts per step (N>1 only)"},
+                       "collective": "all_gather of per-image keypoint counts per step (N>1 only)",
+                       "host_cpus": ("NUMA-local to the GPU: %d CPUs" % len(numa)) if numa else "unbound"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h_imgs.numel()),
                     "d2h_bytes_per_step": int(h_kps.numel() + h_desc.numel() + h_cnt.numel() * 4 + h_ur.numel() * 4 + h_dp.numel() * 4),
                     "steps": args.steps, "how": "mcv_rig_submit / mcv_rig_wait on pinned host buffers, %d steps in flight, wall clock; every " % NF +
