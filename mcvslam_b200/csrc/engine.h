@@ -15,7 +15,10 @@ constexpr int EDGE_THRESHOLD = 19;   // ORBextractor.cc:73
 constexpr int BORDER = 16;           // EDGE_THRESHOLD - 3: origin of FAST candidate coordinates (ORBextractor.cc:588)
 constexpr int MAX_DIM = 4096 + 2 * BORDER;  // candidate coordinates are packed in 12 bits
 constexpr int NUM_SMS = 148;
-constexpr int FS_ROWS = 36;            // rows per FAST strip; FS_ROWS + 6 is a multiple of the kernel's 7-row register ring
+#ifndef MCV_FS_ROWS
+#define MCV_FS_ROWS 36
+#endif
+constexpr int FS_ROWS = MCV_FS_ROWS;            // rows per FAST strip; FS_ROWS + 6 is a multiple of the kernel's 7-row register ring
 constexpr int FS_SEG = 128 * FS_ROWS;  // list entries a strip owns: worst case every pixel of the strip scores
 
 // Candidate / quadtree point: x (12 bits) | y (12 bits) << 12 | response (8 bits) << 24, coordinates relative to BORDER.
