@@ -1,10 +1,10 @@
 // Orientation, steered rBRIEF descriptor and final keypoint assembly for a batch of images (sm_100a).
 //
-// One warp per output keypoint. Replaces, for every keypoint:
+// A quarter-warp per output keypoint (see "Design" below). Replaces, for every keypoint:
 //   * the post-distribution fix-up (ORBextractor.cc:640-649): pt += 16, octave, size = (int)(31 * scale);
 //   * IC_Angle (ORBextractor.cc:75-98): int32 moments over the 15-px circular patch -> cv::fastAtan2;
 //   * computeOrbDescriptor (ORBextractor.cc:101-141) on the 7x7-Gaussian-smoothed level: 256 steered point pairs,
-//     lane i produces descriptor byte i;
+//     lane l of the keypoint's 8 lanes produces descriptor bytes 4l .. 4l + 3;
 //   * the level-major assembly of operator() (ORBextractor.cc:845-897): quadtree keypoints of a level in heap-pop order,
 //     then the caller's pre-seeded keypoints of that octave, pt *= scale for level != 0.
 #include <string.h>
