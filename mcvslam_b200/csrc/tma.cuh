@@ -7,6 +7,10 @@
 #include <cuda.h>
 #include "engine.h"
 
+#ifndef MCV_TMA_L2PROMO
+#define MCV_TMA_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
+
 namespace mcv {
 
 __device__ __forceinline__ void tma_load_3d(unsigned dst_smem, const CUtensorMap* map, int c0, int c1, int c2, unsigned mbar_smem) {
@@ -56,7 +60,7 @@ inline bool encode_level_map(CUtensorMap* m, const uint8_t* base, const Plan& P,
     const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)P.pyr_bytes};    // bytes, dims 1 and 2
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u}, estr[3] = {1u, 1u, 1u};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base) + g.img_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              CU_TENSOR_MAP_SWIZZLE_NONE, MCV_TMA_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 
