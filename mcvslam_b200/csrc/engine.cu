@@ -232,7 +232,8 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
         if ((st = h->nz_cnt.reserve((size_t)std::max(1, P.n_fast_strips) * n_images * 4))) return st;
         if ((st = h->arena_a.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
         if ((st = h->arena_b.reserve((size_t)P.cand_per_image * n_images * 4))) return st;
-        if ((st = h->oct_idx.reserve((size_t)P.cand_per_image * n_images * 2))) return st;
+        // sorted indices (u16 per candidate) | bucket prefix sums of every quadtree task (launch_octree)
+        if ((st = h->oct_idx.reserve((size_t)P.cand_per_image * n_images * 2 + 512 + (size_t)P.n_levels * n_images * OCT_S_BYTES))) return st;
         if ((st = h->cell_cnt.reserve((size_t)P.cells_per_image * n_images * 4))) return st;
         if ((st = h->fallback.reserve(((size_t)P.cells_per_image * n_images + 4) * 4))) return st;
         if ((st = h->out_pts.reserve((size_t)P.out_per_image * n_images * 4))) return st;

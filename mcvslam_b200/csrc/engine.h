@@ -19,6 +19,7 @@ constexpr int NUM_SMS = 148;
 #define MCV_FS_ROWS 36
 #endif
 constexpr int FS_ROWS = MCV_FS_ROWS;            // rows per FAST strip; FS_ROWS + 6 is a multiple of the kernel's 7-row register ring
+constexpr int OCT_S_BYTES = 2 * 2064;    // quadtree: bucket prefix sums per (image, level) task (<= 2048 buckets + 1, u16)
 constexpr int FS_SEG = 128 * FS_ROWS;  // list entries a strip owns: worst case every pixel of the strip scores
 
 // Candidate / quadtree point: x (12 bits) | y (12 bits) << 12 | response (8 bits) << 24, coordinates relative to BORDER.

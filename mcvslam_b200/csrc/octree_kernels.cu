@@ -302,7 +302,11 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
 // counting sort by depth-T bucket, per-bucket sort), then thread 0 replays the heap on counts alone (octree_core.cuh), then
 // all threads pick each surviving node's first-maximum-response point. Everything lives in shared memory.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int OC_THREADS = 64;
+#ifndef MCV_OC_THREADS
+#define MCV_OC_THREADS 128
+#endif
+constexpr int OC_THREADS = MCV_OC_THREADS;   // preparation kernel (data-parallel phases)
+constexpr int OR_THREADS = 32;               // replay kernel: one thread replays the heap, the warp picks the survivors' points
 
 __device__ __forceinline__ int block_excl_scan(int v, int* s_part, int& total) {   // OC_THREADS threads; s_part: OC_THREADS / 32 ints
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -333,15 +337,20 @@ __device__ __forceinline__ void sort8(uint32_t (&c)[8], uint16_t (&x)[8]) {
     }
 }
 
-// One CTA per (image, level). Shared memory holds only what the serial replay touches: R0 = histogram / scatter cursors
-// (nb u32), afterwards heap | node table; S (u16 x nb_pad). Per-point arrays live in global memory (L2-resident): `arena` =
-// candidates in reference order, `scode` / `sidx` = path codes and original indices sorted by code. With ~7 KB per CTA every
-// task of a 128-frame batch is resident at once: the kernel lasts as long as its longest heap replay.
-__global__ void __launch_bounds__(OC_THREADS) k_octree_sorted(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
-                                                              uint32_t* __restrict__ arena, uint32_t* __restrict__ scode_all,
-                                                              uint16_t* __restrict__ sidx_all, uint32_t* __restrict__ out_pts,
-                                                              int* __restrict__ out_cnt, int* __restrict__ overflow,
-                                                              const __grid_constant__ Plan P, int n_images, int nb_pad, int r0_words, int heap_alloc) {
+// Two kernels per batch, one CTA per (image, level) task each:
+//  k_octree_prep   (OC_THREADS threads): gather in reference order, path codes, counting sort by depth-T bucket, per-bucket
+//                  sort; leaves `arena` (candidates in reference order), `scode` / `sidx` (path codes and original indices
+//                  sorted by code) and the bucket prefix sums S (u16 x nb_pad per task) in global memory (L2-resident).
+//  k_octree_replay (one warp): S into shared memory, thread 0 replays the heap on counts (octree_core.cuh), the warp picks every
+//                  surviving node's first-maximum-response point. This kernel lasts as long as its longest heap replay, so it
+//                  is kept as small as possible — 32 threads and ~7 KB of shared memory per task — and leaves the rest of the
+//                  SM (registers above all: the one-kernel version pinned 64 threads x 48 registers per task for the whole
+//                  replay, 98 % of the register file with all tasks resident) to the other stream's stencils.
+__global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
+                                                            uint32_t* __restrict__ arena, uint32_t* __restrict__ scode_all,
+                                                            uint16_t* __restrict__ sidx_all, uint16_t* __restrict__ S_all,
+                                                            int* __restrict__ overflow,
+                                                            const __grid_constant__ Plan P, int n_images, int nb_pad, int r0_words) {
     extern __shared__ __align__(16) unsigned char oc_smem[];
     __shared__ int s_part[OC_THREADS / 32];
     __shared__ int s_total;
@@ -349,9 +358,7 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_sorted(const uint32_t* __
     const int task = blockIdx.x;                       // level-major: the long level-0 tasks start first
     const int level = task / n_images, img = task - level * n_images;
     const LevelGeom& lg = P.lv[level];
-    uint32_t* cur = reinterpret_cast<uint32_t*>(oc_smem);
-    uint32_t* heap = cur + 1;                                  // heap - 1 is 16-byte aligned (oct::load2 / load4)
-    uint32_t* nodes = cur + heap_alloc;
+    uint32_t* cur = reinterpret_cast<uint32_t*>(oc_smem);      // histogram / scatter cursors (nb u32)
     uint16_t* S = reinterpret_cast<uint16_t*>(cur + r0_words);
     const size_t task_off = (size_t)img * P.cand_per_image + lg.cand_off;
     uint32_t* pts = arena + task_off;                  // candidates in reference order
@@ -437,6 +444,40 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_sorted(const uint32_t* __
     }
     __syncthreads();
     if (clk && tid == 0) clk[2] = clock64();
+    uint16_t* Sg = S_all + (size_t)task * nb_pad;
+    for (int b = tid; b <= nb; b += OC_THREADS) Sg[b] = S[b];
+}
+
+#ifndef MCV_OR_MINB
+#define MCV_OR_MINB 1
+#endif
+__global__ void __launch_bounds__(OR_THREADS, MCV_OR_MINB) k_octree_replay(const uint32_t* __restrict__ arena, const uint32_t* __restrict__ scode_all,
+                                                              const uint16_t* __restrict__ sidx_all, const uint16_t* __restrict__ S_all,
+                                                              uint32_t* __restrict__ out_pts, int* __restrict__ out_cnt,
+                                                              const int* __restrict__ overflow, const __grid_constant__ Plan P, int n_images,
+                                                              int nb_pad, int r0_words, int heap_alloc) {
+    extern __shared__ __align__(16) unsigned char oc_smem[];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const int task = blockIdx.x;                       // level-major: the long level-0 tasks start first
+    if (overflow[task]) return;                        // the legacy kernel takes this task
+    const int level = task / n_images, img = task - level * n_images;
+    const LevelGeom& lg = P.lv[level];
+    uint32_t* cur = reinterpret_cast<uint32_t*>(oc_smem);
+    uint32_t* heap = cur + 1;                                  // heap - 1 is 16-byte aligned (oct::load2 / load4)
+    uint32_t* nodes = cur + heap_alloc;
+    uint16_t* S = reinterpret_cast<uint16_t*>(cur + r0_words);
+    const size_t task_off = (size_t)img * P.cand_per_image + lg.cand_off;
+    const uint32_t* pts = arena + task_off;            // candidates in reference order
+    const uint32_t* scode = scode_all + task_off;
+    const uint16_t* sidx = sidx_all + task_off;
+    oct::Geom g;
+    g.n_ini = lg.n_ini; g.h_x = lg.h_x; g.box_h = lg.h - 2 * BORDER; g.N = lg.quota; g.T = oct::tier_for(lg.n_ini);
+    const int nb = lg.n_ini << (2 * g.T);
+    long long* clk = task == 0 ? g_oct_clk : nullptr;
+    const uint16_t* Sg = S_all + (size_t)task * nb_pad;
+    for (int b = tid; b <= nb; b += OR_THREADS) S[b] = Sg[b];
+    __syncthreads();
     // -- serial heap replay on counts
     if (tid == 0) {
         s_total = oct::replay(scode, S, g, heap, nodes, clk ? clk + 3 : nullptr);
@@ -446,7 +487,7 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_sorted(const uint32_t* __
     const int total = s_total;
     const int n_out = min(total, lg.out_cap);
     uint32_t* out = out_pts + (size_t)img * P.out_per_image + lg.out_off;
-    for (int i = tid; i < n_out; i += OC_THREADS) out[i] = oct::select_best(heap[total - 1 - i], nodes, S, g.T, pts, sidx);
+    for (int i = tid; i < n_out; i += OR_THREADS) out[i] = oct::select_best(heap[total - 1 - i], nodes, S, g.T, pts, sidx);
     if (tid == 0) {
         out_cnt[(size_t)img * P.n_levels + level] = n_out;
         if (clk) clk[5] = clock64();
@@ -510,17 +551,24 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
         return launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, nullptr, s);
     static size_t configured = 0;
     if (smem > configured) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_octree_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(k_octree_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_octree_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
         // many small CTAs that live as long as one thread's heap replay: ask for the largest shared-memory carve-out
-        cudaFuncSetAttribute(k_octree_sorted, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_octree_replay, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
     const int tasks = n_images * P.n_levels;
     int* d_overflow = d_out_cnt + tasks;
-    k_octree_sorted<<<tasks, OC_THREADS, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_out_pts, d_out_cnt, d_overflow, P,
-                                                    n_images, nb_pad, r0_words, heap_alloc);
-    if (!can_overflow) return 1;
-    return 1 + launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, d_overflow, s);
+    // bucket prefix sums of every task: behind the sorted-index array (enqueue_extract reserves OCT_S_BYTES per task there)
+    uint16_t* d_S = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(d_oct_idx) + (((size_t)P.cand_per_image * n_images * 2 + 255) & ~(size_t)255));
+    if ((size_t)nb_pad * 2 > OCT_S_BYTES) return launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, nullptr, s);
+    k_octree_prep<<<tasks, OC_THREADS, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_S, d_overflow, P, n_images, OCT_S_BYTES / 2, r0_words);
+    k_octree_replay<<<tasks, OR_THREADS, smem, s>>>(d_arena_a, d_arena_b, d_oct_idx, d_S, d_out_pts, d_out_cnt, d_overflow, P, n_images, OCT_S_BYTES / 2,
+                                                    r0_words, heap_alloc);
+    if (!can_overflow) return 2;
+    return 2 + launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, d_overflow, s);
 }
 
 int octree_debug_clocks(long long out[8]) { return cudaMemcpyFromSymbol(out, g_oct_clk, sizeof(long long) * 8) == cudaSuccess ? 0 : -1; }
