@@ -365,7 +365,7 @@ def main():
         except Exception:
             pass
         kernel_names = {"pyramid": "k_copy_level0 + 7 x k_resize_march", "blur": "k_gauss7", "fast_score": "k_fast_score",
-                        "nms_cells": "k_nms_sparse + k_cell_order", "quadtree": "k_octree_sorted", "orient_desc": "k_orient_desc",
+                        "nms_cells": "k_nms_sparse + k_cell_order", "quadtree": "k_octree_prep + k_octree_replay", "orient_desc": "k_orient_desc",
                         "stereo_match": "k_stereo_rows + k_stereo_match", "stereo_median": "k_stereo_median"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task = blockIdx.x * warps + warp;
     if (task >= n_images * P.n_levels) return;
-    if (only && !only[task]) return;   // fallback launch: only the tasks k_octree_sorted could not hold in shared memory
+    if (only && !only[task]) return;   // fallback launch: only the tasks k_octree_prep could not index with 16 bitsory
     // level-major task order so that the long level-0 tasks start first
     const int level = task / n_images, img = task - level * n_images;
     const LevelGeom& g = P.lv[level];
@@ -298,9 +298,9 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_octree_sorted: one CTA per (image, level). Data-parallel phases on all threads (gather in reference order, path codes,
-// counting sort by depth-T bucket, per-bucket sort), then thread 0 replays the heap on counts alone (octree_core.cuh), then
-// all threads pick each surviving node's first-maximum-response point. Everything lives in shared memory.
+// The sorted path (k_octree_prep + k_octree_replay), one CTA per (image, level) in each kernel: data-parallel phases (gather in
+// reference order, path codes, counting sort by depth-T bucket, per-bucket sort), then one thread replays the heap on counts
+// alone (octree_core.cuh) and its warp picks each surviving node's first-maximum-response point.
 // ---------------------------------------------------------------------------------------------------------
 #ifndef MCV_OC_THREADS
 #define MCV_OC_THREADS 128
@@ -533,7 +533,7 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     static const char* skip_env = getenv("MCV_DEBUG_SKIP_OCTREE_AFTER");
     static long skip_calls = 0;
     if (skip_env && ++skip_calls > atol(skip_env)) return 0;
-    // shared-memory plan of k_octree_sorted: R0 = cursors, later heap | nodes (r0_words u32) | S (nb_pad u16)
+    // shared-memory plan of k_octree_prep / k_octree_replay: R0 = cursors, later heap | nodes (r0_words u32) | S (nb_pad u16)
     int nb = 1, max_ini = 1, max_heap = 8;
     bool can_overflow = false;
     for (int l = 0; l < P.n_levels; ++l) {
