@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __re
                                                             uint32_t* __restrict__ arena, uint32_t* __restrict__ scode_all,
                                                             uint16_t* __restrict__ sidx_all, uint16_t* __restrict__ S_all,
                                                             int* __restrict__ overflow,
-                                                            const __grid_constant__ Plan P, int n_images, int nb_pad, int r0_words) {
+                                                            const __grid_constant__ Plan P, int n_images, int nb_pad, int r0_words, int nb_smem) {
     extern __shared__ __align__(16) unsigned char oc_smem[];
     __shared__ int s_part[OC_THREADS / 32];
     __shared__ int s_total;
@@ -388,15 +388,31 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __re
         return;
     }
     if (tid == 0) overflow[task] = 0;
-    for (int c = c_lo; c < c_hi; ++c) {
-        const int k = cnts[c];
-        const uint32_t* src = cells + (size_t)c * lg.cell_cap;
-        for (int j = 0; j < k; ++j) {
-            const uint32_t p = __ldg(src + j);
-            pts[off + j] = p;
+    if (n_cells < nb_smem) {
+        // balanced: the exclusive prefix of the cell counts goes to S (free until the histogram scan; M < 65536), then thread i
+        // takes points i, i + OC_THREADS, ... and finds each one's cell by bisection. (A thread per run of cells leaves most
+        // threads idle on the small levels: level 7 of 640x480 has 8 cells. ncu: barrier stall 7.4 warps per issue.)
+        for (int c = c_lo; c < c_hi; ++c) { S[c] = (uint16_t)off; off += cnts[c]; }
+        if (tid == 0) S[n_cells] = (uint16_t)M;
+        __syncthreads();
+        for (int i = tid; i < M; i += OC_THREADS) {
+            int lo = 0, hi = n_cells;                  // last cell c with S[c] <= i (empty cells share their successor's prefix)
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)S[mid] <= i) lo = mid; else hi = mid; }
+            const uint32_t p = __ldg(cells + (size_t)lo * lg.cell_cap + (i - (int)S[lo]));
+            pts[i] = p;
             atomicAdd(&cur[min(oct::bucket_direct(p, g), nb - 1)], 1u);   // bucket histogram
         }
-        off += k;
+    } else {
+        for (int c = c_lo; c < c_hi; ++c) {
+            const int k = cnts[c];
+            const uint32_t* src = cells + (size_t)c * lg.cell_cap;
+            for (int j = 0; j < k; ++j) {
+                const uint32_t p = __ldg(src + j);
+                pts[off + j] = p;
+                atomicAdd(&cur[min(oct::bucket_direct(p, g), nb - 1)], 1u);   // bucket histogram
+            }
+            off += k;
+        }
     }
     __syncthreads();
     if (clk && tid == 0) clk[1] = clock64();
@@ -564,7 +580,8 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     // bucket prefix sums of every task: behind the sorted-index array (enqueue_extract reserves OCT_S_BYTES per task there)
     uint16_t* d_S = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(d_oct_idx) + (((size_t)P.cand_per_image * n_images * 2 + 255) & ~(size_t)255));
     if ((size_t)nb_pad * 2 > OCT_S_BYTES) return launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, nullptr, s);
-    k_octree_prep<<<tasks, OC_THREADS, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_S, d_overflow, P, n_images, OCT_S_BYTES / 2, r0_words);
+    k_octree_prep<<<tasks, OC_THREADS, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_S, d_overflow, P, n_images, OCT_S_BYTES / 2, r0_words,
+                                                  nb_pad);
     k_octree_replay<<<tasks, OR_THREADS, smem, s>>>(d_arena_a, d_arena_b, d_oct_idx, d_S, d_out_pts, d_out_cnt, d_overflow, P, n_images, OCT_S_BYTES / 2,
                                                     r0_words, heap_alloc);
     if (!can_overflow) return 2;
