@@ -245,7 +245,7 @@ def main():
     d_kps = torch.empty(kp_bytes, dtype=torch.uint8, device=dev); d_desc = torch.empty(B * 3 * cap * 32, dtype=torch.uint8, device=dev)
     d_cnt = torch.zeros(B * 3, dtype=torch.int32, device=dev)
     d_ur = torch.empty(B * cap, dtype=torch.float32, device=dev); d_dp = torch.empty(B * cap, dtype=torch.float32, device=dev)
-    # two sets of pinned result buffers: the e2e leg keeps two steps in flight (step k's results are read while step k+1 runs)
+    # --inflight sets of pinned result buffers: the e2e leg keeps that many steps in flight (step k's results are read while the next ones run)
     h_out = []
     NF = max(1, min(8, args.inflight))
     for _ in range(NF):
@@ -267,7 +267,7 @@ def main():
         rig.process_ptrs(h_imgs.data_ptr(), B, W, H, h_kps.data_ptr(), h_desc.data_ptr(), h_cnt.data_ptr(), h_ur.data_ptr(), h_dp.data_ptr(), False)
 
     def run_host_pipelined(n_steps):
-        """n_steps through mcv_rig_submit / mcv_rig_wait on pinned HOST buffers, two steps in flight: every step's images are
+        """n_steps through mcv_rig_submit / mcv_rig_wait on pinned HOST buffers, --inflight steps in flight: every step's images are
         copied host->device and every result device->host inside the region; a step counts when its results are on the host
         (its keypoint counts are read)."""
         tickets, total_kp = [], 0
@@ -313,7 +313,7 @@ def main():
         stage_ms, n_calls = rig.stage_ms()
         rig.set_profiling(False)
         # e2e leg: host buffers through the C ABI, copies inside the timed region. (a) one synchronous mcv_rig_process call per
-        # step; (b) the throughput API: mcv_rig_submit / mcv_rig_wait, two steps in flight — (b) is the headline e2e
+        # step; (b) the throughput API: mcv_rig_submit / mcv_rig_wait, --inflight (default 3) steps in flight — (b) is the headline e2e
         for _ in range(2):
             step_host()
         barrier()
