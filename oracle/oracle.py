@@ -232,6 +232,17 @@ def filter_orientation(m, kps1, kps2):
     return m[:n].copy()
 
 
+def filter_fmatrix(m, kps1, kps2, F12, level_sigma2):
+    """MatchRes::FilterFMatrix (src/Matcher.cpp:76-91,310-325): swap-remove by the epipolar distance test."""
+    m = np.ascontiguousarray(m, DM_DTYPE).copy()
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9); s2 = np.ascontiguousarray(level_sigma2, np.float32)
+    L = lib()
+    L.ora_filter_fmatrix.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    n = L.ora_filter_fmatrix(_p(m), len(m), _p(kps1), _p(kps2), _p(F), _p(s2))
+    return m[:n].copy()
+
+
 def stereo_match(orb_l, orb_r, kl, dl, kr, dr, n_rows, bf, b):
     kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
     dl = _u8(dl); dr = _u8(dr)

@@ -618,6 +618,29 @@ int ora_filter_orientation(DMatch* m, int n, const KeyPoint* kps1, const KeyPoin
     return (int)ret.size();
 }
 
+// MatchRes::FilterFMatrix + CheckDistEpipolarLine — src/Matcher.cpp:76-91,310-325. F12 = 3x3 row-major float (F12.at<float>(r, c)),
+// LevelSigma2 = the SECOND object's extractor->mvLevelSigma2 (src/Map.cpp:307). Epipolar line in image 2: l = x1' F12 = [a b c]
+// (column sums with kp1), float arithmetic in source order; `den == 0` rejects; the final compare promotes to double
+// (3.84 is a double literal). Swap-remove like FilterThreshold: survivors are reordered. In place; returns the new size.
+static bool CheckDistEpipolarLine(const KeyPoint& kp1, const KeyPoint& kp2, const float* F12, const float* LevelSigma2) {
+    const float a = kp1.x * F12[0 * 3 + 0] + kp1.y * F12[1 * 3 + 0] + F12[2 * 3 + 0];
+    const float b = kp1.x * F12[0 * 3 + 1] + kp1.y * F12[1 * 3 + 1] + F12[2 * 3 + 1];
+    const float c = kp1.x * F12[0 * 3 + 2] + kp1.y * F12[1 * 3 + 2] + F12[2 * 3 + 2];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * LevelSigma2[kp2.octave];
+}
+int ora_filter_fmatrix(DMatch* m, int n, const KeyPoint* kps1, const KeyPoint* kps2, const float* F12, const float* level_sigma2) {
+    int i = 0, j = n - 1;
+    while (i <= j) {
+        DMatch d = m[i];
+        if (false == CheckDistEpipolarLine(kps1[d.queryIdx], kps2[d.trainIdx], F12, level_sigma2)) m[i] = m[j--]; else i++;
+    }
+    return i;
+}
+
 // ---- stereo (uses the pyramids held by the two extractor handles, as the reference does) ----
 int ora_stereo_match(void* hl, void* hr, const KeyPoint* kl, const uint8_t* dl, int nl, const KeyPoint* kr, const uint8_t* dr, int nr,
                      int nRows, float bf, float b, float* u_right, float* depth_left, int* best_dist, int* best_r) {
