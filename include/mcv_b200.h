@@ -79,8 +79,11 @@ void mcv_orb_destroy(mcv_orb* h);
 mcv_status mcv_orb_get_scales(const mcv_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                               int32_t* features_per_level);
 /* Upper bound of keypoints one Extract call can return for `n_seeds` pre-seeded keypoints (quadtree overshoot
- * included, ORBextractor.cc:557-565). Size kps_out/desc_out with this. */
+ * included, ORBextractor.cc:557-565): per level quota + 3 + the number of quadtree roots. mcv_orb_max_keypoints is valid for
+ * every image size the engine accepts (15 roots per level); mcv_orb_max_keypoints_for is the exact bound for a w x h image
+ * (roots = round(width / height) of the level's usable area, ORBextractor.cc:527). Size kps_out/desc_out with either. */
 int mcv_orb_max_keypoints(const mcv_orb* h, int n_seeds);
+int mcv_orb_max_keypoints_for(const mcv_orb* h, int w, int hgt, int n_seeds);
 
 /* BaseExtractor::Extract(img, kps, desps) (BaseExtractor.hpp:17) == ORBextractor::operator() (ORBextractor.cc:831-899).
  * img: CV_8UC1 host image (w x h, row stride in bytes). seeds: caller's pre-seeded keypoints (may be NULL/0), appended
@@ -112,6 +115,14 @@ mcv_status mcv_orb_distribute_octree(mcv_orb* h, const mcv_keypoint* in, int n, 
 /* ------------------------------------------------------------------------------------------------------------
  * Matcher — replaces MCVSLAM::Matcher statics (include/Matcher.hpp:58-92, src/Matcher.cpp).
  * Descriptors are rows of 32 bytes. All buffers host unless the name ends in _device.
+ *
+ * Threading (the reference's Matcher is stateless, "may be called from any thread"): every entry point of this section and of
+ * the caller-side sections below (projection / fuse / window tracking / distinctive descriptors / optical flow / BoW) is
+ * re-entrant. Each host thread owns a private context per device — a non-blocking stream and all scratch buffers — created
+ * on first use on the calling thread's CURRENT device (cudaGetDevice; the library never switches devices here) and released
+ * when the thread exits. mcv_knn2_bf_device works on the caller's stream with a stream-ordered scratch allocation. Extractor
+ * and rig handles are stateful like the reference's static ORB instances: one call at a time per handle, different handles
+ * concurrently.
  * ---------------------------------------------------------------------------------------------------------- */
 
 /* Matcher::KnnMatch(const cv::Mat&, const cv::Mat&, 2) / KnnMatch_cv (src/Matcher.cpp:134-138,304-308) ==
@@ -174,7 +185,10 @@ mcv_status mcv_rig_create(const mcv_rig_params* params, int device, void* stream
 mcv_status mcv_rig_set_input_channels(mcv_rig* r, int channels);
 mcv_status mcv_orb_set_input_channels(mcv_orb* h, int channels);
 void mcv_rig_destroy(mcv_rig* r);
+/* Per-image keypoint slots (`cap`) the rig's outputs need: the bound for aspect ratios <= 4.5 (4 quadtree roots per level), and
+ * the exact bound for a w x h image. A too small cap is MCV_ERR_CAPACITY, never an overrun. */
 int mcv_rig_max_keypoints(const mcv_rig* r);
+int mcv_rig_max_keypoints_for(const mcv_rig* r, int w, int hgt);
 /* The extractor of slot 0 (image index = 3*frame + cam within the chunk it processed last; cam 0=L,1=R,2=W). The whole batch
  * is in it when it ran as one chunk: n_frames <= chunk_frames/... see mcv_rig_set_chunk_frames(r, 0). */
 mcv_orb* mcv_rig_extractor(mcv_rig* r);
@@ -199,8 +213,9 @@ mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames
  * the step — host->device copy of the images, kernels, device->host copy of every result — on the rig's internal streams and
  * returns a ticket; consecutive submits overlap (copies of one step beside the kernels of another; this replaces the reference's
  * capture thread running ahead of Frame construction, src/System.cpp:60-66). The outputs of a submit are complete after
- * mcv_rig_wait(ticket) (or mcv_rig_sync). The caller keeps the buffers alive and untouched until then; at most 8 tickets may be
- * outstanding. Chunk size: env MCV_RIG_SUBMIT_CHUNK (default 64 frames). */
+ * mcv_rig_wait(ticket) (or mcv_rig_sync). The caller keeps the buffers alive and untouched until then. Tickets complete in
+ * submission order; the library tracks the last 8 individually — waiting on an older one waits for the later ticket that
+ * took over its slot (never returns early). Chunk size: env MCV_RIG_SUBMIT_CHUNK (default 128 frames). */
 mcv_status mcv_rig_submit(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, mcv_keypoint* kps_out, uint8_t* desc_out,
                           int32_t* counts, float* u_right, float* depth_left, int cap, long long* ticket);
 mcv_status mcv_rig_wait(mcv_rig* r, long long ticket);

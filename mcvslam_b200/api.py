@@ -25,7 +25,7 @@ ORB_GOOD_THRESHOLD = 46  # include/Matcher.hpp:14
 
 EXPORTS = [
     "mcv_last_error", "mcv_version", "mcv_device_count", "mcv_orb_create", "mcv_orb_destroy", "mcv_orb_get_scales",
-    "mcv_orb_max_keypoints", "mcv_orb_extract", "mcv_orb_extract_batch", "mcv_orb_download_level", "mcv_orb_level_device",
+    "mcv_orb_max_keypoints", "mcv_orb_max_keypoints_for", "mcv_rig_max_keypoints_for", "mcv_orb_extract", "mcv_orb_extract_batch", "mcv_orb_download_level", "mcv_orb_level_device",
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
     "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
@@ -69,6 +69,8 @@ def lib():
         L.mcv_orb_destroy.restype = None
         L.mcv_orb_get_scales.argtypes = [vp] * 6
         L.mcv_orb_max_keypoints.argtypes = [vp, i]
+        L.mcv_orb_max_keypoints_for.argtypes = [vp, i, i, i]
+        L.mcv_rig_max_keypoints_for.argtypes = [vp, i, i]
         L.mcv_orb_extract.argtypes = [vp, vp, i, i, sz, vp, i, vp, vp, i, C.POINTER(i)]
         L.mcv_orb_extract_batch.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, i, i]
         L.mcv_orb_download_level.argtypes = [vp, i, i, vp, sz, C.POINTER(i), C.POINTER(i)]
@@ -183,7 +185,10 @@ class ORB:
     def GetLevels(self):
         return self.nlevels
 
-    def max_keypoints(self, n_seeds=0):
+    def max_keypoints(self, n_seeds=0, w=0, h=0):
+        """Size-independent bound, or the exact bound for a w x h image."""
+        if w and h:
+            return lib().mcv_orb_max_keypoints_for(self._h, w, h, n_seeds)
         return lib().mcv_orb_max_keypoints(self._h, n_seeds)
 
     def Extract(self, img, kps=None):
@@ -202,7 +207,7 @@ class ORB:
                 img = np.ascontiguousarray(img)
         seeds = None if kps is None or len(kps) == 0 else np.ascontiguousarray(kps, KP_DTYPE)
         ns = 0 if seeds is None else len(seeds)
-        cap = self.max_keypoints(ns)
+        cap = self.max_keypoints(ns, img.shape[1], img.shape[0])
         out_k = np.zeros(cap, KP_DTYPE); out_d = np.zeros((cap, 32), np.uint8)
         n = C.c_int(0)
         _check(lib().mcv_orb_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(seeds), ns, _p(out_k), _p(out_d),
@@ -213,7 +218,7 @@ class ORB:
         """imgs: (n, H, W) u8 host array. Returns list of (kps, desps)."""
         imgs = _u8(imgs)
         n, h, w = imgs.shape
-        cap = self.max_keypoints(0)
+        cap = self.max_keypoints(0, w, h)
         out_k = np.zeros((n, cap), KP_DTYPE); out_d = np.zeros((n, cap, 32), np.uint8); cnt = np.zeros(n, np.int32)
         _check(lib().mcv_orb_extract_batch(self._h, _p(imgs), n, w, h, 0, _p(out_k), _p(out_d), _p(cnt), cap, 0))
         return [(out_k[i, :cnt[i]].copy(), out_d[i, :cnt[i]].copy()) for i in range(n)]

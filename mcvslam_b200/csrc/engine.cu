@@ -349,10 +349,26 @@ mcv_status mcv_orb_get_scales(const mcv_orb* h, float* scale, float* inv_scale, 
     return MCV_OK;
 }
 
+// per level: quota + 3 (overshoot of the last split, ORBextractor.cc:557-565) + n_ini roots (build_plan: out_cap)
+static int max_keypoints_roots(const mcv_orb* h, int roots_per_level) {
+    int n = 0;
+    for (int l = 0; l < h->prm.nlevels; ++l) n += h->quota[l] + 3 + roots_per_level;
+    return n;
+}
 int mcv_orb_max_keypoints(const mcv_orb* h, int n_seeds) {
     if (!h) return 0;
+    // size-independent bound: 15 roots per level is the most the quadtree kernels accept (any aspect ratio)
+    return max_keypoints_roots(h, 15) + std::max(0, n_seeds);
+}
+int mcv_orb_max_keypoints_for(const mcv_orb* h, int w, int hgt, int n_seeds) {
+    if (!h || w <= 0 || hgt <= 0) return 0;
     int n = 0;
-    for (int l = 0; l < h->prm.nlevels; ++l) n += h->quota[l] + 3 + 4;  // +n_ini roots (<= 4 for aspect <= 4.5)
+    for (int l = 0; l < h->prm.nlevels; ++l) {   // n_ini exactly as build_plan / ORBextractor.cc:527-529
+        const int lw = cv_round_host((float)w * h->inv_scale[l]), lh = cv_round_host((float)hgt * h->inv_scale[l]);
+        const int den = lh - 2 * BORDER;
+        const int n_ini = den > 0 ? (int)roundf((float)(lw - 2 * BORDER) / (float)den) : 15;
+        n += h->quota[l] + 3 + std::max(1, std::min(15, n_ini));
+    }
     return n + std::max(0, n_seeds);
 }
 
@@ -367,7 +383,7 @@ mcv_status mcv_orb_extract(mcv_orb* h, const uint8_t* img, int w, int hgt, size_
     mcv_status st = ensure_workspace(h, w, hgt, 1, std::max(cap, 1));
     if (st) return st;
     const Plan& P = h->plan;
-    if (cap < P.max_quad_kp + n_seeds) { set_error("cap smaller than mcv_orb_max_keypoints()"); return MCV_ERR_CAPACITY; }
+    if (cap < P.max_quad_kp + n_seeds) { set_error("cap smaller than mcv_orb_max_keypoints_for(w, h)"); return MCV_ERR_CAPACITY; }
     SeedInfo si{};
     if (n_seeds > 0) {
         for (int i = 0; i < n_seeds; ++i) {
@@ -409,7 +425,7 @@ mcv_status mcv_orb_extract_batch(mcv_orb* h, const uint8_t* imgs, int n_images, 
     MCV_CUDA(cudaSetDevice(h->device));
     mcv_status st = ensure_workspace(h, w, hgt, n_images, out_on_device ? 1 : cap);
     if (st) return st;
-    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_orb_max_keypoints()"); return MCV_ERR_CAPACITY; }
+    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_orb_max_keypoints_for(w, h)"); return MCV_ERR_CAPACITY; }
     const uint8_t* d_imgs = imgs;
     const size_t img_bytes = (size_t)w * hgt * h->channels;
     if (!imgs_on_device) {
@@ -529,39 +545,67 @@ mcv_status mcv_orb_distribute_octree(mcv_orb* h, const mcv_keypoint* in, int n, 
 // matcher (stateless in the reference: process-wide scratch on the current device, default stream 0 unless given)
 // =========================================================================================================
 namespace {
-struct MatchScratch {
-    DevBuf q, t, idx, dist, off, cidx;
+// The reference's Matcher is stateless and callable from any thread (include/Matcher.hpp:58-92). Every host
+// thread therefore gets its OWN context per device — a non-blocking stream plus every scratch buffer the matcher-side entry
+// points use — created on first use on the calling thread's current device (cudaGetDevice, like any CUDA library) and freed
+// when the thread exits. Concurrent calls from different threads, or on different devices, share no state.
+struct MatchCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    DevBuf q, t, idx, dist, off, cidx, part;
+    DevBuf slot[12];          // per-entry-point buffers (project / fuse / wnd_track / distinctive / lk / bow / debug)
 };
-MatchScratch g_ms;
-cudaStream_t g_match_stream = nullptr;
+struct MatchCtxList {
+    std::vector<MatchCtx*> v;
+    ~MatchCtxList() {
+        for (MatchCtx* c : v) {
+            if (cudaSetDevice(c->device) == cudaSuccess) {   // fails harmlessly once the runtime is shutting down
+                DevBuf* all[] = {&c->q, &c->t, &c->idx, &c->dist, &c->off, &c->cidx, &c->part};
+                for (DevBuf* b : all) b->release();
+                for (DevBuf& b : c->slot) b.release();
+                if (c->stream) cudaStreamDestroy(c->stream);
+            }
+            delete c;
+        }
+    }
+};
+thread_local MatchCtxList tl_match;
 
-mcv_status match_stream(cudaStream_t* s) {
+mcv_status match_ctx(MatchCtx** out) {
     if (mcv_device_count() < 1) { set_error("no CUDA device"); return MCV_ERR_NO_DEVICE; }
-    if (!g_match_stream) MCV_CUDA(cudaStreamCreateWithFlags(&g_match_stream, cudaStreamNonBlocking));
-    *s = g_match_stream;
+    int dev = 0;
+    MCV_CUDA(cudaGetDevice(&dev));
+    for (MatchCtx* c : tl_match.v) if (c->device == dev) { *out = c; return MCV_OK; }
+    MatchCtx* c = new MatchCtx;
+    c->device = dev;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; set_error("cudaStreamCreate failed"); return MCV_ERR_CUDA; }
+    tl_match.v.push_back(c);
+    *out = c;
     return MCV_OK;
 }
 
 // runs brute-force 2-NN on host descriptors, returns idx/dist vectors (nq*2)
 mcv_status bf_host(const uint8_t* q, int nq, const uint8_t* t, int nt, std::vector<int32_t>& idx, std::vector<int32_t>& dist) {
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
+    cudaStream_t s = mc->stream;
     idx.assign((size_t)nq * 2, -1); dist.assign((size_t)nq * 2, 0x7fffffff);
     if (nq == 0) return MCV_OK;
-    if ((st = g_ms.q.reserve((size_t)nq * 32))) return st;
-    if ((st = g_ms.t.reserve(std::max<size_t>(32, (size_t)nt * 32)))) return st;
-    if ((st = g_ms.idx.reserve((size_t)nq * 8))) return st;
-    if ((st = g_ms.dist.reserve((size_t)nq * 8))) return st;
-    MCV_CUDA(cudaMemcpyAsync(g_ms.q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
-    if (nt) MCV_CUDA(cudaMemcpyAsync(g_ms.t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
-    if (launch_knn2_bf(g_ms.q.as<uint8_t>(), nq, g_ms.t.as<uint8_t>(), nt, 0, g_ms.idx.as<int32_t>(), g_ms.dist.as<int32_t>(), s) < 0) {
+    if ((st = mc->q.reserve((size_t)nq * 32))) return st;
+    if ((st = mc->t.reserve(std::max<size_t>(32, (size_t)nt * 32)))) return st;
+    if ((st = mc->idx.reserve((size_t)nq * 8))) return st;
+    if ((st = mc->dist.reserve((size_t)nq * 8))) return st;
+    MCV_CUDA(cudaMemcpyAsync(mc->q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt) MCV_CUDA(cudaMemcpyAsync(mc->t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    if ((st = mc->part.reserve(std::max<size_t>(8, knn2_bf_part_bytes(nq, nt))))) return st;
+    if (launch_knn2_bf(mc->q.as<uint8_t>(), nq, mc->t.as<uint8_t>(), nt, 0, mc->idx.as<int32_t>(), mc->dist.as<int32_t>(), mc->part.as<unsigned>(), s) < 0) {
         set_error("knn2_bf: train set larger than 4M rows per call (tile it with train_offset) or out of memory");
         return MCV_ERR_CAPACITY;
     }
     MCV_CUDA(cudaGetLastError());
-    MCV_CUDA(cudaMemcpyAsync(idx.data(), g_ms.idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
-    MCV_CUDA(cudaMemcpyAsync(dist.data(), g_ms.dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(idx.data(), mc->idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(dist.data(), mc->dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaStreamSynchronize(s));
     return MCV_OK;
 }
@@ -612,25 +656,26 @@ mcv_status mcv_knn2_candidates(const uint8_t* q, int nq, const uint8_t* t, int n
     if (total < 0 || (total > 0 && (!cand_idx || !t))) return MCV_ERR_BAD_ARG;
     for (int i = 0; i < nq; ++i) if (cand_off[i + 1] < cand_off[i] || cand_off[i + 1] - cand_off[i] >= (1 << 20)) return MCV_ERR_BAD_ARG;
     for (int i = 0; i < total; ++i) if (cand_idx[i] < 0 || cand_idx[i] >= nt) return MCV_ERR_BAD_ARG;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    if ((st = g_ms.q.reserve((size_t)nq * 32))) return st;
-    if ((st = g_ms.t.reserve(std::max<size_t>(32, (size_t)nt * 32)))) return st;
-    if ((st = g_ms.idx.reserve((size_t)nq * 8))) return st;
-    if ((st = g_ms.dist.reserve((size_t)nq * 8))) return st;
-    if ((st = g_ms.off.reserve((size_t)(nq + 1) * 4))) return st;
-    if ((st = g_ms.cidx.reserve(std::max<size_t>(4, (size_t)total * 4)))) return st;
-    MCV_CUDA(cudaMemcpyAsync(g_ms.q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
-    if (nt) MCV_CUDA(cudaMemcpyAsync(g_ms.t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
-    MCV_CUDA(cudaMemcpyAsync(g_ms.off.p, cand_off, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
-    if (total) MCV_CUDA(cudaMemcpyAsync(g_ms.cidx.p, cand_idx, (size_t)total * 4, cudaMemcpyHostToDevice, s));
-    launch_knn2_candidates(g_ms.q.as<uint8_t>(), nq, g_ms.t.as<uint8_t>(), g_ms.off.as<int32_t>(), g_ms.cidx.as<int32_t>(), g_ms.idx.as<int32_t>(),
-                           g_ms.dist.as<int32_t>(), s);
+    cudaStream_t s = mc->stream;
+    if ((st = mc->q.reserve((size_t)nq * 32))) return st;
+    if ((st = mc->t.reserve(std::max<size_t>(32, (size_t)nt * 32)))) return st;
+    if ((st = mc->idx.reserve((size_t)nq * 8))) return st;
+    if ((st = mc->dist.reserve((size_t)nq * 8))) return st;
+    if ((st = mc->off.reserve((size_t)(nq + 1) * 4))) return st;
+    if ((st = mc->cidx.reserve(std::max<size_t>(4, (size_t)total * 4)))) return st;
+    MCV_CUDA(cudaMemcpyAsync(mc->q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt) MCV_CUDA(cudaMemcpyAsync(mc->t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    MCV_CUDA(cudaMemcpyAsync(mc->off.p, cand_off, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (total) MCV_CUDA(cudaMemcpyAsync(mc->cidx.p, cand_idx, (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    launch_knn2_candidates(mc->q.as<uint8_t>(), nq, mc->t.as<uint8_t>(), mc->off.as<int32_t>(), mc->cidx.as<int32_t>(), mc->idx.as<int32_t>(),
+                           mc->dist.as<int32_t>(), s);
     MCV_CUDA(cudaGetLastError());
     std::vector<int32_t> idx((size_t)nq * 2), dist((size_t)nq * 2);
-    MCV_CUDA(cudaMemcpyAsync(idx.data(), g_ms.idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
-    MCV_CUDA(cudaMemcpyAsync(dist.data(), g_ms.dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(idx.data(), mc->idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(dist.data(), mc->dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < nq; ++i)
         for (int e = 0; e < 2; ++e) out[2 * i + e] = mcv_dmatch{i, idx[2 * i + e], -1, (float)dist[2 * i + e]};
@@ -639,11 +684,15 @@ mcv_status mcv_knn2_candidates(const uint8_t* q, int nq, const uint8_t* t, int n
 
 mcv_status mcv_knn2_bf_device(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, void* stream) {
     if (nq < 0 || nt < 0 || (nq > 0 && (!d_q || !d_idx || !d_dist)) || (nt > 0 && !d_t)) return MCV_ERR_BAD_ARG;
-    if (launch_knn2_bf(d_q, nq, d_t, nt, train_offset, d_idx, d_dist, (cudaStream_t)stream) < 0) {
-        set_error("knn2_bf_device: train set larger than 4M rows per call or out of memory");
-        return MCV_ERR_CAPACITY;
-    }
-    MCV_CUDA(cudaGetLastError());
+    if (nq == 0) return MCV_OK;
+    // the partial keys live in a stream-ordered allocation on the CALLER's stream: safe with any stream from any thread
+    unsigned* d_part = nullptr;
+    MCV_CUDA(cudaMallocAsync((void**)&d_part, std::max<size_t>(8, knn2_bf_part_bytes(nq, nt)), (cudaStream_t)stream));
+    const int rc = launch_knn2_bf(d_q, nq, d_t, nt, train_offset, d_idx, d_dist, d_part, (cudaStream_t)stream);
+    const cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(d_part, (cudaStream_t)stream);
+    if (rc < 0) { set_error("knn2_bf_device: train set larger than 4M rows per call"); return MCV_ERR_CAPACITY; }
+    MCV_CUDA(le);
     return MCV_OK;
 }
 
@@ -656,10 +705,11 @@ mcv_status mcv_project_match(const mcv_keypoint* kps, const uint8_t* desc, int n
     for (int m = 0; m < n_mp; ++m) if (mp_level[m] < 0 || mp_level[m] >= nlevels) return MCV_ERR_BAD_ARG;
     if (n_matched) *n_matched = 0;
     if (n_mp == 0) return MCV_OK;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b_kps, b_desc, b_f, b_xyz, b_mpd, b_lvl, b_oi, b_od;
+    cudaStream_t s = mc->stream;
+    DevBuf &b_kps = mc->slot[0], &b_desc = mc->slot[1], &b_f = mc->slot[2], &b_xyz = mc->slot[3], &b_mpd = mc->slot[4], &b_lvl = mc->slot[5], &b_oi = mc->slot[6], &b_od = mc->slot[7];
     if ((st = b_kps.reserve(std::max<size_t>(28, (size_t)n * sizeof(mcv_keypoint))))) return st;
     if ((st = b_desc.reserve(std::max<size_t>(32, (size_t)n * 32)))) return st;
     if ((st = b_f.reserve((size_t)(nlevels + 16) * 4))) return st;
@@ -700,10 +750,11 @@ mcv_status mcv_fuse_match(const mcv_keypoint* kps, const uint8_t* desc, int n, i
     for (int i = 0; i < n; ++i) if (kps[i].octave < 0 || kps[i].octave >= nlevels) return MCV_ERR_BAD_ARG;
     if (n_matched) *n_matched = 0;
     if (n_mp == 0) return MCV_OK;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b_kps, b_desc, b_f, b_dl, b_xyz, b_nrm, b_mpd, b_lvl, b_oi, b_od;
+    cudaStream_t s = mc->stream;
+    DevBuf &b_kps = mc->slot[0], &b_desc = mc->slot[1], &b_f = mc->slot[2], &b_dl = mc->slot[3], &b_xyz = mc->slot[4], &b_nrm = mc->slot[5], &b_mpd = mc->slot[6], &b_lvl = mc->slot[7], &b_oi = mc->slot[8], &b_od = mc->slot[9];
     if ((st = b_kps.reserve(std::max<size_t>(28, (size_t)n * sizeof(mcv_keypoint))))) return st;
     if ((st = b_desc.reserve(std::max<size_t>(32, (size_t)n * 32)))) return st;
     if ((st = b_dl.reserve(std::max<size_t>(4, (size_t)n * 4)))) return st;
@@ -746,10 +797,11 @@ mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1,
     for (int q = 0; q < n_q; ++q) if (q_idx[q] < 0 || q_idx[q] >= n1) return MCV_ERR_BAD_ARG;
     if (n_matched) *n_matched = 0;
     if (n_q == 0) return MCV_OK;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b_k1, b_d1, b_q, b_k2, b_d2, b_oi, b_ob, b_od;
+    cudaStream_t s = mc->stream;
+    DevBuf &b_k1 = mc->slot[0], &b_d1 = mc->slot[1], &b_q = mc->slot[2], &b_k2 = mc->slot[3], &b_d2 = mc->slot[4], &b_oi = mc->slot[5], &b_ob = mc->slot[6], &b_od = mc->slot[7];
     if ((st = b_k1.reserve((size_t)n1 * sizeof(mcv_keypoint)))) return st;
     if ((st = b_d1.reserve((size_t)n1 * 32))) return st;
     if ((st = b_q.reserve((size_t)n_q * 4))) return st;
@@ -785,10 +837,11 @@ mcv_status mcv_distinctive_descriptors(const uint8_t* desc, const int32_t* mp_of
     for (int m = 0; m < n_mp; ++m) if (mp_off[m + 1] < mp_off[m] || mp_off[m + 1] - mp_off[m] >= (1 << 22)) return MCV_ERR_BAD_ARG;
     const int total = mp_off[n_mp];
     if (total > 0 && !desc) return MCV_ERR_BAD_ARG;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b_d, b_off, b_bi, b_bm;
+    cudaStream_t s = mc->stream;
+    DevBuf &b_d = mc->slot[0], &b_off = mc->slot[1], &b_bi = mc->slot[2], &b_bm = mc->slot[3];
     if ((st = b_d.reserve(std::max<size_t>(32, (size_t)total * 32)))) return st;
     if ((st = b_off.reserve((size_t)(n_mp + 1) * 4))) return st;
     if ((st = b_bi.reserve((size_t)n_mp * 4))) return st;
@@ -817,10 +870,11 @@ mcv_status mcv_lk_track_batch(const uint8_t* prev, const uint8_t* next, int n_pa
     for (int k = 0; k < n_pairs; ++k) if (pt_off[k + 1] < pt_off[k]) return MCV_ERR_BAD_ARG;
     const int n = pt_off[n_pairs];
     if (n > 0 && (!pts || !next_pts || !status || !err)) return MCV_ERR_BAD_ARG;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b_img, b_ws, b_pts, b_pair, b_out, b_st, b_err;
+    cudaStream_t s = mc->stream;
+    DevBuf &b_img = mc->slot[0], &b_ws = mc->slot[1], &b_pts = mc->slot[2], &b_pair = mc->slot[3], &b_out = mc->slot[4], &b_st = mc->slot[5], &b_err = mc->slot[6];
     const size_t img_bytes = (size_t)w * hgt;
     if ((st = b_img.reserve(2 * img_bytes * n_pairs))) return st;
     if ((st = b_ws.reserve(lk_workspace_bytes(w, hgt) * n_pairs))) return st;
@@ -885,7 +939,7 @@ mcv_status mcv_kl_track(const uint8_t* prev, const uint8_t* next, int w, int hgt
 // ---- Object::ComputeBow: DBoW3 vocabulary on the device + Vocabulary::transform ----
 struct mcv_voc {
     int device = 0, n_nodes = 0, L = 0, weighting = 0, norm = 1;
-    DevBuf child_off, child_ids, node_desc, feat, leaf, nid;
+    DevBuf child_off, child_ids, node_desc;
     std::vector<int32_t> word_id, h_child_off;
     std::vector<double> weight;
 };
@@ -919,7 +973,7 @@ mcv_status mcv_voc_create(int n_nodes, const int32_t* child_off, const uint32_t*
 void mcv_voc_destroy(mcv_voc* v) {
     if (!v) return;
     cudaSetDevice(v->device);
-    for (DevBuf* b : {&v->child_off, &v->child_ids, &v->node_desc, &v->feat, &v->leaf, &v->nid}) b->release();
+    for (DevBuf* b : {&v->child_off, &v->child_ids, &v->node_desc}) b->release();
     delete v;
 }
 
@@ -930,17 +984,19 @@ mcv_status mcv_bow_transform(mcv_voc* v, const uint8_t* desc, int n, int levelsu
     if (fv_off) fv_off[0] = 0;
     if (n == 0) return MCV_OK;
     MCV_CUDA(cudaSetDevice(v->device));
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    if ((st = v->feat.reserve((size_t)n * 32)) || (st = v->leaf.reserve((size_t)n * 4)) || (st = v->nid.reserve((size_t)n * 4))) return st;
-    MCV_CUDA(cudaMemcpyAsync(v->feat.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
-    launch_bow_descend(v->feat.as<uint8_t>(), n, v->child_off.as<int32_t>(), v->child_ids.as<uint32_t>(), v->node_desc.as<uint8_t>(), v->L - levelsup,
-                       std::max(v->L, 1) + 32, v->leaf.as<uint32_t>(), v->nid.as<uint32_t>(), s);
+    cudaStream_t s = mc->stream;
+    DevBuf &b_feat = mc->slot[0], &b_leaf = mc->slot[1], &b_nid = mc->slot[2];   // per calling thread: two threads may share one vocabulary
+    if ((st = b_feat.reserve((size_t)n * 32)) || (st = b_leaf.reserve((size_t)n * 4)) || (st = b_nid.reserve((size_t)n * 4))) return st;
+    MCV_CUDA(cudaMemcpyAsync(b_feat.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    launch_bow_descend(b_feat.as<uint8_t>(), n, v->child_off.as<int32_t>(), v->child_ids.as<uint32_t>(), v->node_desc.as<uint8_t>(), v->L - levelsup,
+                       std::max(v->L, 1) + 32, b_leaf.as<uint32_t>(), b_nid.as<uint32_t>(), s);
     MCV_CUDA(cudaGetLastError());
     std::vector<uint32_t> leaf(n), nid(n);
-    MCV_CUDA(cudaMemcpyAsync(leaf.data(), v->leaf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    MCV_CUDA(cudaMemcpyAsync(nid.data(), v->nid.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(leaf.data(), b_leaf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    MCV_CUDA(cudaMemcpyAsync(nid.data(), b_nid.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaStreamSynchronize(s));
     // BowVector / FeatureVector assembly (Vocabulary.cpp:586-631, BowVector.cpp, FeatureVector.cpp): std::map insertions in
     // feature order — the order the weights of one word are summed in is part of the (double) result
@@ -981,10 +1037,11 @@ mcv_status mcv_bow_transform(mcv_voc* v, const uint8_t* desc, int n, int levelsu
 
 mcv_status mcv_debug_sincosf(const float* a, int n, float* so, float* co) {
     if (n <= 0 || !a || !so || !co) return MCV_ERR_BAD_ARG;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b;
+    cudaStream_t s = mc->stream;
+    DevBuf &b = mc->slot[0];
     if ((st = b.reserve((size_t)n * 12))) return st;
     float* d = b.as<float>();
     MCV_CUDA(cudaMemcpyAsync(d, a, (size_t)n * 4, cudaMemcpyHostToDevice, s));
@@ -998,10 +1055,11 @@ mcv_status mcv_debug_sincosf(const float* a, int n, float* so, float* co) {
 
 mcv_status mcv_debug_fast_atan2(const float* y, const float* x, int n, float* out) {
     if (n <= 0 || !y || !x || !out) return MCV_ERR_BAD_ARG;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b;
+    cudaStream_t s = mc->stream;
+    DevBuf &b = mc->slot[0];
     if ((st = b.reserve((size_t)n * 12))) return st;
     float* d = b.as<float>();
     MCV_CUDA(cudaMemcpyAsync(d, y, (size_t)n * 4, cudaMemcpyHostToDevice, s));
@@ -1021,10 +1079,11 @@ mcv_status mcv_debug_octree_clocks(long long* out8) {
 
 mcv_status mcv_debug_popc_peak(int iters, double* popc_per_s, double* ms_out) {
     if (iters <= 0) return MCV_ERR_BAD_ARG;
-    cudaStream_t s;
-    mcv_status st = match_stream(&s);
+    MatchCtx* mc;
+    mcv_status st = match_ctx(&mc);
     if (st) return st;
-    static DevBuf b;
+    cudaStream_t s = mc->stream;
+    DevBuf &b = mc->slot[0];
     if ((st = b.reserve(64))) return st;
     const int blocks = NUM_SMS * 8, threads = 256;
     launch_popc_peak(iters, b.as<unsigned>(), blocks, threads, s);  // warm-up
@@ -1093,7 +1152,7 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
     mcv_orb* h = sl.orb;
     mcv_status st = ensure_workspace(h, w, hgt, 3 * n_frames, 1);
     if (st) return st;
-    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints()"); return MCV_ERR_CAPACITY; }
+    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints_for(w, h)"); return MCV_ERR_CAPACITY; }
     if ((st = sl.best_dist.reserve((size_t)n_frames * cap * 4))) return st;
     if ((st = sl.st_scratch.reserve(stereo_scratch_bytes(h->plan, n_frames, cap)))) return st;
     st = enqueue_extract(h, d_imgs, (size_t)w * h->channels, (size_t)w * hgt * h->channels, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap,
@@ -1214,7 +1273,8 @@ void mcv_rig_destroy(mcv_rig* r) {
     delete r;
 }
 
-int mcv_rig_max_keypoints(const mcv_rig* r) { return r ? mcv_orb_max_keypoints(r->slot[0].orb, 0) : 0; }
+int mcv_rig_max_keypoints(const mcv_rig* r) { return r ? max_keypoints_roots(r->slot[0].orb, 4) : 0; }   // aspect ratio <= 4.5
+int mcv_rig_max_keypoints_for(const mcv_rig* r, int w, int hgt) { return r ? mcv_orb_max_keypoints_for(r->slot[0].orb, w, hgt, 0) : 0; }
 mcv_orb* mcv_rig_extractor(mcv_rig* r) { return r ? r->slot[0].orb : nullptr; }
 int mcv_rig_last_launches(const mcv_rig* r) { return r ? r->last_launches : 0; }
 mcv_status mcv_rig_set_chunk_frames(mcv_rig* r, int chunk_frames) {
@@ -1357,8 +1417,9 @@ mcv_status mcv_rig_submit(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, 
 
 mcv_status mcv_rig_wait(mcv_rig* r, long long ticket) {
     if (!r || ticket <= 0 || ticket > r->submitted) return MCV_ERR_BAD_ARG;
-    if (r->submitted - ticket >= RIG_TICKETS) return MCV_OK;   // older than the ring: completed before a later ticket was recorded over it
     MCV_CUDA(cudaSetDevice(r->device));
+    // A ticket older than the ring shares its event slot with a LATER ticket; tickets complete in submission order (one ordered
+    // gather stream), so waiting on the slot's current occupant is a correct — merely later — completion point.
     MCV_CUDA(cudaEventSynchronize(r->ticket[ticket % RIG_TICKETS]));
     return MCV_OK;
 }

@@ -108,7 +108,9 @@ int launch_octree_standalone(const uint32_t* d_pts, int n, int w_box, int h_box,
 int octree_debug_clocks(long long out[8]);
 
 // matching
-int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, cudaStream_t s);
+size_t knn2_bf_part_bytes(int nq, int nt);   // partial-key scratch one call needs (owned by the caller: the launchers are stateless)
+int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, unsigned* d_part,
+                   cudaStream_t s);
 int launch_knn2_candidates(const uint8_t* d_q, int nq, const uint8_t* d_t, const int32_t* d_off, const int32_t* d_cidx, int32_t* d_idx,
                            int32_t* d_dist, cudaStream_t s);
 int launch_project(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_scale, const float* d_pose,

@@ -75,26 +75,30 @@ __global__ void __launch_bounds__(256) k_knn2_merge(const unsigned* __restrict__
     dist[2 * qi + 1] = k1 == BF_SENT ? 0x7fffffff : (int)(k1 >> BF_IDX_BITS);
 }
 
-// scratch for the partial keys: grown on demand, one per device (the matcher is stateless in the reference)
-static unsigned* g_part = nullptr;
-static size_t g_part_bytes = 0;
-
-int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, cudaStream_t s) {
-    if (nq <= 0) return 0;
-    if (nt > (1 << BF_IDX_BITS)) return -1;
-    const int q_blocks = (nq + BF_THREADS - 1) / BF_THREADS;
-    // enough CTAs for ~4 per SM, but at least BF_TILE train rows each
-    int n_splits = std::max(1, std::min((4 * NUM_SMS + q_blocks - 1) / q_blocks, (nt + BF_TILE - 1) / BF_TILE));
-    int per_split = nt > 0 ? ((nt + n_splits - 1) / n_splits + BF_TILE - 1) / BF_TILE * BF_TILE : BF_TILE;
+// Split geometry of one brute-force call: enough CTAs for ~4 per SM, but at least BF_TILE train rows each.
+static void bf_splits(int nq, int nt, int& q_blocks, int& n_splits, int& per_split) {
+    q_blocks = (nq + BF_THREADS - 1) / BF_THREADS;
+    n_splits = std::max(1, std::min((4 * NUM_SMS + q_blocks - 1) / q_blocks, (nt + BF_TILE - 1) / BF_TILE));
+    per_split = nt > 0 ? ((nt + n_splits - 1) / n_splits + BF_TILE - 1) / BF_TILE * BF_TILE : BF_TILE;
     n_splits = nt > 0 ? (nt + per_split - 1) / per_split : 1;
-    const size_t need = (size_t)n_splits * nq * 2 * sizeof(unsigned);
-    if (need > g_part_bytes) {
-        if (g_part) cudaFree(g_part);
-        if (cudaMalloc(&g_part, need) != cudaSuccess) { g_part = nullptr; g_part_bytes = 0; return -1; }
-        g_part_bytes = need;
-    }
-    k_knn2_bf<<<dim3(q_blocks, n_splits), BF_THREADS, 0, s>>>(d_q, nq, d_t, nt, per_split, g_part);
-    k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(g_part, nq, n_splits, train_offset, d_idx, d_dist);
+}
+
+// bytes of partial-key scratch one call needs; the CALLER owns it (per thread / per stream), the launcher keeps no state
+size_t knn2_bf_part_bytes(int nq, int nt) {
+    if (nq <= 0) return 0;
+    int q_blocks, n_splits, per_split;
+    bf_splits(nq, nt, q_blocks, n_splits, per_split);
+    return (size_t)n_splits * nq * 2 * sizeof(unsigned);
+}
+
+int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, unsigned* d_part,
+                   cudaStream_t s) {
+    if (nq <= 0) return 0;
+    if (nt > (1 << BF_IDX_BITS) || !d_part) return -1;
+    int q_blocks, n_splits, per_split;
+    bf_splits(nq, nt, q_blocks, n_splits, per_split);
+    k_knn2_bf<<<dim3(q_blocks, n_splits), BF_THREADS, 0, s>>>(d_q, nq, d_t, nt, per_split, d_part);
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(d_part, nq, n_splits, train_offset, d_idx, d_dist);
     return 2;
 }
 

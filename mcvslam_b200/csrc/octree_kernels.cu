@@ -531,11 +531,8 @@ static int launch_octree_legacy(const Plan& P, const uint32_t* d_cell_pts, const
     }
     int warps; size_t smem;
     if (oct_config(heap_cap, pts_cap, warps, smem)) return -1;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    // function attributes are per DEVICE and the call is cheap: set it on every launch that needs the opt-in (no process-wide cache)
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int tasks = n_images * P.n_levels;
     k_octree<<<(tasks + warps - 1) / warps, 32 * warps, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, P,
                                                                    n_images, heap_cap, pts_cap, d_only);
@@ -544,11 +541,13 @@ static int launch_octree_legacy(const Plan& P, const uint32_t* d_cell_pts, const
 
 int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
                   uint16_t* d_oct_idx, uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s) {
-    // profiling aid (what does the stage cost inside the pipelined step?): MCV_DEBUG_SKIP_OCTREE_AFTER=n stops launching the
-    // quadtree after n calls — downstream then consumes the previous call's selection, so results are only valid for repeated input
+#ifdef MCV_EXPERIMENTS
+    // profiling aid, compiled only into experiment builds (MCV_NVCC_EXTRA=-DMCV_EXPERIMENTS): MCV_DEBUG_SKIP_OCTREE_AFTER=n stops
+    // launching the quadtree after n calls — downstream then consumes the previous call's selection (valid for repeated input only)
     static const char* skip_env = getenv("MCV_DEBUG_SKIP_OCTREE_AFTER");
     static long skip_calls = 0;
     if (skip_env && ++skip_calls > atol(skip_env)) return 0;
+#endif
     // shared-memory plan of k_octree_prep / k_octree_replay: R0 = cursors, later heap | nodes (r0_words u32) | S (nb_pad u16)
     int nb = 1, max_ini = 1, max_heap = 8;
     bool can_overflow = false;
@@ -565,15 +564,20 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     const size_t smem = (size_t)r0_words * 4 + (size_t)nb_pad * 2;
     if (max_ini > oct::MAX_ROOTS || max_heap > 65000 || smem > 200 * 1024)   // panoramas / huge quotas: legacy kernel for everything
         return launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, nullptr, s);
-    static size_t configured = 0;
-    if (smem > configured) {
+    // function attributes are per DEVICE: cache per device (16 is more than one box holds), set on first use there
+    static bool configured[16] = {};
+    static size_t configured_smem[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int di = dev & 15;
+    if (!configured[di] || smem > configured_smem[di]) {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(k_octree_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(k_octree_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         // many small CTAs that live as long as one thread's heap replay: ask for the largest shared-memory carve-out
         cudaFuncSetAttribute(k_octree_replay, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = smem;
+        configured[di] = true; configured_smem[di] = std::max(configured_smem[di], smem);   // benign race: the calls are idempotent
     }
     const int tasks = n_images * P.n_levels;
     int* d_overflow = d_out_cnt + tasks;

@@ -102,7 +102,7 @@ class ORBextractor {
         if (_image.empty()) return -1;
         if (!h_) { status_ = MCV_ERR_BAD_ARG; err_ = "extractor not initialised"; return status_; }
         const std::vector<cv::KeyPoint> seeds = _keypoints;
-        const int cap = mcv_orb_max_keypoints(h_.get(), (int)seeds.size());
+        const int cap = mcv_orb_max_keypoints_for(h_.get(), _image.cols, _image.rows, (int)seeds.size());
         std::vector<cv::KeyPoint> out((size_t)cap);
         cv::Mat desc(cap, 32, CV_8U);
         int n = 0;
@@ -615,6 +615,7 @@ class Rig {
     // imgs: [n_frames][3][h][w] u8 host. Outputs sized by the callee: kps/desc [n_frames*3][cap], counts [n_frames*3], u_right/depth [n_frames][cap].
     void Process(const uint8_t* imgs, int n_frames, int w, int h, std::vector<cv::KeyPoint>& kps, std::vector<uint8_t>& desc, std::vector<int32_t>& counts,
                  std::vector<float>& u_right, std::vector<float>& depth_left) {
+        cap_ = std::max(cap_, mcv_rig_max_keypoints_for(r_.get(), w, h));   // wide panoramas have more than 4 quadtree roots per level
         kps.resize((size_t)n_frames * 3 * cap_); desc.resize((size_t)n_frames * 3 * cap_ * 32); counts.resize((size_t)n_frames * 3);
         u_right.resize((size_t)n_frames * cap_); depth_left.resize((size_t)n_frames * cap_);
         const mcv_status st = mcv_rig_process(r_.get(), imgs, n_frames, w, h, 0, mcv_host::kp_ptr(kps), desc.data(), counts.data(), u_right.data(),

@@ -413,3 +413,50 @@ def kl_track(orb, prev, nxt, kps):
     new = np.zeros(len(kps) + 1, KP_DTYPE); src = np.full(len(kps) + 1, -1, np.int32)
     cnt = lib().ref_kl_track(orb.h, _p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(kps), len(kps), _p(new), _p(src))
     return cnt, new[:cnt].copy(), src[:cnt].copy()
+
+
+# ---- CPU baseline legs of bench.py (the reference timed on the box's host cores) ------------------------------------------
+def bench_frames(cfg, n_procs, n_distinct, seed0, w, h, repeat, cv_threads=1, timeout_s=600):
+    """n_procs concurrent replicas of the unmodified reference, one PROCESS each (the three extractors are process-wide statics,
+    src/Frame.cpp:24-26, so replicas cannot share a process); every replica constructs n_distinct * repeat Frames from the same
+    seeded synthetic triplets, and every Frame fans its three extractions out over the reference's own ThreadPool(3).
+    Returns (frames/s over the union of the replicas' timed windows, total frames, stage seconds of replica 0)."""
+    import json
+    import subprocess
+    import sys
+    import time
+    start_at = time.time() + (0.0 if n_procs <= 1 else 4.0 + 0.1 * n_procs)
+    job = json.dumps(dict(cfg=list(cfg), n_distinct=n_distinct, seed0=seed0, w=w, h=h, repeat=repeat, start_at=start_at, cv_threads=cv_threads))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = [subprocess.Popen([sys.executable, "-m", "oracle.ref", job], cwd=root, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+             for _ in range(max(1, n_procs))]
+    res = []
+    for p in procs:
+        out, _ = p.communicate(timeout=timeout_s)
+        res.append(json.loads(out.strip().splitlines()[-1]))
+    t0 = min(r["t0"] for r in res); t1 = max(r["t1"] for r in res)
+    n = sum(r["frames"] for r in res)
+    return n / (t1 - t0), n, res[0]["stages"]
+
+
+def _worker_main(job):
+    import json
+    import sys
+    import time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from mcvslam_b200 import synth
+    j = json.loads(job)
+    lib().ref_set_num_threads(int(j["cv_threads"]))
+    frames = np.stack([synth.triplet(j["seed0"] + s, j["w"], j["h"]) for s in range(j["n_distinct"])])
+    rig = Rig(*j["cfg"])
+    rig.bench(frames[:1], 1)                       # warm-up: page in, allocate the pyramids
+    while time.time() < j["start_at"]:
+        time.sleep(0.001)
+    t0 = time.time()
+    s, kp, stages = rig.bench(frames, int(j["repeat"]))
+    print(json.dumps(dict(t0=t0, t1=time.time(), frames=len(frames) * int(j["repeat"]), kp=kp, stages=stages)), flush=True)
+
+
+if __name__ == "__main__":
+    import sys
+    _worker_main(sys.argv[1])

@@ -7,9 +7,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, "host_mirror_test.cpp")
 BIN = os.path.join(HERE, "_build", "host_mirror_test")
+SRC_THREADS = os.path.join(HERE, "matcher_threads_test.cpp")
+BIN_THREADS = os.path.join(HERE, "_build", "matcher_threads_test")
 
 
 def build(force=False):
+    _build_one(SRC_THREADS, BIN_THREADS, force)
+    return _build_one(SRC, BIN, force)
+
+
+def _build_one(SRC, BIN, force=False):
     pkg = os.path.join(ROOT, "mcvslam_b200")
     ora = os.path.join(ROOT, "oracle", "_build")
     deps = [SRC, os.path.join(pkg, "host", "mcvslam_b200.hpp"), os.path.join(pkg, "host", "cv_shim.hpp"), os.path.join(ROOT, "include", "mcv_b200.h"),

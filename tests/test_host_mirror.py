@@ -30,3 +30,13 @@ def test_host_mirror_equals_oracle(oracle, tmp_path):
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all results equal the oracle" in r.stdout
+
+
+@pytest.mark.gpu
+def test_matcher_entry_points_are_reentrant(oracle, tmp_path):
+    """Four host threads inside the matcher entry points at once (per-thread stream + scratch): every result equals the oracle."""
+    _bin(oracle)
+    import build_host_test
+    r = subprocess.run([build_host_test.BIN_THREADS, "4", "12"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all results equal the oracle" in r.stdout
