@@ -1,0 +1,318 @@
+// Probe: brute-force Hamming 2-NN on the 5th-gen tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+// Hamming(a, b) over 256 bits = (256 - <a', b'>) / 2 with a', b' the descriptors expanded to +-1 int8, so the all-pairs distance
+// table is an int8 GEMM (M = queries, N = train rows, K = 256) and the 2-NN is its epilogue.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tc_knn_probe tc_knn_probe.cu && ./tc_knn_probe
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int TC_M = 128;            // queries per CTA (UMMA M)
+constexpr int TC_N = 256;            // train rows per tile (UMMA N)
+constexpr int TC_KB = 128;           // bytes of K per shared-memory tile (one 128-byte swizzle atom row)
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr unsigned A_TILE_BYTES = TC_M * TC_KB;           // 16 KB per K half
+constexpr unsigned B_TILE_BYTES = TC_N * TC_KB;           // 32 KB per K half
+constexpr unsigned STAGE_BYTES = 2 * B_TILE_BYTES;        // 64 KB
+constexpr unsigned SMEM_BYTES = 2 * A_TILE_BYTES + TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int IDX_BITS = 22;
+constexpr unsigned SENT = 0xffffffffu;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned b, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned b, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned b) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\nW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\nD_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+// K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(unsigned smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);          // start address
+    d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset
+    d |= (uint64_t)1 << 46;                               // version
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+// kind::i8: D s32, A/B signed 8 bit, both K-major, M = 128, N = 256
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(unsigned tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, int (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+                 "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(taddr));
+}
+__host__ __device__ __forceinline__ void top2_update(unsigned& k0, unsigned& k1, unsigned key) { const unsigned hi = k0 > key ? k0 : key; k1 = k1 < hi ? k1 : hi; k0 = k0 < key ? k0 : key; }
+
+// descriptors (32 bytes) -> 256 int8 of +-1 (bit set -> -1), bit b of byte j at position 8 j + b
+__global__ void k_expand_pm1(const uint8_t* __restrict__ d, int n, int8_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // one 32-bit word of a descriptor
+    if (i >= n * 8) return;
+    const unsigned w = reinterpret_cast<const unsigned*>(d)[i];
+    uint4 o[2];
+    unsigned* ow = reinterpret_cast<unsigned*>(o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned nib = (w >> (4 * k)) & 0xfu;
+        const unsigned bits = (nib * 0x00204081u) & 0x01010101u;    // bit j of the nibble -> byte j
+        ow[k] = 0x01010101u ^ (bits * 0xfeu);                          // 0 -> 0x01 (+1), 1 -> 0xff (-1)
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * 32);
+    dst[0] = o[0]; dst[1] = o[1];
+}
+
+// grid = (ceil(nq / 128), n_splits). part[split][q][2] = partial top-2 keys (dist << 22 | trainIdx) of train rows [split * per_split, ...)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, int nq, int nt,
+                                                           int per_split, unsigned* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const unsigned sA = base, sB = base + 2 * A_TILE_BYTES, sBar = sB + TC_STAGES * STAGE_BYTES;
+    // barriers: a_full | full[S] | empty[S] | tmem_full[2] | tmem_empty[2] ; then the TMEM base address
+    const unsigned bar_a = sBar, bar_full = sBar + 8, bar_empty = bar_full + 8 * TC_STAGES, bar_tfull = bar_empty + 8 * TC_STAGES, bar_tempty = bar_tfull + 16;
+    const unsigned tmem_slot = bar_tempty + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * TC_M;
+    const int t_begin = blockIdx.y * per_split, t_end = min(nt, t_begin + per_split);
+    const int n_tiles = (t_end - t_begin + TC_N - 1) / TC_N;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: all 512 columns (two 128 x 256 s32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    unsigned tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, 2 * A_TILE_BYTES);
+            tma_load_2d(sA, &map_q, 0, q0, bar_a);
+            tma_load_2d(sA + A_TILE_BYTES, &map_q, TC_KB, q0, bar_a);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i % TC_STAGES;
+                if (i >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((i / TC_STAGES) - 1) & 1);
+                mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                const int row = t_begin + i * TC_N;
+                tma_load_2d(sB + s * STAGE_BYTES, &map_t, 0, row, bar_full + 8 * s);
+                tma_load_2d(sB + s * STAGE_BYTES + B_TILE_BYTES, &map_t, TC_KB, row, bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i % TC_STAGES, b = i & 1;
+                if (i >= 2) mbar_wait(bar_tempty + 8 * b, ((i >> 1) - 1) & 1);
+                mbar_wait(bar_full + 8 * s, (i / TC_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned d_tmem = tmem_base + (unsigned)(b * TC_N);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t da = umma_desc_sw128(sA + kb * A_TILE_BYTES), db = umma_desc_sw128(sB + s * STAGE_BYTES + kb * B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)    // 32 bytes of K per instruction: advance the start address inside the swizzle atom
+                        umma_i8(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(bar_empty + 8 * s);     // smem stage free once these MMAs have read it
+                umma_commit(bar_tfull + 8 * b);     // accumulator ready
+            }
+        }
+    } else {
+        // epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 = query rows; one row per thread, all columns of the tile
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        unsigned k0 = SENT, k1 = SENT;
+        int thr = -100000;                          // dot product of the current second best: only a strictly larger one can enter
+        for (int i = 0; i < n_tiles; ++i) {
+            const int b = i & 1;
+            mbar_wait(bar_tfull + 8 * b, (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int col_base = t_begin + i * TC_N;
+#pragma unroll 1
+            for (int c = 0; c < TC_N / 32; ++c) {
+                int v[32];
+                tmem_ld32(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(b * TC_N + c * 32), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int m = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = max(m, v[j]);
+                if (m > thr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int idx = col_base + c * 32 + j;
+                        if (v[j] > thr && idx < t_end) {
+                            top2_update(k0, k1, ((unsigned)((256 - v[j]) >> 1) << IDX_BITS) | (unsigned)idx);
+                            if (k1 != SENT) thr = 256 - 2 * (int)(k1 >> IDX_BITS);
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        if (q0 + row < nq) {
+            unsigned* o = part + ((size_t)blockIdx.y * nq + q0 + row) * 2;
+            o[0] = k0; o[1] = k1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) { __syncwarp(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory"); }
+}
+
+__global__ void k_merge(const unsigned* part, int nq, int n_splits, int* idx, int* dist) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned k0 = SENT, k1 = SENT;
+    for (int s = 0; s < n_splits; ++s) { const unsigned* p = part + ((size_t)s * nq + q) * 2; top2_update(k0, k1, p[0]); top2_update(k0, k1, p[1]); }
+    const unsigned mask = (1u << IDX_BITS) - 1;
+    idx[2 * q] = k0 == SENT ? -1 : (int)(k0 & mask); dist[2 * q] = k0 == SENT ? 0x7fffffff : (int)(k0 >> IDX_BITS);
+    idx[2 * q + 1] = k1 == SENT ? -1 : (int)(k1 & mask); dist[2 * q + 1] = k1 == SENT ? 0x7fffffff : (int)(k1 >> IDX_BITS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_map(CUtensorMap* m, const int8_t* base, int rows, int box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[2] = {256, (cuuint64_t)rows}, strides[1] = {256};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Runner {
+    int8_t *eq = nullptr, *et = nullptr; unsigned* part = nullptr; int *idx = nullptr, *dist = nullptr;
+    uint8_t *dq = nullptr, *dt = nullptr;
+    int nq, nt, n_splits, per_split;
+    void setup(const std::vector<uint8_t>& q, const std::vector<uint8_t>& t, int nq_, int nt_, int splits_hint) {
+        nq = nq_; nt = nt_;
+        CK(cudaMalloc(&dq, (size_t)nq * 32)); CK(cudaMalloc(&dt, (size_t)nt * 32));
+        CK(cudaMemcpy(dq, q.data(), (size_t)nq * 32, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, t.data(), (size_t)nt * 32, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&eq, (size_t)nq * 256)); CK(cudaMalloc(&et, (size_t)nt * 256));
+        const int q_tiles = (nq + TC_M - 1) / TC_M, t_tiles = (nt + TC_N - 1) / TC_N;
+        n_splits = splits_hint > 0 ? splits_hint : std::max(1, std::min((148 + q_tiles - 1) / q_tiles, t_tiles));
+        per_split = ((t_tiles + n_splits - 1) / n_splits) * TC_N;
+        n_splits = (nt + per_split - 1) / per_split;
+        CK(cudaMalloc(&part, (size_t)n_splits * nq * 8)); CK(cudaMalloc(&idx, (size_t)nq * 8)); CK(cudaMalloc(&dist, (size_t)nq * 8));
+        CK(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    }
+    void run(bool expand_t) {
+        k_expand_pm1<<<(nq * 8 + 255) / 256, 256>>>(dq, nq, eq);
+        if (expand_t) k_expand_pm1<<<(nt * 8 + 255) / 256, 256>>>(dt, nt, et);
+        CUtensorMap mq, mt;
+        if (!make_map(&mq, eq, nq, TC_M) || !make_map(&mt, et, nt, TC_N)) { printf("tensor map encode failed\n"); exit(1); }
+        k_knn2_tc<<<dim3((nq + TC_M - 1) / TC_M, n_splits), TC_THREADS, SMEM_BYTES>>>(mq, mt, nq, nt, per_split, part);
+        k_merge<<<(nq + 255) / 256, 256>>>(part, nq, n_splits, idx, dist);
+    }
+    void release() { cudaFree(dq); cudaFree(dt); cudaFree(eq); cudaFree(et); cudaFree(part); cudaFree(idx); cudaFree(dist); }
+};
+
+static int check(int nq, int nt, bool low, int splits_hint, unsigned seed) {
+    std::vector<uint8_t> q((size_t)nq * 32), t((size_t)nt * 32);
+    srand(seed);
+    for (auto& b : q) b = (uint8_t)(low ? rand() & 3 : rand());
+    for (auto& b : t) b = (uint8_t)(low ? rand() & 3 : rand());
+    Runner r; r.setup(q, t, nq, nt, splits_hint);
+    r.run(true);
+    CK(cudaDeviceSynchronize());
+    std::vector<int> idx((size_t)nq * 2), dist((size_t)nq * 2);
+    CK(cudaMemcpy(idx.data(), r.idx, idx.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(dist.data(), r.dist, dist.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (int i = 0; i < nq; ++i) {
+        unsigned k0 = SENT, k1 = SENT;
+        for (int j = 0; j < nt; ++j) {
+            int d = 0;
+            for (int w = 0; w < 4; ++w) d += __builtin_popcountll(((const uint64_t*)&q[(size_t)i * 32])[w] ^ ((const uint64_t*)&t[(size_t)j * 32])[w]);
+            top2_update(k0, k1, ((unsigned)d << IDX_BITS) | (unsigned)j);
+        }
+        const int e[4] = {(int)(k0 & ((1u << IDX_BITS) - 1)), (int)(k0 >> IDX_BITS), k1 == SENT ? -1 : (int)(k1 & ((1u << IDX_BITS) - 1)), k1 == SENT ? 0x7fffffff : (int)(k1 >> IDX_BITS)};
+        if (idx[2 * i] != e[0] || dist[2 * i] != e[1] || idx[2 * i + 1] != e[2] || dist[2 * i + 1] != e[3]) {
+            if (bad < 5) printf("  q %d: got (%d,%d) (%d,%d) want (%d,%d) (%d,%d)\n", i, idx[2 * i], dist[2 * i], idx[2 * i + 1], dist[2 * i + 1], e[0], e[1], e[2], e[3]);
+            ++bad;
+        }
+    }
+    printf("check nq %d nt %d low %d splits %d (per_split %d): %d mismatches\n", nq, nt, (int)low, r.n_splits, r.per_split, bad);
+    r.release();
+    return bad;
+}
+
+static void timeit(int nq, int nt, int reps) {
+    std::vector<uint8_t> q((size_t)nq * 32), t((size_t)nt * 32);
+    srand(5);
+    for (auto& b : q) b = (uint8_t)rand();
+    for (auto& b : t) b = (uint8_t)rand();
+    Runner r; r.setup(q, t, nq, nt, 0);
+    r.run(true); CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int pass = 0; pass < 2; ++pass) {
+        cudaEventRecord(e0);
+        for (int i = 0; i < reps; ++i) r.run(pass == 0);
+        cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+        printf("time nq %d nt %d (%s): %.3f ms, %.3e pairs/s, %.1f TOP/s int8\n", nq, nt, pass == 0 ? "incl. train expansion" : "train pre-expanded", ms,
+               (double)nq * nt / (ms * 1e-3), (double)nq * nt * 512 / (ms * 1e-3) / 1e12);
+    }
+    r.release();
+}
+
+int main(int argc, char** argv) {
+    int bad = 0;
+    bad += check(128, 256, false, 1, 1);
+    bad += check(300, 1000, false, 0, 2);
+    bad += check(257, 4100, true, 0, 3);
+    bad += check(2000, 2003, false, 0, 4);
+    bad += check(1, 2, false, 0, 5);
+    bad += check(1000, 5000, true, 1, 6);
+    printf("total mismatching checks: %d\n", bad);
+    if (argc > 1 && !strcmp(argv[1], "--time")) {
+        timeit(2000, 2000, 50);
+        timeit(5000, 5000, 50);
+        timeit(131072, 1 << 20, 2);
+    }
+    return bad != 0;
+}
