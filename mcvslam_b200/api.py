@@ -28,7 +28,7 @@ EXPORTS = [
     "mcv_orb_max_keypoints", "mcv_orb_max_keypoints_for", "mcv_rig_max_keypoints_for", "mcv_orb_extract", "mcv_orb_extract_batch", "mcv_orb_download_level", "mcv_orb_level_device",
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
-    "mcv_knn2_bf_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
+    "mcv_knn2_bf_device", "mcv_knn2_pairs_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
     "mcv_rig_set_chunk_frames", "mcv_rig_process", "mcv_rig_set_input_channels", "mcv_orb_set_input_channels", "mcv_rig_process_async", "mcv_rig_submit", "mcv_rig_wait", "mcv_rig_join", "mcv_rig_sync", "mcv_rig_last_launches", "mcv_rig_set_profiling",
     "mcv_rig_stage_ms", "mcv_stereo_match",
     "mcv_project_match", "mcv_fuse_match", "mcv_wnd_track", "mcv_distinctive_descriptors", "mcv_lk_track", "mcv_lk_track_batch", "mcv_kl_track", "mcv_voc_create", "mcv_voc_destroy", "mcv_bow_transform", "mcv_debug_sincosf", "mcv_debug_fast_atan2", "mcv_debug_level_keypoints",
@@ -85,6 +85,7 @@ def lib():
         L.mcv_filter_fmatrix.argtypes = [vp, C.POINTER(i), vp, i, vp, i, vp, vp, i]
         L.mcv_dbow_match.argtypes = [vp, i, vp, vp, vp, i, vp, i, vp, vp, vp, i, vp, C.POINTER(i)]
         L.mcv_knn2_bf_device.argtypes = [vp, i, vp, i, i, vp, vp, vp]
+        L.mcv_knn2_pairs_device.argtypes = [vp, vp, i, i, vp, vp, i, vp, vp, vp]
         L.mcv_rig_create.argtypes = [C.POINTER(RigParams), i, vp, C.POINTER(vp)]
         L.mcv_rig_destroy.argtypes = [vp]
         L.mcv_rig_destroy.restype = None

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 SO = os.path.join(HERE, "libmcv_b200.so")
 SOURCES = ["engine.cu", "image_kernels.cu", "fast_kernels.cu", "octree_kernels.cu", "describe_kernels.cu", "stereo_kernels.cu", "host_filters.cu",
-           "match_kernels.cu", "lk_kernels.cu"]
+           "match_kernels.cu", "match_tc_kernels.cu", "lk_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # --fmad=false: the parity-critical float code uses explicit _rn intrinsics; this is the safety net for everything else.
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-Xcompiler", "-fPIC",

@@ -696,6 +696,21 @@ mcv_status mcv_knn2_bf_device(const uint8_t* d_q, int nq, const uint8_t* d_t, in
     return MCV_OK;
 }
 
+mcv_status mcv_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int n_images, int cap, const int32_t* d_pair_q, const int32_t* d_pair_t,
+                                 int n_pairs, int32_t* d_idx, int32_t* d_dist, void* stream) {
+    if (n_images < 1 || cap < 2 || cap > (1 << 22) || n_pairs < 0 || !d_desc || !d_counts || (n_pairs > 0 && (!d_pair_q || !d_pair_t || !d_idx || !d_dist)))
+        return MCV_ERR_BAD_ARG;
+    if (n_pairs == 0) return MCV_OK;
+    void* d_scratch = nullptr;   // stream-ordered on the CALLER's stream, like mcv_knn2_bf_device
+    MCV_CUDA(cudaMallocAsync(&d_scratch, knn2_tc_scratch_bytes(n_images * cap, 0, cap, cap, n_pairs), (cudaStream_t)stream));
+    const int rc = launch_knn2_tc(d_desc, cap, d_desc, cap, 0, d_idx, d_dist, d_scratch, n_images, d_counts, d_pair_q, d_pair_t, n_pairs, (cudaStream_t)stream);
+    const cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(d_scratch, (cudaStream_t)stream);
+    if (rc < 0) { set_error("knn2_pairs_device: tensor map encoding failed"); return MCV_ERR_CUDA; }
+    MCV_CUDA(le);
+    return MCV_OK;
+}
+
 mcv_status mcv_project_match(const mcv_keypoint* kps, const uint8_t* desc, int n, int w, int hgt, const float* scale_factors, int nlevels,
                              const float* Rcw, const float* tcw, const float* intr, const float* mp_xyz, const uint8_t* mp_desc,
                              const int32_t* mp_level, int n_mp, float r_threshold, int32_t* out_idx, int32_t* out_dist, int* n_matched) {

@@ -108,6 +108,11 @@ int launch_octree_standalone(const uint32_t* d_pts, int n, int w_box, int h_box,
 int octree_debug_clocks(long long out[8]);
 
 // matching
+// tensor-core brute force (match_tc_kernels.cu): single problem (n_images == 0) or pairs of images of one descriptor array
+bool knn2_tc_usable(int nq, int nt);
+size_t knn2_tc_scratch_bytes(int nq_rows, int nt_rows, int nq, int nt, int n_pairs);
+int launch_knn2_tc(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, void* d_scratch,
+                   int n_images, const int32_t* d_counts, const int32_t* d_pair_q, const int32_t* d_pair_t, int n_pairs, cudaStream_t s);
 size_t knn2_bf_part_bytes(int nq, int nt);   // partial-key scratch one call needs (owned by the caller: the launchers are stateless)
 int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, unsigned* d_part,
                    cudaStream_t s);

@@ -83,18 +83,28 @@ static void bf_splits(int nq, int nt, int& q_blocks, int& n_splits, int& per_spl
     n_splits = nt > 0 ? (nt + per_split - 1) / per_split : 1;
 }
 
-// bytes of partial-key scratch one call needs; the CALLER owns it (per thread / per stream), the launcher keeps no state
+// MCV_KNN_POPC=1 keeps every brute-force call on the integer-pipe kernel (comparison runs, ncu of k_knn2_bf)
+static bool force_popc() {
+    static const int v = [] { const char* e = getenv("MCV_KNN_POPC"); return e && atoi(e) != 0 ? 1 : 0; }();
+    return v != 0;
+}
+
+// bytes of scratch one call needs; the CALLER owns it (per thread / per stream), the launchers keep no state
 size_t knn2_bf_part_bytes(int nq, int nt) {
     if (nq <= 0) return 0;
+    if (!force_popc() && knn2_tc_usable(nq, nt)) return knn2_tc_scratch_bytes(nq, nt, nq, nt, 1);
     int q_blocks, n_splits, per_split;
     bf_splits(nq, nt, q_blocks, n_splits, per_split);
     return (size_t)n_splits * nq * 2 * sizeof(unsigned);
 }
 
+// Brute-force 2-NN: tensor-core path (match_tc_kernels.cu) from 2^20 pairs up, integer-pipe kernel below that.
 int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, unsigned* d_part,
                    cudaStream_t s) {
     if (nq <= 0) return 0;
     if (nt > (1 << BF_IDX_BITS) || !d_part) return -1;
+    if (!force_popc() && knn2_tc_usable(nq, nt))
+        return launch_knn2_tc(d_q, nq, d_t, nt, train_offset, d_idx, d_dist, d_part, 0, nullptr, nullptr, nullptr, 1, s);
     int q_blocks, n_splits, per_split;
     bf_splits(nq, nt, q_blocks, n_splits, per_split);
     k_knn2_bf<<<dim3(q_blocks, n_splits), BF_THREADS, 0, s>>>(d_q, nq, d_t, nt, per_split, d_part);

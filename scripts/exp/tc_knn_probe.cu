@@ -17,12 +17,20 @@
 constexpr int TC_M = 128;            // queries per CTA (UMMA M)
 constexpr int TC_N = 256;            // train rows per tile (UMMA N)
 constexpr int TC_KB = 128;           // bytes of K per shared-memory tile (one 128-byte swizzle atom row)
-constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+#ifndef TC_STAGES_N
+#define TC_STAGES_N 2
+#endif
+#ifndef TC_EPI_WARPS
+#define TC_EPI_WARPS 8
+#endif
+constexpr int TC_STAGES = TC_STAGES_N;
+constexpr int EPI_WARPS = TC_EPI_WARPS;                    // 4: one warp per TMEM lane quarter; 8: two per quarter, half of a tile's columns each
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..: epilogue
+constexpr int EPI_COLS = TC_N / (EPI_WARPS / 4);           // columns of a tile one epilogue warp scans
 constexpr unsigned A_TILE_BYTES = TC_M * TC_KB;           // 16 KB per K half
 constexpr unsigned B_TILE_BYTES = TC_N * TC_KB;           // 32 KB per K half
 constexpr unsigned STAGE_BYTES = 2 * B_TILE_BYTES;        // 64 KB
-constexpr unsigned SMEM_BYTES = 2 * A_TILE_BYTES + TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr unsigned SMEM_BYTES = 2 * A_TILE_BYTES + TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*second-half keys*/;
 constexpr int IDX_BITS = 22;
 constexpr unsigned SENT = 0xffffffffu;
 
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
     if (threadIdx.x == 0) {
         mbar_init(bar_a, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: all 512 columns (two 128 x 256 s32 accumulators)
@@ -157,40 +165,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
             }
         }
     } else {
-        // epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 = query rows; one row per thread, all columns of the tile
-        const int quarter = warp & 3;
+        // epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 = query rows; one row per thread, EPI_COLS columns of every tile
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         unsigned k0 = SENT, k1 = SENT;
         int thr = -100000;                          // dot product of the current second best: only a strictly larger one can enter
+        auto scan = [&](const int (&v)[32], int idx0) {
+            int m = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = max(m, v[j]);
+            if (m > thr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (v[j] > thr && idx0 + j < t_end) {
+                        top2_update(k0, k1, ((unsigned)((256 - v[j]) >> 1) << IDX_BITS) | (unsigned)(idx0 + j));
+                        if (k1 != SENT) thr = 256 - 2 * (int)(k1 >> IDX_BITS);
+                    }
+                }
+            }
+        };
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
             mbar_wait(bar_tfull + 8 * b, (i >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int col_base = t_begin + i * TC_N;
+            const int col0 = half * EPI_COLS;
+            const int idx_base = t_begin + i * TC_N + col0;
+            const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(b * TC_N + col0);
+            int va[32], vb[32];
+            tmem_ld32(taddr, va);
 #pragma unroll 1
-            for (int c = 0; c < TC_N / 32; ++c) {
-                int v[32];
-                tmem_ld32(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(b * TC_N + c * 32), v);
+            for (int c = 0; c < EPI_COLS / 32; c += 2) {       // two chunks per round: the next load is in flight while one is scanned
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                int m = v[0];
-#pragma unroll
-                for (int j = 1; j < 32; ++j) m = max(m, v[j]);
-                if (m > thr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int idx = col_base + c * 32 + j;
-                        if (v[j] > thr && idx < t_end) {
-                            top2_update(k0, k1, ((unsigned)((256 - v[j]) >> 1) << IDX_BITS) | (unsigned)idx);
-                            if (k1 != SENT) thr = 256 - 2 * (int)(k1 >> IDX_BITS);
-                        }
-                    }
-                }
+                tmem_ld32(taddr + (unsigned)((c + 1) * 32), vb);
+                scan(va, idx_base + c * 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 2 < EPI_COLS / 32) tmem_ld32(taddr + (unsigned)((c + 2) * 32), va);
+                scan(vb, idx_base + (c + 1) * 32);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
         }
-        if (q0 + row < nq) {
+        unsigned* sk = reinterpret_cast<unsigned*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));   // [128][2] keys of the second column half
+        if (half == 1) { sk[2 * row] = k0; sk[2 * row + 1] = k1; }
+        if (EPI_WARPS == 8) asm volatile("bar.sync 1, 256;" ::: "memory");                                  // epilogue warps only
+        if (half == 0 && q0 + row < nq) {
+            if (EPI_WARPS == 8) { top2_update(k0, k1, sk[2 * row]); top2_update(k0, k1, sk[2 * row + 1]); }
             unsigned* o = part + ((size_t)blockIdx.y * nq + q0 + row) * 2;
             o[0] = k0; o[1] = k1;
         }

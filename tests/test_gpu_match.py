@@ -263,3 +263,49 @@ def test_distinctive_descriptors_ties(api, oracle):
     assert bi.tolist() == [0, 0] and bm.tolist() == [0, 0]
     bi, bm, od = api.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), [0])
     assert len(bi) == 0
+
+
+@pytest.mark.parametrize("nq,nt,low", [(128, 8193, False), (129, 8192, True), (2003, 2000, False), (5000, 5001, True), (1000, 70000, True),
+                                       (20000, 300, False), (257, 4100, True), (1, 1 << 20, False), (40000, 40, True)])
+def test_knn2_tensor_core_path(api, oracle, nq, nt, low):
+    """Problems of >= 2^20 pairs run on tcgen05 (int8 GEMM of the +-1 expanded descriptors, match_tc_kernels.cu): tile edges
+    (M = 128 queries, N = 256 train rows per tile), the split + merge path (few query tiles, long train walk), tie-heavy sets."""
+    assert nq * nt >= 1 << 20
+    q = synth.descriptors(nq, 21, low); t = synth.descriptors(nt, 22, low)
+    if low:
+        q[:, 2:] = 0; t[:, 2:] = 0          # 16 significant bits: most nearest neighbours tie, the index order decides
+    res = api.Matcher.KnnMatch(q, t)
+    if nq * nt <= 400_000_000:
+        ref, k = oracle.knn2_bf(q, t)
+    else:
+        s, ref = oracle.bench_knn2(q, t, 8); k = 2
+    _eq_dm(res.knn, ref[:, :k])
+
+
+def test_knn2_pairs_device(api, oracle):
+    """mcv_knn2_pairs_device: BF 2-NN between images of one device-resident descriptor array (configs[3]: consecutive frames),
+    ragged per-image counts incl. an empty image and a full one; every pair == the oracle on the two descriptor sets."""
+    import torch
+    rng = np.random.default_rng(31)
+    n_img, cap = 7, 1500
+    counts = np.array([1500, 1203, 0, 1, 777, 1499, 300], np.int32)
+    desc = rng.integers(0, 256, (n_img, cap, 32), dtype=np.uint8)
+    desc[5, :, 2:] = 0; desc[6, :, 2:] = 0                                 # tie-heavy pair
+    pq = np.array([0, 1, 2, 3, 4, 5, 6, 0, 5], np.int32); pt = np.array([1, 2, 3, 4, 5, 6, 0, 0, 5], np.int32)
+    dev = torch.device("cuda", 0)
+    d_desc = torch.from_numpy(desc).to(dev); d_cnt = torch.from_numpy(counts).to(dev)
+    d_pq = torch.from_numpy(pq).to(dev); d_pt = torch.from_numpy(pt).to(dev)
+    idx = torch.full((len(pq), cap, 2), -7, dtype=torch.int32, device=dev); dst = torch.full((len(pq), cap, 2), -7, dtype=torch.int32, device=dev)
+    api._check(api.lib().mcv_knn2_pairs_device(d_desc.data_ptr(), d_cnt.data_ptr(), n_img, cap, d_pq.data_ptr(), d_pt.data_ptr(), len(pq), idx.data_ptr(),
+                                               dst.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.synchronize()
+    idx = idx.cpu().numpy(); dst = dst.cpu().numpy()
+    for p in range(len(pq)):
+        nq, nt = counts[pq[p]], counts[pt[p]]
+        assert (idx[p, nq:] == -7).all()                                    # rows beyond the query image's count are untouched
+        if nq == 0:
+            continue
+        ref, k = oracle.knn2_bf(desc[pq[p], :nq], desc[pt[p], :nt])
+        assert np.array_equal(idx[p, :nq, :k], ref["trainIdx"][:, :k]), p
+        assert np.array_equal(dst[p, :nq, :k], ref["distance"][:, :k].astype(np.int32)), p
+        assert (idx[p, :nq, k:] == -1).all()
