@@ -85,8 +85,8 @@ static void bf_splits(int nq, int nt, int& q_blocks, int& n_splits, int& per_spl
 
 // MCV_KNN_POPC=1 keeps every brute-force call on the integer-pipe kernel (comparison runs, ncu of k_knn2_bf)
 static bool force_popc() {
-    static const int v = [] { const char* e = getenv("MCV_KNN_POPC"); return e && atoi(e) != 0 ? 1 : 0; }();
-    return v != 0;
+    const char* e = getenv("MCV_KNN_POPC");   // read per call: bench.py flips it between its two matching legs
+    return e && atoi(e) != 0;
 }
 
 // bytes of scratch one call needs; the CALLER owns it (per thread / per stream), the launchers keep no state
