@@ -21,6 +21,7 @@ constexpr int NUM_SMS = 148;
 constexpr int FS_ROWS = MCV_FS_ROWS;            // rows per FAST strip; FS_ROWS + 6 is a multiple of the kernel's 7-row register ring
 constexpr int OCT_S_BYTES = 2 * 2064;    // quadtree: bucket prefix sums per (image, level) task (<= 2048 buckets + 1, u16)
 constexpr int FS_SEG = 128 * FS_ROWS;  // list entries a strip owns: worst case every pixel of the strip scores
+constexpr int FS_EDGE_BYTES = (256 + 2 * FS_ROWS + 15) & ~15;   // per-strip edge record: scores on its first / last row and column (fast_kernels.cu)
 
 // Candidate / quadtree point: x (12 bits) | y (12 bits) << 12 | response (8 bits) << 24, coordinates relative to BORDER.
 __host__ __device__ inline uint32_t pack_pt(int x, int y, int r) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)r << 24); }
@@ -86,7 +87,7 @@ void set_error(const std::string& s);
 int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t src_image_stride, int src_channels, uint8_t* d_pyr,
                    const int* d_tabs, int n_images, cudaStream_t s);
 int launch_blur(const Plan& P, const uint8_t* d_pyr, uint8_t* d_blur, int n_images, cudaStream_t s);
-int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
+int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_edges, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
                       uint32_t* d_cell_pts, int* d_cell_cnt, int* d_fallback, int n_images, cudaStream_t s, cudaEvent_t after_score = nullptr);
 int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_cnt, uint32_t* d_arena_a, uint32_t* d_arena_b,
                   uint16_t* d_oct_idx, uint32_t* d_out_pts, int* d_out_cnt, int n_images, cudaStream_t s);

@@ -4,7 +4,7 @@
 // reference calls cv::FAST(cell image, iniThFAST, nonmax=true) and, if that returns nothing, again with minThFAST.
 // Four kernels (k_fast_score, k_nms_sparse, k_cell_order; the quadtree kernel consumes the result):
 //
-//  k_fast_score — threshold-free FAST score map S of every level (u8, 0 where S < minThFAST). S = max over the 16 arcs of 9
+//  k_fast_score — threshold-free FAST score S of every pixel of every level. S = max over the 16 arcs of 9
 //    contiguous circle pixels of min(v - p) resp. min(p - v), minus 1 (OpenCV cornerScore<16>); a pixel is a corner at
 //    threshold T iff S >= T. Register-marching stencil, no shared-memory tile: a warp owns a 128-px strip (lane = one aligned
 //    4-px word) and marches down the rows keeping the last 7 row words in a register ring. Per row: one coalesced 32-bit
@@ -13,13 +13,17 @@
 //    pushed to a per-warp queue and scored 32 at a time (one lane per pixel) so the expensive arc min/max network never runs
 //    divergent.
 //
-//    Every pixel with S >= minThFAST (6-7 % of the pixels) is also appended to the strip's own list segment (the warp owns
-//    the strip, so the fill count is a register: no atomics), so that nothing downstream has to scan the dense map again.
+//    There is NO dense score map (round 1 wrote one — 97 % zeros — and the NMS read it back: 0.8 GB of DRAM traffic per
+//    128-frame step). Every pixel with S >= threshold (3-7 % of the pixels) is appended to the strip's own list segment (the
+//    warp owns the strip, so the fill count is a register: no atomics); the scores on the strip's four BORDER lines (first /
+//    last row, first / last column) are also written to a 336-byte edge record per strip, which is all a neighbouring
+//    strip's NMS needs to know about this one.
 //
-//  k_nms_sparse — one warp per strip: stages the strip's window of the dense map (+1 px ring) in shared memory with
-//    coalesced word loads, then runs one lane per listed pixel: strict 8-neighbour maximum test, where neighbours outside
-//    the pixel's own cell (detection rims of adjacent cells tile the level without overlap) count as 0 — exactly what the
-//    per-cell cv::FAST sees. Survivors are appended (atomicAdd, unordered) to their cell's slot array.
+//  k_nms_sparse — one warp per strip: rebuilds the strip's score tile (+1 px ring) in shared memory from the strip's own
+//    list (scatter) and the facing edge lines of its eight neighbours' records, then runs one lane per listed pixel: strict
+//    8-neighbour maximum test, where neighbours outside the pixel's own cell (detection rims of adjacent cells tile the level
+//    without overlap) count as 0 — exactly what the per-cell cv::FAST sees. Survivors are appended (atomicAdd, unordered) to
+//    their cell's slot array.
 //
 //  k_cell_order — one warp per cell: applies the ini -> min threshold fallback ("any maximum with S >= ini ? S >= ini :
 //    S >= min" — equivalent to re-running FAST at minThFAST) and sorts the survivors by (y, x), i.e. the
@@ -77,13 +81,23 @@ __device__ __forceinline__ unsigned gt4(unsigned a, unsigned add_lo7, bool add_h
     return add_hi ? (a | s) : (a & s);                  // carry out of bit 7 of a + add, add's bit 7 being a constant
 }
 
-// Scores queued pixels 32 at a time (one lane each) while at least `keep_below` + 1 are queued. Pixels with score >= Tm go
-// to the dense map and, packed x | y << 12 | score << 24 (level coordinates), to the strip's list. Returns
-// (list fill << 8) | queue fill.
-__device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_below, const uint8_t* src, uint8_t* dst, int pitch, int Tm,
-                                        unsigned* __restrict__ list, int ln) {
+// Edge record of a strip: the scores on its first / last row (128 bytes each, by strip column) and first / last column
+// (FS_ROWS bytes each, by strip row); zero where nothing scored.
+constexpr int FE_TOP = 0, FE_BOT = 128, FE_LEFT = 256, FE_RIGHT = 256 + FS_ROWS;
+static_assert(FS_EDGE_BYTES >= 256 + 2 * FS_ROWS && FS_EDGE_BYTES % 16 == 0, "edge record layout");
+
+// Scores queued pixels 32 at a time (one lane each) while at least `keep_below` + 1 are queued. Pixels with score >= Tm go,
+// packed x | y << 12 | score << 24 (level coordinates), to the strip's list, and to the strip's edge record when they lie on
+// one of its border lines (sxy = the strip's first column | first row << 16; its last row follows from the level's y_hi).
+// Returns (list fill << 8) | queue fill.
+__device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_below, const uint8_t* src, uint8_t* __restrict__ edges, const unsigned* nz_base,
+                                        int pitch, int Tm, unsigned* __restrict__ list, int ln, unsigned sxy, int y_hi) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
+    const int sx0 = (int)(sxy & 0xffffu), sy0 = (int)(sxy >> 16), y_last = min(sy0 + FS_ROWS, y_hi) - 1;
+    // the strip's edge record, located from its list segment (both are indexed by image * strips + strip): keeps the caller's
+    // marching loop free of one more live pointer
+    uint8_t* edge = edges + (size_t)((list - nz_base) / FS_SEG) * FS_EDGE_BYTES;
     __syncwarp();
     while (qn > keep_below) {
         const int n = min(qn, 32);
@@ -93,7 +107,13 @@ __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_belo
             const unsigned e = q[qn - n + lane];
             const int x = (int)(e & 0xffffu), y = (int)(e >> 16);
             const int sc = fast_score16(src + y * pitch + x, pitch);
-            if (sc >= Tm) { dst[y * pitch + x] = (uint8_t)sc; hit = true; packed = pack_pt(x, y, sc); }
+            if (sc >= Tm) {
+                hit = true; packed = pack_pt(x, y, sc);
+                if (y == sy0) edge[FE_TOP + x - sx0] = (uint8_t)sc;
+                if (y == y_last) edge[FE_BOT + x - sx0] = (uint8_t)sc;
+                if (x == sx0) edge[FE_LEFT + y - sy0] = (uint8_t)sc;
+                if (x == sx0 + 127) edge[FE_RIGHT + y - sy0] = (uint8_t)sc;
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (hit) list[ln + __popc(m & lt)] = packed;
@@ -104,7 +124,7 @@ __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_belo
     return (ln << 8) | qn;
 }
 
-__global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score,
+__global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ edges,
                                                                unsigned* __restrict__ nz_list, int* __restrict__ nz_cnt,
                                                                const __grid_constant__ Plan P, const __grid_constant__ StripTable T, int Tm) {
     __shared__ unsigned s_q[FS_WARPS][FS_QCAP];
@@ -119,7 +139,8 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
     const int y0 = EDGE_THRESHOLD + (t / T.strips_x[level]) * FS_ROWS;
     const int w = g.w, h = g.h, pitch = g.pitch;
     const uint8_t* src = pyr + (size_t)img * P.pyr_bytes + g.img_off;
-    uint8_t* dst = score + (size_t)img * P.pyr_bytes + g.img_off;
+    if (lane < FS_EDGE_BYTES / 16)
+        reinterpret_cast<uint4*>(edges + ((size_t)img * P.n_fast_strips + sid) * FS_EDGE_BYTES)[lane] = make_uint4(0u, 0u, 0u, 0u);   // ordered before the scores by drain_queue's __syncwarp
     unsigned* list = nz_list + ((size_t)img * P.n_fast_strips + sid) * FS_SEG;   // this strip's own segment
     int ln = 0;                                             // its fill (warp-uniform)
     const int x_lo = EDGE_THRESHOLD, x_hi = w - EDGE_THRESHOLD, y_hi = h - EDGE_THRESHOLD;   // detection region [19, n-19)
@@ -146,7 +167,6 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
     }
     const uint8_t* lp = src + (size_t)(y0 + 4) * pitch + x0;              // input row y0 - 3 + (r + 7) for r = 0
     const uint8_t* lpe = lp + (ex - x0);
-    uint8_t* sp = dst + (size_t)(y0 - 6) * pitch + x0;                     // output row y0 + r - 6 for r = 0
 #pragma unroll 1
     for (int rb = 0; rb < FS_ROWS + 6; rb += 7) {
         // candidates of the block's 7 rows: row j's four pass bits (bit 7 of each byte) shifted right by j never collide
@@ -169,8 +189,6 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
             const bool row_ok = r >= 6 && r < FS_ROWS + 6 && y < y_hi;   // warp-uniform; every row belongs to exactly one strip
                                                                          // (a pixel listed twice would survive NMS twice)
             const unsigned pass = row_ok ? ((mt | mb) & (ml | mr) & colmask) : 0u;
-            if (row_ok && colmask) *reinterpret_cast<unsigned*>(sp) = 0u;   // zero first; scores land later
-            sp += pitch;
             acc |= pass >> j;
         }
         if (__any_sync(0xffffffffu, acc != 0u)) {
@@ -187,10 +205,10 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
                 acc &= acc - 1u;
                 q[pos++] = (unsigned)(x0 + (b >> 3)) | ((unsigned)(yb - (b & 7)) << 16);
             }
-            if (qn >= 32) { const int r2 = drain_queue(q, qn, 31, src, dst, pitch, Tm, list, ln); qn = r2 & 0xff; ln = r2 >> 8; }
+            if (qn >= 32) { const int r2 = drain_queue(q, qn, 31, src, edges, nz_list, pitch, Tm, list, ln, (unsigned)(x0 - lane * 4) | ((unsigned)y0 << 16), y_hi); qn = r2 & 0xff; ln = r2 >> 8; }
         }
     }
-    ln = drain_queue(q, qn, 0, src, dst, pitch, Tm, list, ln) >> 8;
+    ln = drain_queue(q, qn, 0, src, edges, nz_list, pitch, Tm, list, ln, (unsigned)(x0 - lane * 4) | ((unsigned)y0 << 16), y_hi) >> 8;
     if (lane == 0) nz_cnt[(size_t)img * P.n_fast_strips + sid] = ln;
 }
 
@@ -198,19 +216,15 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
 // sparse NMS: one warp per strip (same strip table as k_fast_score).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int NMS_WARPS = 4;
-constexpr int NMS_TP = 128 + 32;                // tile pitch in bytes: the strip's 128 px + 16 on either side (TMA boxes start 16-byte aligned)
+constexpr int NMS_TP = 144;                     // tile pitch in bytes: strip column k at byte 4 + k, ring columns at bytes 3 and 132
 constexpr int NMS_TR = FS_ROWS + 2;             // tile rows: the strip's rows + one above and below
 constexpr int NMS_TILE_BYTES = NMS_TR * NMS_TP;
-constexpr int NMS_TILE_STRIDE = (NMS_TILE_BYTES + 127) & ~127;
 
-struct LevelMaps { CUtensorMap m[MAX_LEVELS]; };   // per level: (pitch, h, n_images) u8 view of the score map, box NMS_TP x NMS_TR
-
-__global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const __grid_constant__ LevelMaps maps, const unsigned* __restrict__ nz_list,
+__global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __restrict__ edges, const unsigned* __restrict__ nz_list,
                                                                const int* __restrict__ nz_cnt, uint32_t* __restrict__ cell_raw,
                                                                int* __restrict__ cell_cnt, const __grid_constant__ Plan P,
                                                                const __grid_constant__ StripTable T) {
-    __shared__ __align__(128) uint8_t s_tile[NMS_WARPS][NMS_TILE_STRIDE];
-    __shared__ __align__(8) unsigned long long s_mbar[NMS_WARPS];
+    __shared__ __align__(16) uint8_t s_tile[NMS_WARPS][NMS_TILE_BYTES];
     const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sid = blockIdx.x * NMS_WARPS + warp;
     if (sid >= P.n_fast_strips) return;
@@ -220,32 +234,52 @@ __global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const __grid_cons
     while (level + 1 < P.n_levels && sid >= T.first[level + 1]) ++level;
     const LevelGeom& g = P.lv[level];
     const int t = sid - T.first[level];
-    const int tx0 = BORDER + (t % T.strips_x[level]) * 128 - 16;          // level x of tile byte 0 (a multiple of 16)
-    const int ty0 = EDGE_THRESHOLD + (t / T.strips_x[level]) * FS_ROWS - 1;   // level y of tile row 0
-    // stage the window with ONE TMA box load: rows ty0 .. ty0 + NMS_TR - 1, bytes tx0 .. tx0 + 159; whatever lies outside the
-    // level comes back as zeros. Bytes outside the level's detection region may hold anything (the dense map is only written
-    // inside it); the test below never reads them. (The previous version staged the tile with 41 rounds of 32-bit loads per
-    // warp: 41 % of the kernel's instructions and nearly all of its long-scoreboard stalls.)
-    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar[warp]);
-    if (lane == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(mbar, NMS_TILE_BYTES);
-        tma_load_3d((unsigned)__cvta_generic_to_shared(s_tile[warp]), &maps.m[level], tx0, ty0, img, mbar);
+    const int nsx = T.strips_x[level], nsy = (T.first[level + 1] - T.first[level]) / nsx;
+    const int sxi = t % nsx, syi = t / nsx;
+    const int sx0 = BORDER + sxi * 128;                                   // level x of strip column 0 = tile byte 4
+    const int ty0 = EDGE_THRESHOLD + syi * FS_ROWS - 1;                   // level y of tile row 0
+    uint8_t* tile = s_tile[warp];
+    const unsigned* list = nz_list + ((size_t)img * P.n_fast_strips + sid) * FS_SEG;
+    // the first (up to) 128 list entries are fetched once and stay in registers for both passes
+    unsigned ent[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ent[u] = lane + 32 * u < count ? __ldg(list + lane + 32 * u) : 0u;
+    for (int i = lane; i < NMS_TILE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    // ring: the facing border lines of the eight neighbouring strips (their records are zero where nothing scored)
+    const uint8_t* E = edges + ((size_t)img * P.n_fast_strips + T.first[level]) * FS_EDGE_BYTES;
+    const bool up_ok = syi > 0, dn_ok = syi + 1 < nsy, lf_ok = sxi > 0, rt_ok = sxi + 1 < nsx;
+    if (up_ok) reinterpret_cast<unsigned*>(tile + 4)[lane] = __ldg(reinterpret_cast<const unsigned*>(E + (size_t)(t - nsx) * FS_EDGE_BYTES + FE_BOT) + lane);
+    if (dn_ok) reinterpret_cast<unsigned*>(tile + (NMS_TR - 1) * NMS_TP + 4)[lane] = __ldg(reinterpret_cast<const unsigned*>(E + (size_t)(t + nsx) * FS_EDGE_BYTES + FE_TOP) + lane);
+    for (int r = lane; r < FS_ROWS; r += 32) {
+        if (lf_ok) tile[(1 + r) * NMS_TP + 3] = __ldg(E + (size_t)(t - 1) * FS_EDGE_BYTES + FE_RIGHT + r);
+        if (rt_ok) tile[(1 + r) * NMS_TP + 132] = __ldg(E + (size_t)(t + 1) * FS_EDGE_BYTES + FE_LEFT + r);
+    }
+    if (lane == 0 && up_ok && lf_ok) tile[3] = __ldg(E + (size_t)(t - nsx - 1) * FS_EDGE_BYTES + FE_BOT + 127);
+    if (lane == 1 && up_ok && rt_ok) tile[132] = __ldg(E + (size_t)(t - nsx + 1) * FS_EDGE_BYTES + FE_BOT);
+    if (lane == 2 && dn_ok && lf_ok) tile[(NMS_TR - 1) * NMS_TP + 3] = __ldg(E + (size_t)(t + nsx - 1) * FS_EDGE_BYTES + FE_TOP + 127);
+    if (lane == 3 && dn_ok && rt_ok) tile[(NMS_TR - 1) * NMS_TP + 132] = __ldg(E + (size_t)(t + nsx + 1) * FS_EDGE_BYTES + FE_TOP);
+    // own pixels: scatter the list
+    for (int i0 = lane; i0 < count; i0 += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + 32 * u >= count) break;
+            const unsigned e = i0 < 128 ? ent[u] : __ldg(list + i0 + 32 * u);
+            tile[(pt_y(e) - ty0) * NMS_TP + (pt_x(e) - sx0 + 4)] = (uint8_t)pt_r(e);
+        }
     }
     __syncwarp();
-    mbar_wait(mbar, 0);
-    const uint8_t* tb = s_tile[warp];
-    const unsigned* list = nz_list + ((size_t)img * P.n_fast_strips + sid) * FS_SEG;
+    const uint8_t* tb = tile;
     int* cnts = cell_cnt + (size_t)img * P.cells_per_image + g.cell_base;
     uint32_t* cells = cell_raw + (size_t)img * P.cand_per_image + g.cand_off;
     const float inv_wc = 1.0f / (float)g.w_cell, inv_hc = 1.0f / (float)g.h_cell;
     const int x_hi = g.w - EDGE_THRESHOLD, y_hi = g.h - EDGE_THRESHOLD;
     constexpr int TP = NMS_TP;                                            // tile pitch in bytes
     for (int i0 = lane; i0 < count; i0 += 128) {
-        unsigned ent[4];
+        if (i0 >= 128) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) ent[u] = i0 + 32 * u < count ? __ldg(list + i0 + 32 * u) : 0u;   // four list loads in flight
+            for (int u = 0; u < 4; ++u) ent[u] = i0 + 32 * u < count ? __ldg(list + i0 + 32 * u) : 0u;   // four list loads in flight
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (i0 + 32 * u >= count) break;
@@ -256,7 +290,7 @@ __global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const __grid_cons
             const int cx = (int)(((float)ux + 0.5f) * inv_wc), cy = (int)(((float)uy + 0.5f) * inv_hc);
             const int rx = ux - cx * g.w_cell, ry = uy - cy * g.h_cell;
             const bool lf = rx > 0, rt = rx < g.w_cell - 1 && x + 1 < x_hi, up = ry > 0, dn = ry < g.h_cell - 1 && y + 1 < y_hi;
-            const uint8_t* c = tb + (y - ty0) * TP + (x - tx0);
+            const uint8_t* c = tb + (y - ty0) * TP + (x - sx0 + 4);
             // neighbours outside the cell's detection region count as 0
             const int l0 = lf ? 1 : 0, r0 = rt ? 1 : 0;
             int m = max(lf ? (int)c[-1] : 0, rt ? (int)c[1] : 0);
@@ -425,7 +459,7 @@ int fast_strip_table(const Plan& P, StripTable& T) {
     return n;
 }
 
-int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
+int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_edges, unsigned* d_nz_list, int* d_nz_cnt, uint32_t* d_cell_raw,
                       uint32_t* d_cell_pts, int* d_cell_cnt, int* d_fallback, int n_images, cudaStream_t s, cudaEvent_t after_score) {
     StripTable T{};
     const int n = fast_strip_table(P, T);
@@ -436,16 +470,11 @@ int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_score, uns
     cudaMemsetAsync(d_cell_cnt, 0, (size_t)n_images * P.cells_per_image * sizeof(int), s);
     if (two_pass) cudaMemsetAsync(d_fallback, 0, sizeof(int), s);
     if (n > 0)
-        k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_score, d_nz_list, d_nz_cnt, P, T,
+        k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_edges, d_nz_list, d_nz_cnt, P, T,
                                                                                              two_pass ? P.ini_th : P.min_th);
     if (after_score) cudaEventRecord(after_score, s);   // stage boundary for mcv_rig_stage_ms
-    if (n > 0) {
-        LevelMaps maps;
-        memset(&maps, 0, sizeof(maps));
-        for (int l = 0; l < P.n_levels; ++l)
-            if (!encode_level_map(&maps.m[l], d_score, P, l, n_images, NMS_TP, NMS_TR)) { set_error("cuTensorMapEncodeTiled failed for the NMS tiles"); return -1; }
-        k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(maps, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
-    }
+    if (n > 0)
+        k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(d_edges, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
     k_cell_order<<<dim3((P.cells_per_image + ORD_WARPS - 1) / ORD_WARPS, n_images), 32 * ORD_WARPS, 0, s>>>(d_cell_raw, d_cell_pts, d_cell_cnt, P,
                                                                                                           two_pass ? d_fallback : nullptr);
     if (!two_pass) return 3;

@@ -19,3 +19,16 @@ o, s, e = A.LkTrack(a, b, pts)
 print("lk", int(s.sum()))
 bi, bm, od = A.ComputeDistinctiveDescriptors(d[:50], [0, 20, 50])
 print("distinctive", bi)
+# matcher family: integer-pipe kernel (small), tensor-core kernel (>= 2^20 pairs, split + merge), batched image pairs
+q = synth.descriptors(300, 1); t = synth.descriptors(500, 2)
+print("knn popc", int(A.Matcher.KnnMatch(q, t).knn["distance"].min()))
+q = synth.descriptors(1000, 3); t = synth.descriptors(9000, 4)
+print("knn tensor", int(A.Matcher.KnnMatch(q, t).knn["distance"].min()))
+import torch
+dev = torch.device("cuda", 0)
+desc = torch.from_numpy(synth.descriptors(3 * 1100, 5).reshape(3, 1100, 32)).to(dev); cnt = torch.tensor([1100, 900, 1000], dtype=torch.int32, device=dev)
+pq = torch.tensor([0, 1], dtype=torch.int32, device=dev); pt = torch.tensor([1, 2], dtype=torch.int32, device=dev)
+idx = torch.zeros((2, 1100, 2), dtype=torch.int32, device=dev); dst = torch.zeros_like(idx)
+A._check(A.lib().mcv_knn2_pairs_device(desc.data_ptr(), cnt.data_ptr(), 3, 1100, pq.data_ptr(), pt.data_ptr(), 2, idx.data_ptr(), dst.data_ptr(), 0))
+torch.cuda.synchronize()
+print("knn pairs", int(dst[0, :1100, 0].min()))
