@@ -140,7 +140,7 @@ def time_knn2(A, torch, dev, stream, nq, nt, reps, seed=5, warm=1):
 def bench_matching(A, torch, dev, stream):
     """Brute-force Hamming 2-NN (mcv_knn2_bf_device) on device-resident random descriptors: configs[0]'s 2000 x 2000, configs[3]'s
     5000 x 5000 and one GPU's query shard of configs[4] (131072 of the 1M queries x all 1M train rows). Two legs: the shipped
-    path (tcgen05 int8 GEMM of the +-1 expanded descriptors from 2^20 pairs up; 512 int8 ops per pair against the dense int8
+    path (tcgen05 int8 GEMM of the +-1 expanded descriptors from 2^23 pairs up, the integer-pipe kernel below; 512 int8 ops per pair against the dense int8
     peak) and the integer-pipe kernel (MCV_KNN_POPC=1; 8 popc32 per pair against the live measured xor+popc peak)."""
     peak, _ = A.popc_peak(8192)
     out = {"unit": "descriptor pairs/s", "popc32_peak_per_s": peak, "popc_peak_source": "mcv_debug_popc_peak (8 independent xor+popc+add chains per thread, whole GPU)",
@@ -153,8 +153,11 @@ def bench_matching(A, torch, dev, stream):
         sec_p = time_knn2(A, torch, dev, stream, nq, nt, max(1, reps // 2), warm=3 if nq < 10000 else 1)
         os.environ["MCV_KNN_POPC"] = "0"
         pairs = float(nq) * nt / sec; pairs_p = float(nq) * nt / sec_p
-        out["cases"].append({"case": name, "ms": sec * 1e3, "pairs_per_s": pairs, "int8_tops": pairs * 512 / 1e12, "frac_of_int8_peak": pairs * 512 / 1e12 / I8_DENSE_TOPS,
-                             "kernel": "k_expand_pm1 + k_knn2_tc (tcgen05.mma kind::i8)",
+        tensor = nq * nt >= 1 << 23        # dispatch rule of launch_knn2_bf (match_tc_kernels.cu: knn2_tc_usable)
+        out["cases"].append({"case": name, "ms": sec * 1e3, "pairs_per_s": pairs, "int8_tops": pairs * 512 / 1e12 if tensor else None,
+                             "frac_of_int8_peak": pairs * 512 / 1e12 / I8_DENSE_TOPS if tensor else None,
+                             "frac_of_popc_peak": None if tensor else pairs * 8 / peak,
+                             "kernel": "k_expand_pm1 + k_knn2_tc (tcgen05.mma kind::i8)" if tensor else "k_knn2_bf + k_knn2_merge (integer pipe: below 2^23 pairs)",
                              "popc_path": {"ms": sec_p * 1e3, "pairs_per_s": pairs_p, "popc32_per_s": pairs_p * 8, "frac_of_popc_peak": pairs_p * 8 / peak,
                                            "kernel": "k_knn2_bf + k_knn2_merge"}, "speedup_vs_popc_path": sec_p / sec})
     return out

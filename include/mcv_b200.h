@@ -169,8 +169,9 @@ mcv_status mcv_knn2_bf_device(const uint8_t* d_q, int nq, const uint8_t* d_t, in
  * d_desc [n_images][cap][32] with d_counts [n_images] valid rows each (the layout mcv_orb_extract_batch / mcv_rig_process leave
  * on the device) — BASELINE config "batch of 4096 frames, extract + match": pair p matches the rows of image d_pair_q[p]
  * (queries) against image d_pair_t[p] (train), e.g. consecutive frames (i, i + 1). Outputs d_idx / d_dist [n_pairs][cap][2],
- * rows >= the query image's count are left untouched. Every pair == mcv_knn2_bf on the two descriptor sets. Asynchronous on
- * `stream`. (All brute-force entry points run on the tensor cores from 2^20 pairs per problem up — int8 GEMM of the +-1
+ * rows >= the query image's count are left untouched. Every pair == mcv_knn2_bf on the two descriptor sets. At most 65535
+ * pairs and 2^27 descriptor rows per call. Asynchronous on
+ * `stream`. (All brute-force entry points run on the tensor cores from 2^23 pairs per problem up — int8 GEMM of the +-1
  * expanded descriptors, exact — and on the integer pipe below; env MCV_KNN_POPC=1 forces the integer-pipe kernel.) */
 mcv_status mcv_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int n_images, int cap, const int32_t* d_pair_q,
                                  const int32_t* d_pair_t, int n_pairs, int32_t* d_idx, int32_t* d_dist, void* stream);

@@ -714,7 +714,7 @@ mcv_status mcv_knn2_bf_device(const uint8_t* d_q, int nq, const uint8_t* d_t, in
 
 mcv_status mcv_knn2_pairs_device(const uint8_t* d_desc, const int32_t* d_counts, int n_images, int cap, const int32_t* d_pair_q, const int32_t* d_pair_t,
                                  int n_pairs, int32_t* d_idx, int32_t* d_dist, void* stream) {
-    if (n_images < 1 || cap < 2 || cap > (1 << 22) || n_pairs < 0 || !d_desc || !d_counts || (n_pairs > 0 && (!d_pair_q || !d_pair_t || !d_idx || !d_dist)))
+    if (n_images < 1 || cap < 2 || cap > (1 << 22) || n_pairs < 0 || n_pairs > 65535 /* grid.z */ || (long long)n_images * cap > (1ll << 27) || !d_desc || !d_counts || (n_pairs > 0 && (!d_pair_q || !d_pair_t || !d_idx || !d_dist)))
         return MCV_ERR_BAD_ARG;
     if (n_pairs == 0) return MCV_OK;
     void* d_scratch = nullptr;   // stream-ordered on the CALLER's stream, like mcv_knn2_bf_device

@@ -98,7 +98,7 @@ size_t knn2_bf_part_bytes(int nq, int nt) {
     return (size_t)n_splits * nq * 2 * sizeof(unsigned);
 }
 
-// Brute-force 2-NN: tensor-core path (match_tc_kernels.cu) from 2^20 pairs up, integer-pipe kernel below that.
+// Brute-force 2-NN: tensor-core path (match_tc_kernels.cu) from 2^23 pairs up, integer-pipe kernel below that.
 int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, unsigned* d_part,
                    cudaStream_t s) {
     if (nq <= 0) return 0;

@@ -9,13 +9,14 @@
 // an int8 GEMM:    <a', b'> = (#equal bits) - (#different bits) = 256 - 2 Hamming(a, b)      (exact in the s32 accumulator).
 //
 // k_knn2_tc: one CTA owns 128 queries (UMMA M) and walks its train range in tiles of 256 rows (UMMA N); K = 256 bytes = two
-// swizzle atoms = 8 instructions of K = 32 per tile. Warp 0 = TMA producer (2-stage ring of 64 KB train tiles, the query tile
+// swizzle atoms = 8 instructions of K = 32 per tile. Warp 0 = TMA producer (3-stage ring of 64 KB train tiles, the query tile
 // is loaded once), warp 1 = MMA issuer and TMEM owner (two 128 x 256 s32 accumulators = all 512 columns, so the epilogue of
-// tile i overlaps the MMAs of tile i + 1), warps 2..9 = epilogue: thread = one query row (TMEM lane), two warps per lane
-// quarter take 128 columns each with tcgen05.ld.32x32b.x32, double-buffered. The 2-NN needs no key per pair: a thread sees
-// its columns in ascending train index, so a column can only enter the top-2 when its dot product is STRICTLY larger than the
-// current second best's; one max-reduction per 32 columns decides that, and only then the (distance << 22 | index) keys are
-// formed (about 2 ln T times per row). Results are the same lexicographic (distance, index) top-2 as k_knn2_bf.
+// tile i overlaps the MMAs of tile i + 1), warps 2..17 = epilogue: thread = one query row (TMEM lane), four warps per lane
+// quarter take 64 columns each (two tcgen05.ld.32x32b.x32 in flight together; the TMEM buffer is handed back as soon as they
+// land, before the scan). The 2-NN needs no key per pair: a thread sees its columns in ascending train index, so a column can
+// only enter the top-2 when its dot product is STRICTLY larger than the current second best's; one max-reduction per 32
+// columns decides that, and only then the (distance << 22 | index) keys are formed (about 2 ln T times per row). Results are
+// the same lexicographic (distance, index) top-2 as k_knn2_bf.
 #include <cuda.h>
 
 #include "engine.h"
@@ -26,14 +27,15 @@ namespace mcv {
 constexpr int TC_M = 128;
 constexpr int TC_N = 256;
 constexpr int TC_KB = 128;                 // bytes of K per shared-memory tile row (one swizzle atom)
-constexpr int TC_STAGES = 2;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_STAGES = 3;                // 3 x 64 KB train tiles + 32 KB of queries: a TMA load has two tiles of MMA time to land
+constexpr int TC_EPI_WARPS = 16;            // four warps per TMEM lane quarter, 64 columns of every tile each
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_EPI_COLS = TC_N / (TC_EPI_WARPS / 4);
 constexpr unsigned TC_A_TILE = TC_M * TC_KB;            // 16 KB per K half
 constexpr unsigned TC_B_TILE = TC_N * TC_KB;            // 32 KB per K half
 constexpr unsigned TC_STAGE_BYTES = 2 * TC_B_TILE;
-constexpr unsigned TC_SMEM_BYTES = 2 * TC_A_TILE + TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/ + 1024 /*second-half keys*/;
+constexpr unsigned TC_SMEM_BYTES = 2 * TC_A_TILE + TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+static_assert(TC_SMEM_BYTES <= 232448, "shared memory per CTA");
 constexpr int TC_IDX_BITS = 22;            // same key as k_knn2_bf: distance << 22 | trainIdx
 constexpr unsigned TC_SENT = 0xffffffffu;
 
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
     if (q0 >= nq) return;                                            // block-uniform, before any barrier or TMEM allocation
     const unsigned base = (tc_smem_u32(smem_raw) + 1023u) & ~1023u;
     const unsigned sA = base, sB = base + 2 * TC_A_TILE, sBar = sB + TC_STAGES * TC_STAGE_BYTES;
-    // barriers: a_full | full[S] | empty[S] | tmem_full[2] | tmem_empty[2]; then the TMEM base address; then the second-half keys
+    // barriers: a_full | full[S] | empty[S] | tmem_full[2] | tmem_empty[2]; then the TMEM base address
     const unsigned bar_a = sBar, bar_full = sBar + 8, bar_empty = bar_full + 8 * TC_STAGES, bar_tfull = bar_empty + 8 * TC_STAGES, bar_tempty = bar_tfull + 16;
     const unsigned tmem_slot = bar_tempty + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
         }
     } else {
         // epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 = query rows; one row per thread, TC_EPI_COLS columns of every tile
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int quarter = warp & 3, part = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         unsigned k0 = TC_SENT, k1 = TC_SENT;
         int thr = -100000;                          // dot product of the current second best: only a strictly larger one can enter
@@ -190,34 +192,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
                 }
             }
         };
+        static_assert(TC_EPI_COLS == 64, "the epilogue keeps its two 32-column loads of a tile in flight together");
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
             mbar_wait(bar_tfull + 8 * b, (i >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int col0 = half * TC_EPI_COLS;
+            const int col0 = part * TC_EPI_COLS;
             const int idx_base = t_begin + i * TC_N + col0;
             const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(b * TC_N + col0);
             int va[32], vb[32];
             tmem_ld32(taddr, va);
-#pragma unroll 1
-            for (int c = 0; c < TC_EPI_COLS / 32; c += 2) {       // the next 32 columns are in flight while one chunk is scanned
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tmem_ld32(taddr + (unsigned)((c + 1) * 32), vb);
-                scan(va, idx_base + c * 32);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 2 < TC_EPI_COLS / 32) tmem_ld32(taddr + (unsigned)((c + 2) * 32), va);
-                scan(vb, idx_base + (c + 1) * 32);
-            }
+            tmem_ld32(taddr + 32u, vb);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // the accumulator is in registers: hand the TMEM buffer back before scanning
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(bar_tempty + 8 * b);
+            scan(va, idx_base);
+            scan(vb, idx_base + 32);
         }
-        unsigned* sk = reinterpret_cast<unsigned*>(smem_raw + (tmem_slot + 16 - tc_smem_u32(smem_raw)));   // [128][2] keys of the second column half
-        if (half == 1) { sk[2 * row] = k0; sk[2 * row + 1] = k1; }
+        // [parts - 1][128][2] keys of the other column parts, in the first train stage: every MMA has completed (the last tile's
+        // accumulator was awaited above), so nothing reads the stages any more
+        unsigned* sk = reinterpret_cast<unsigned*>(smem_raw + (sB - tc_smem_u32(smem_raw)));
+        if (part > 0) { sk[((part - 1) * TC_M + row) * 2] = k0; sk[((part - 1) * TC_M + row) * 2 + 1] = k1; }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");                               // epilogue warps only
         const int q = q0 + row;
-        if (half == 0 && q < nq) {
-            tc_top2(k0, k1, sk[2 * row]); tc_top2(k0, k1, sk[2 * row + 1]);
+        if (part == 0 && q < nq) {
+#pragma unroll
+            for (int p = 0; p < TC_EPI_WARPS / 4 - 1; ++p) { tc_top2(k0, k1, sk[(p * TC_M + row) * 2]); tc_top2(k0, k1, sk[(p * TC_M + row) * 2 + 1]); }
             if (A.n_splits > 1) {
                 unsigned* o = A.part + (((size_t)pair * A.n_splits + blockIdx.y) * A.q_stride + q) * 2;
                 o[0] = k0; o[1] = k1;
@@ -280,7 +282,9 @@ static void tc_splits(int nq, int nt, int n_pairs, int& n_splits, int& per_split
     n_splits = std::max(1, (nt + per_split - 1) / per_split);
 }
 
-bool knn2_tc_usable(int nq, int nt) { return nq >= 1 && nt >= 2 && (long long)nq * nt >= (1 << 20) && nt <= (1 << TC_IDX_BITS); }
+// single problems: from 2^23 pairs up (B200: 2000 x 2000 = 23 us on the integer pipe vs 31 us here — the expansion launch and the
+// pipeline fill dominate; 5000 x 5000 = 68 us vs 42 us)
+bool knn2_tc_usable(int nq, int nt) { return nq >= 1 && nt >= 2 && (long long)nq * nt >= (1 << 23) && nt <= (1 << TC_IDX_BITS); }
 
 // scratch of one call: expanded queries | expanded train rows | partial keys
 size_t knn2_tc_scratch_bytes(int nq_rows, int nt_rows, int nq, int nt, int n_pairs) {

@@ -265,12 +265,12 @@ def test_distinctive_descriptors_ties(api, oracle):
     assert len(bi) == 0
 
 
-@pytest.mark.parametrize("nq,nt,low", [(128, 8193, False), (129, 8192, True), (2003, 2000, False), (5000, 5001, True), (1000, 70000, True),
-                                       (20000, 300, False), (257, 4100, True), (1, 1 << 20, False), (40000, 40, True)])
+@pytest.mark.parametrize("nq,nt,low", [(1025, 8193, False), (129, 70001, True), (4097, 2049, False), (5000, 5001, True), (1000, 70000, True),
+                                       (30000, 300, False), (2049, 4100, True), (8, 1 << 20, False), (300000, 40, True)])
 def test_knn2_tensor_core_path(api, oracle, nq, nt, low):
-    """Problems of >= 2^20 pairs run on tcgen05 (int8 GEMM of the +-1 expanded descriptors, match_tc_kernels.cu): tile edges
+    """Problems of >= 2^23 pairs run on tcgen05 (int8 GEMM of the +-1 expanded descriptors, match_tc_kernels.cu): tile edges
     (M = 128 queries, N = 256 train rows per tile), the split + merge path (few query tiles, long train walk), tie-heavy sets."""
-    assert nq * nt >= 1 << 20
+    assert nq * nt >= 1 << 23
     q = synth.descriptors(nq, 21, low); t = synth.descriptors(nt, 22, low)
     if low:
         q[:, 2:] = 0; t[:, 2:] = 0          # 16 significant bits: most nearest neighbours tie, the index order decides
