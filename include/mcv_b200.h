@@ -202,8 +202,9 @@ int mcv_rig_max_keypoints_for(const mcv_rig* r, int w, int hgt);
 /* The extractor of slot 0 (image index = 3*frame + cam within the chunk it processed last; cam 0=L,1=R,2=W). The whole batch
  * is in it when it ran as one chunk: n_frames <= chunk_frames/... see mcv_rig_set_chunk_frames(r, 0). */
 mcv_orb* mcv_rig_extractor(mcv_rig* r);
-/* Batches are cut into chunks of `chunk_frames` triplets pipelined over 3 internal streams (H2D / kernels / D2H overlap
- * inside one synchronous call). Default 32 (env MCV_RIG_CHUNK); 0 = never chunk. */
+/* Batches are cut into chunks of at most `chunk_frames` triplets pipelined over 6 internal streams (H2D / kernels / D2H overlap
+ * inside one synchronous call; every stream gets a chunk). Default 32 (env MCV_RIG_CHUNK); 0 = never chunk. Chunks of up to 32
+ * frames replay a CUDA graph captured on the second call with the same shape (env MCV_RIG_GRAPH_MAX, 0 = direct launches). */
 mcv_status mcv_rig_set_chunk_frames(mcv_rig* r, int chunk_frames);
 
 /* Frame::Frame ORBE + SMatch stages for a batch of n_frames triplets. imgs: [n_frames][3][hgt][w] u8 (L, R, W), host

@@ -70,6 +70,7 @@ struct mcv_orb {
     Plan plan{};
     bool have_plan = false;
     int cap_images = 0;     // workspace capacity (images)
+    unsigned ws_epoch = 0;  // bumped whenever the workspace buffers are (re)allocated: captured graphs of older epochs are stale
     int last_images = 0;    // images processed by the last extract
     DevBuf tabs, src, pyr, blur, score, nz_list, nz_cnt, cell_raw, cell_pts, cell_cnt, fallback, arena_a, arena_b, oct_idx, out_pts, out_cnt, kps, desc, counts, seeds, misc;
     HostBuf h_stage;
@@ -239,6 +240,7 @@ static mcv_status ensure_workspace(mcv_orb* h, int w, int hgt, int n_images, int
         if ((st = h->out_pts.reserve((size_t)P.out_per_image * n_images * 4))) return st;
         if ((st = h->out_cnt.reserve((size_t)P.n_levels * n_images * 4 * 2))) return st;   // counts | per-task overflow flags (launch_octree)
         h->cap_images = n_images;
+        ++h->ws_epoch;
     }
     mcv_status st;
     if ((st = h->kps.reserve((size_t)cap * n_images * sizeof(mcv_keypoint)))) return st;
@@ -1143,14 +1145,29 @@ mcv_status mcv_debug_popc_peak(int iters, double* popc_per_s, double* ms_out) {
 // and the device->host copy of chunk i-1 overlap, and the latency-bound quadtree kernel of one chunk shares the SMs with
 // the throughput-bound stencils of another (CUDA streams replace the reference's ThreadPool(3), src/Frame.cpp:22).
 // =========================================================================================================
-constexpr int RIG_SLOTS = 3;
+#ifndef MCV_RIG_SLOTS_N
+#define MCV_RIG_SLOTS_N 6
+#endif
+constexpr int RIG_SLOTS = MCV_RIG_SLOTS_N;
 constexpr int RIG_TICKETS = 8;
+
+// A chunk's whole kernel sequence (about 25 launches and memsets) captured once per shape and pointer set and replayed with one
+// cudaGraphLaunch: small chunks are bound by the host's launch rate, not by the GPU (B200: 128 frames as 8 chunks of 16 through
+// mcv_rig_process = 5.6 ms with direct launches).
+struct ChunkKey {
+    int n_frames, w, h, cap, channels; unsigned epoch;
+    const void *imgs, *kps, *desc, *counts, *ur, *dp, *best, *scratch;
+    bool operator==(const ChunkKey& o) const { return memcmp(this, &o, sizeof(ChunkKey)) == 0; }
+};
+struct ChunkGraph { ChunkKey key; cudaGraphExec_t exec = nullptr; int launches = 0; bool warm_only = true; };
 
 struct RigSlot {
     mcv_orb* orb = nullptr;
     DevBuf imgs, kps, desc, counts, u_right, depth, best_dist, st_scratch;
     cudaEvent_t done = nullptr, front = nullptr;   // all work of the last chunk / its front half
+    std::vector<ChunkGraph> graphs;                // most recently used last; at most RIG_GRAPHS_PER_SLOT
 };
+constexpr int RIG_GRAPHS_PER_SLOT = 8;
 
 struct mcv_rig {
     mcv_rig_params prm{};
@@ -1159,10 +1176,12 @@ struct mcv_rig {
     bool own_stream = false;
     RigSlot slot[RIG_SLOTS];
     cudaEvent_t fork = nullptr;
-    int chunk_frames = 32;          // host path: chunks pipeline H2D / kernels / D2H
+    int chunk_frames = 32;          // host path: chunks pipeline H2D / kernels / D2H (capped at ceil(n / slots) so that every slot gets work)
     int chunk_frames_dev = 128;     // device-resident path: consecutive calls overlap instead (see mcv_rig_process_async)
     int next_slot = 0;              // chunks rotate over the slots across calls
-    int use_slots = RIG_SLOTS;      // host path: slots in rotation (env MCV_RIG_SLOTS)
+    int use_slots = RIG_SLOTS;      // synchronous host path: slots in rotation (env MCV_RIG_SLOTS). B200, 128 frames per mcv_rig_process call:
+                                    // 3 slots 25.1 k frames/s, 4 slots 27.7 k, 6 slots 29.4 k (a chunk no longer waits for the D2H of the chunk
+                                    // that used its slot before); mcv_rig_submit keeps whole steps in flight and rotates over three
     int use_slots_dev = 2;          // device-resident path (env MCV_RIG_SLOTS_DEV): consecutive calls alternate between two
                                     // streams, so the latency-bound quadtree of one batch runs beside the stencils of the next
                                     // (B200, current kernels: 34.0k frames/s on one stream, 37.3k on two, 37.3k on three; a
@@ -1175,22 +1194,17 @@ struct mcv_rig {
     int submit_chunk = 128;                 // frames per chunk of mcv_rig_submit (env MCV_RIG_SUBMIT_CHUNK); B200, 3 steps in flight: 128 -> 35.7k frames/s, 64 -> 34.7k, 32 -> 29.2k
     bool pending_join = false;
     int last_launches = 0;
+    int graph_max_frames = 32;              // chunks of at most this many frames replay a captured CUDA graph (env MCV_RIG_GRAPH_MAX, 0 = never)
 };
 
 // ORBE + SMatch of n_frames device-resident triplets on one slot (its stream); all pointers are device pointers.
-static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
-                            uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth, int cap, int* launches,
-                            bool stagger = true) {
+static mcv_status rig_chunk_enqueue(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
+                                    uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth, int cap, int* launches, bool stagger, bool events) {
     mcv_orb* h = sl.orb;
-    mcv_status st = ensure_workspace(h, w, hgt, 3 * n_frames, 1);
+    mcv_status st = enqueue_extract(h, d_imgs, (size_t)w * h->channels, (size_t)w * hgt * h->channels, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap,
+                                    events && stagger && !r->no_stagger && r->last_front != sl.front ? r->last_front : nullptr, events ? sl.front : nullptr);
     if (st) return st;
-    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints_for(w, h)"); return MCV_ERR_CAPACITY; }
-    if ((st = sl.best_dist.reserve((size_t)n_frames * cap * 4))) return st;
-    if ((st = sl.st_scratch.reserve(stereo_scratch_bytes(h->plan, n_frames, cap)))) return st;
-    st = enqueue_extract(h, d_imgs, (size_t)w * h->channels, (size_t)w * hgt * h->channels, 3 * n_frames, nullptr, d_kps, d_desc, d_counts, cap,
-                         stagger && !r->no_stagger && r->last_front != sl.front ? r->last_front : nullptr, sl.front);
-    if (st) return st;
-    r->last_front = sl.front;
+    if (events) r->last_front = sl.front;
     int n = h->last_launches;
     cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 7] : nullptr;
     n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
@@ -1202,14 +1216,61 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
     return MCV_OK;
 }
 
+static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
+                            uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth, int cap, int* launches,
+                            bool stagger = true) {
+    mcv_orb* h = sl.orb;
+    mcv_status st = ensure_workspace(h, w, hgt, 3 * n_frames, 1);
+    if (st) return st;
+    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_rig_max_keypoints_for(w, h)"); return MCV_ERR_CAPACITY; }
+    if ((st = sl.best_dist.reserve((size_t)n_frames * cap * 4))) return st;
+    if ((st = sl.st_scratch.reserve(stereo_scratch_bytes(h->plan, n_frames, cap)))) return st;
+    const bool graph_ok = n_frames <= r->graph_max_frames && !h->profile && !h->quad_stream && r->no_stagger;
+    if (!graph_ok) return rig_chunk_enqueue(r, sl, d_imgs, n_frames, w, hgt, d_kps, d_desc, d_counts, d_u_right, d_depth, cap, launches, stagger, true);
+    const ChunkKey key{n_frames, w, hgt, cap, h->channels, h->ws_epoch, d_imgs, d_kps, d_desc, d_counts, d_u_right, d_depth, sl.best_dist.p, sl.st_scratch.p};
+    for (size_t i = 0; i < sl.graphs.size(); ++i) {
+        if (!(sl.graphs[i].key == key)) continue;
+        ChunkGraph g = sl.graphs[i];
+        sl.graphs.erase(sl.graphs.begin() + i);
+        if (g.warm_only) {
+            // second call with this shape and pointer set: every lazy allocation and function attribute is settled -> capture
+            cudaGraph_t graph = nullptr;
+            int n = 0;
+            if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); r->graph_max_frames = 0; break; }
+            st = rig_chunk_enqueue(r, sl, d_imgs, n_frames, w, hgt, d_kps, d_desc, d_counts, d_u_right, d_depth, cap, &n, false, false);
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (st || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+                cudaGetLastError();
+                if (graph) cudaGraphDestroy(graph);
+                r->graph_max_frames = 0;         // capture is not available here: direct launches from now on
+                if (st) return st;
+                break;
+            }
+            cudaGraphDestroy(graph);
+            g.launches = n; g.warm_only = false;
+        }
+        MCV_CUDA(cudaGraphLaunch(g.exec, h->stream));
+        *launches += g.launches;
+        h->last_images = 3 * n_frames; h->last_cap = cap; h->last_launches = g.launches;
+        sl.graphs.push_back(g);
+        return MCV_OK;
+    }
+    if (r->graph_max_frames > 0) {
+        if ((int)sl.graphs.size() >= RIG_GRAPHS_PER_SLOT) { if (sl.graphs[0].exec) cudaGraphExecDestroy(sl.graphs[0].exec); sl.graphs.erase(sl.graphs.begin()); }
+        ChunkGraph g; g.key = key;
+        sl.graphs.push_back(g);
+    }
+    return rig_chunk_enqueue(r, sl, d_imgs, n_frames, w, hgt, d_kps, d_desc, d_counts, d_u_right, d_depth, cap, launches, stagger, true);
+}
+
 // Host-buffer path: per chunk H2D -> kernels -> D2H on the slot's stream (all asynchronous), chunks rotating over the slots.
 static mcv_status rig_enqueue_host(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, int imgs_on_device, mcv_keypoint* kps_out,
-                                   uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device, int chunk) {
+                                   uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device, int chunk, int n_slots) {
     const size_t img3 = (size_t)3 * w * hgt * r->slot[0].orb->channels, kb = sizeof(mcv_keypoint);
     int launches = 0;
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
-        RigSlot& sl = r->slot[r->next_slot % r->use_slots];
-        r->next_slot = (r->next_slot + 1) % r->use_slots;
+        RigSlot& sl = r->slot[r->next_slot % n_slots];
+        r->next_slot = (r->next_slot + 1) % n_slots;
         cudaStream_t s = sl.orb->stream;
         const int nf = std::min(chunk, n_frames - f0);
         const size_t n_img = (size_t)3 * nf;
@@ -1248,7 +1309,7 @@ static mcv_status rig_enqueue_host(mcv_rig* r, const uint8_t* imgs, int n_frames
 static inline int rig_chunk_size(const mcv_rig* r, int n_frames) {
     // profiling measures whole-batch kernels on one stream; otherwise chunk so that all slots get work
     if (r->slot[0].orb->profile || r->chunk_frames <= 0) return n_frames;
-    return std::max(1, std::min(r->chunk_frames, (n_frames + RIG_SLOTS - 1) / RIG_SLOTS));
+    return std::max(1, std::min(r->chunk_frames, (n_frames + r->use_slots - 1) / r->use_slots));
 }
 
 extern "C" {
@@ -1283,6 +1344,7 @@ mcv_status mcv_rig_create(const mcv_rig_params* p, int device, void* stream, mcv
     if (const char* e = getenv("MCV_RIG_SUBMIT_CHUNK")) r->submit_chunk = atoi(e);
     if (const char* e = getenv("MCV_RIG_SLOTS")) r->use_slots = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     if (const char* e = getenv("MCV_RIG_STAGGER")) r->no_stagger = atoi(e) == 0;
+    if (const char* e = getenv("MCV_RIG_GRAPH_MAX")) r->graph_max_frames = atoi(e);
     if (const char* e = getenv("MCV_RIG_SLOTS_DEV")) r->use_slots_dev = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     *out = r;
     return MCV_OK;
@@ -1297,6 +1359,7 @@ void mcv_rig_destroy(mcv_rig* r) {
         for (DevBuf* b : {&sl.imgs, &sl.kps, &sl.desc, &sl.counts, &sl.u_right, &sl.depth, &sl.best_dist, &sl.st_scratch}) b->release();
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.front) cudaEventDestroy(sl.front);
+        for (ChunkGraph& g : sl.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         mcv_orb_destroy(sl.orb);
     }
     if (r->fork) cudaEventDestroy(r->fork);
@@ -1419,7 +1482,7 @@ mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w,
     // host side involved: per-chunk H2D -> kernels -> D2H on the slot's stream, chunks overlapping across slots
     MCV_CUDA(cudaStreamSynchronize(r->stream));
     mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, imgs_on_device, kps_out, desc_out, counts, u_right, depth_left, cap,
-                                     out_on_device, rig_chunk_size(r, n_frames));
+                                     out_on_device, rig_chunk_size(r, n_frames), r->use_slots);
     if (st) return st;
     for (RigSlot& sl : r->slot) MCV_CUDA(cudaStreamSynchronize(sl.orb->stream));
     return MCV_OK;
@@ -1432,7 +1495,7 @@ mcv_status mcv_rig_submit(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, 
     if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
     MCV_CUDA(cudaSetDevice(r->device));
     const int chunk = r->slot[0].orb->profile || r->submit_chunk <= 0 ? n_frames : std::min(n_frames, r->submit_chunk);
-    mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, 0, kps_out, desc_out, counts, u_right, depth_left, cap, 0, chunk);
+    mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, 0, kps_out, desc_out, counts, u_right, depth_left, cap, 0, chunk, std::min(3, r->use_slots));   // whole steps in flight: three slots are enough
     if (st) return st;
     // completion = every slot's stream has drained what this call put on it
     const long long id = ++r->submitted;

@@ -162,3 +162,35 @@ def test_rig_submit_wait_matches_sync_call(api):
             m = cnt[f, 0]
             assert np.array_equal(o["ur"].numpy().reshape(n, cap)[f, :m].view(np.uint32), ref["u_right"][f, :m].view(np.uint32))
     rig.close()
+
+
+@pytest.mark.gpu
+def test_rig_small_chunks_replay_captured_graph(api, oracle):
+    """Chunks of <= 32 frames replay a CUDA graph captured on the second call with the same shape (engine.cu: rig_chunk). Five
+    calls on ONE rig with different images each time — direct, capture, three replays — must all equal the oracle; then the
+    same for the one-triplet call (the reference's Frame-per-call pattern) and after the workspace re-grows in between."""
+    rig = api.Rig()
+    orbs = [oracle.Orb() for _ in range(3)]
+
+    def check(frames, out):
+        for f in range(len(frames)):
+            ks, ds = [], []
+            for c in range(3):
+                n, k, d = orbs[c].extract(frames[f, c])
+                assert out["counts"][f, c] == n
+                assert out["kps"][f, c, :n].tobytes() == k.tobytes() and out["desc"][f, c, :n].tobytes() == d.tobytes()
+                ks.append(k); ds.append(d)
+            n, ur, dp, bd, br = oracle.stereo_match(orbs[0], orbs[1], ks[0], ds[0], ks[1], ds[1], 480, 955.40503, 1.0)
+            assert out["u_right"][f, :len(ks[0])].tobytes() == ur.tobytes()
+
+    for call in range(5):
+        frames = np.stack([synth.triplet(300 + 2 * call), synth.triplet(301 + 2 * call)])
+        check(frames, rig.process(frames))
+    for call in range(4):
+        frames = np.stack([synth.triplet(320 + call)])
+        check(frames, rig.process(frames))
+    big = np.stack([synth.triplet(330 + i) for i in range(7)])      # 3 chunks of 3 / 3 / 1 frames: grows the slots' workspaces
+    check(big[:2], {k: v[:2] for k, v in rig.process(big).items()})
+    for call in range(3):
+        frames = np.stack([synth.triplet(340 + call)])
+        check(frames, rig.process(frames))
