@@ -48,8 +48,8 @@ PYR_BYTES_PER_IMAGE = 950532          # all 8 levels
 STAGE_BYTES_PER_IMAGE = {
     "pyramid": 307200 + 950532,                 # read input, write 8 levels
     "blur": 2 * 950532,                         # read pyramid, write smoothed pyramid
-    "fast_score": 2 * 950532,                   # read pyramid, write the score map
-    "nms_cells": 950532 + 4 * 6500,             # read score map, write ~6.5k packed candidates
+    "fast_score": 950532 + 4 * 6500,            # read pyramid, write ~6.5k packed scored pixels (round 1 also wrote a dense score map: 2 x 950532)
+    "nms_cells": 2 * 4 * 6500,                  # read the scored-pixel lists, write the surviving candidates
     "quadtree": 2 * 4 * 6500 + 4 * 2000,        # read candidates, write them ordered, write 2000 selected
     "orient_desc": 2000 * (31 * 31 + 37 * 37 + 60),  # per keypoint: intensity patch + smoothed patch + 60 B out
     "stereo_match": (2 * 2000 * 60 + 2000 * 16) / 3.0,   # per frame / 3 images
