@@ -744,6 +744,8 @@ mcv_status mcv_project_match(const mcv_keypoint* kps, const uint8_t* desc, int n
     if (st) return st;
     cudaStream_t s = mc->stream;
     DevBuf &b_kps = mc->slot[0], &b_desc = mc->slot[1], &b_f = mc->slot[2], &b_xyz = mc->slot[3], &b_mpd = mc->slot[4], &b_lvl = mc->slot[5], &b_oi = mc->slot[6], &b_od = mc->slot[7];
+    DevBuf& b_grid = mc->slot[11];   // 30 x 30 cell table: 901 prefix entries | n keypoint indices
+    if ((st = b_grid.reserve((size_t)(1024 + std::max(n, 1)) * 4))) return st;
     if ((st = b_kps.reserve(std::max<size_t>(28, (size_t)n * sizeof(mcv_keypoint))))) return st;
     if ((st = b_desc.reserve(std::max<size_t>(32, (size_t)n * 32)))) return st;
     if ((st = b_f.reserve((size_t)(nlevels + 16) * 4))) return st;
@@ -764,7 +766,8 @@ mcv_status mcv_project_match(const mcv_keypoint* kps, const uint8_t* desc, int n
     MCV_CUDA(cudaMemcpyAsync(b_mpd.p, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, s));
     MCV_CUDA(cudaMemcpyAsync(b_lvl.p, mp_level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, s));
     launch_project(b_kps.as<mcv_keypoint>(), b_desc.as<uint8_t>(), n, w, hgt, b_f.as<float>() + 16, b_f.as<float>(), b_xyz.as<float>(),
-                   b_mpd.as<uint8_t>(), b_lvl.as<int32_t>(), n_mp, r_threshold, b_oi.as<int32_t>(), b_od.as<int32_t>(), s);
+                   b_mpd.as<uint8_t>(), b_lvl.as<int32_t>(), n_mp, r_threshold, b_grid.as<int32_t>(), b_grid.as<int32_t>() + 1024, b_oi.as<int32_t>(),
+                   b_od.as<int32_t>(), s);
     MCV_CUDA(cudaGetLastError());
     MCV_CUDA(cudaMemcpyAsync(out_idx, b_oi.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaMemcpyAsync(out_dist, b_od.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
@@ -789,6 +792,8 @@ mcv_status mcv_fuse_match(const mcv_keypoint* kps, const uint8_t* desc, int n, i
     if (st) return st;
     cudaStream_t s = mc->stream;
     DevBuf &b_kps = mc->slot[0], &b_desc = mc->slot[1], &b_f = mc->slot[2], &b_dl = mc->slot[3], &b_xyz = mc->slot[4], &b_nrm = mc->slot[5], &b_mpd = mc->slot[6], &b_lvl = mc->slot[7], &b_oi = mc->slot[8], &b_od = mc->slot[9];
+    DevBuf& b_grid = mc->slot[11];
+    if ((st = b_grid.reserve((size_t)(1024 + std::max(n, 1)) * 4))) return st;
     if ((st = b_kps.reserve(std::max<size_t>(28, (size_t)n * sizeof(mcv_keypoint))))) return st;
     if ((st = b_desc.reserve(std::max<size_t>(32, (size_t)n * 32)))) return st;
     if ((st = b_dl.reserve(std::max<size_t>(4, (size_t)n * 4)))) return st;
@@ -814,7 +819,8 @@ mcv_status mcv_fuse_match(const mcv_keypoint* kps, const uint8_t* desc, int n, i
     MCV_CUDA(cudaMemcpyAsync(b_mpd.p, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, s));
     MCV_CUDA(cudaMemcpyAsync(b_lvl.p, mp_level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, s));
     launch_fuse_match(b_kps.as<mcv_keypoint>(), b_desc.as<uint8_t>(), n, w, hgt, b_f.as<float>(), nlevels, b_dl.as<float>(), b_xyz.as<float>(),
-                      b_nrm.as<float>(), b_mpd.as<uint8_t>(), b_lvl.as<int32_t>(), n_mp, b_oi.as<int32_t>(), b_od.as<int32_t>(), s);
+                      b_nrm.as<float>(), b_mpd.as<uint8_t>(), b_lvl.as<int32_t>(), n_mp, b_grid.as<int32_t>(), b_grid.as<int32_t>() + 1024, b_oi.as<int32_t>(),
+                      b_od.as<int32_t>(), s);
     MCV_CUDA(cudaGetLastError());
     MCV_CUDA(cudaMemcpyAsync(out_idx, b_oi.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaMemcpyAsync(out_dist, b_od.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, s));
@@ -836,6 +842,8 @@ mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1,
     if (st) return st;
     cudaStream_t s = mc->stream;
     DevBuf &b_k1 = mc->slot[0], &b_d1 = mc->slot[1], &b_q = mc->slot[2], &b_k2 = mc->slot[3], &b_d2 = mc->slot[4], &b_oi = mc->slot[5], &b_ob = mc->slot[6], &b_od = mc->slot[7];
+    DevBuf& b_grid = mc->slot[11];
+    if ((st = b_grid.reserve((size_t)(1024 + std::max(n2, 1)) * 4))) return st;
     if ((st = b_k1.reserve((size_t)n1 * sizeof(mcv_keypoint)))) return st;
     if ((st = b_d1.reserve((size_t)n1 * 32))) return st;
     if ((st = b_q.reserve((size_t)n_q * 4))) return st;
@@ -852,7 +860,7 @@ mcv_status mcv_wnd_track(const mcv_keypoint* kps1, const uint8_t* desc1, int n1,
         MCV_CUDA(cudaMemcpyAsync(b_d2.p, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
     }
     launch_wnd_track(b_k1.as<mcv_keypoint>(), b_d1.as<uint8_t>(), b_q.as<int32_t>(), n_q, b_k2.as<mcv_keypoint>(), b_d2.as<uint8_t>(), n2, w, hgt,
-                     b_oi.as<int32_t>(), b_ob.as<int32_t>(), b_od.as<int32_t>(), s);
+                     b_grid.as<int32_t>(), b_grid.as<int32_t>() + 1024, b_oi.as<int32_t>(), b_ob.as<int32_t>(), b_od.as<int32_t>(), s);
     MCV_CUDA(cudaGetLastError());
     MCV_CUDA(cudaMemcpyAsync(out_idx, b_oi.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));
     MCV_CUDA(cudaMemcpyAsync(out_best, b_ob.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));

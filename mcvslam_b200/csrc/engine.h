@@ -120,13 +120,14 @@ int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t
 int launch_knn2_candidates(const uint8_t* d_q, int nq, const uint8_t* d_t, const int32_t* d_off, const int32_t* d_cidx, int32_t* d_idx,
                            int32_t* d_dist, cudaStream_t s);
 int launch_project(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_scale, const float* d_pose,
-                   const float* d_xyz, const uint8_t* d_mp_desc, const int32_t* d_level, int n_mp, float r_th, int32_t* d_idx,
-                   int32_t* d_dist, cudaStream_t s);
+                   const float* d_xyz, const uint8_t* d_mp_desc, const int32_t* d_level, int n_mp, float r_th, int32_t* d_cell_start,
+                   int32_t* d_cell_idx, int32_t* d_idx, int32_t* d_dist, cudaStream_t s);   // d_cell_start: 901 ints, d_cell_idx: n ints (30 x 30 cell table, built here)
 int launch_fuse_match(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_par, int n_levels,
                       const float* d_depth_left, const float* d_xyz, const float* d_normal, const uint8_t* d_mp_desc, const int32_t* d_level,
-                      int n_mp, int32_t* d_idx, int32_t* d_dist, cudaStream_t s);
+                      int n_mp, int32_t* d_cell_start, int32_t* d_cell_idx, int32_t* d_idx, int32_t* d_dist, cudaStream_t s);
 int launch_wnd_track(const mcv_keypoint* d_kps1, const uint8_t* d_desc1, const int32_t* d_qidx, int n_q, const mcv_keypoint* d_kps2,
-                     const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_idx, int32_t* d_best, int32_t* d_dist, cudaStream_t s);
+                     const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_cell_start, int32_t* d_cell_idx, int32_t* d_idx, int32_t* d_best,
+                     int32_t* d_dist, cudaStream_t s);
 int launch_bow_descend(const uint8_t* d_desc, int n, const int32_t* d_child_off, const uint32_t* d_child_ids, const uint8_t* d_node_desc,
                        int nid_level, int max_depth, uint32_t* d_leaf, uint32_t* d_nid, cudaStream_t s);
 int launch_distinctive(const uint8_t* d_desc, const int32_t* d_off, int n_mp, int32_t* d_best_idx, int32_t* d_best_median, cudaStream_t s);

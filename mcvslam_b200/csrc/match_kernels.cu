@@ -155,16 +155,73 @@ int launch_knn2_candidates(const uint8_t* d_q, int nq, const uint8_t* d_t, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// projection matching: one warp per MapPoint, brute-force gate over the camera's keypoints with a 64-bit key
-// (distance, grid-cell-major candidate order) so ties resolve exactly like the reference's candidate list.
-// pose = Rcw (9, row-major) | tcw (3) | fx fy cx cy
+// Object::AssignFeaturesToGrid / PosInGrid (src/Object.cpp:182-201,249-257) on the device: the 30 x 30 cell table of one image's
+// keypoints in the order GetFeaturesInArea walks it (cell-column-major = key gx * 30 + gy, ascending keypoint index inside a
+// cell). cell_start[901] = exclusive prefix of the cell populations, cell_idx[n] = keypoint indices. One CTA: shared-memory
+// histogram, scan, unordered scatter, then one thread per cell puts its (short) list in ascending order.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GRID_N = 30;  // FRAME_GRID_COLS / ROWS, include/Object.hpp:27-28
+constexpr int GRID_CELLS = GRID_N * GRID_N;
 
+__device__ __forceinline__ int grid_cell_of(float kx, float ky, float winv, float hinv) {
+    // PosInGrid: round(), keypoints whose cell falls outside [0, 30) are not in the grid at all
+    const int gx = (int)roundf(__fmul_rn(kx, winv)), gy = (int)roundf(__fmul_rn(ky, hinv));
+    return (gx < 0 || gx >= GRID_N || gy < 0 || gy >= GRID_N) ? -1 : gx * GRID_N + gy;
+}
+
+__global__ void __launch_bounds__(1024) k_grid_build(const mcv_keypoint* __restrict__ kps, int n, int w, int h, int32_t* __restrict__ cell_start,
+                                                     int32_t* __restrict__ cell_idx) {
+    __shared__ int s_cnt[GRID_CELLS], s_start[GRID_CELLS + 1];
+    const int tid = threadIdx.x;
+    const float winv = (float)((double)GRID_N / w), hinv = (float)((double)GRID_N / h);
+    for (int c = tid; c < GRID_CELLS; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) { const int c = grid_cell_of(kps[i].x, kps[i].y, winv, hinv); if (c >= 0) atomicAdd(&s_cnt[c], 1); }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of 900 counters by one warp (29 per lane)
+        const int per = (GRID_CELLS + 31) / 32, lo = min(tid * per, GRID_CELLS), hi = min(lo + per, GRID_CELLS);
+        int sum = 0;
+        for (int c = lo; c < hi; ++c) sum += s_cnt[c];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+        int run = incl - sum;
+        for (int c = lo; c < hi; ++c) { s_start[c] = run; run += s_cnt[c]; }
+        if (tid == 31) s_start[GRID_CELLS] = run;
+    }
+    __syncthreads();
+    for (int c = tid; c < GRID_CELLS; c += blockDim.x) s_cnt[c] = s_start[c];   // scatter cursors
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) { const int c = grid_cell_of(kps[i].x, kps[i].y, winv, hinv); if (c >= 0) cell_idx[atomicAdd(&s_cnt[c], 1)] = i; }
+    __syncthreads();
+    for (int c = tid; c < GRID_CELLS; c += blockDim.x) {   // ascending keypoint index inside the cell (insertion sort, lists are short)
+        const int lo = s_start[c], hi = s_start[c + 1];
+        for (int a = lo + 1; a < hi; ++a) {
+            const int v = cell_idx[a];
+            int b = a;
+            while (b > lo && cell_idx[b - 1] > v) { cell_idx[b] = cell_idx[b - 1]; --b; }
+            cell_idx[b] = v;
+        }
+    }
+    for (int c = tid; c <= GRID_CELLS; c += blockDim.x) cell_start[c] = s_start[c];
+}
+
+int launch_grid_build(const mcv_keypoint* d_kps, int n, int w, int h, int32_t* d_cell_start, int32_t* d_cell_idx, cudaStream_t s) {
+    k_grid_build<<<1, 1024, 0, s>>>(d_kps, n, w, h, d_cell_start, d_cell_idx);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// projection matching: one warp per MapPoint over the cell table's window (the columns of cells [min_cx, max_cx] x [min_cy, max_cy]
+// are contiguous runs of cell_idx) with a 64-bit key (distance, grid-cell-major candidate order), so ties resolve exactly like
+// the reference's candidate list.
+// pose = Rcw (9, row-major) | tcw (3) | fx fy cx cy
+// ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_project_match(const mcv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int n, int w,
                                                        int h, const float* __restrict__ scale, const float* __restrict__ pose,
                                                        const float* __restrict__ xyz, const uint8_t* __restrict__ mp_desc,
                                                        const int32_t* __restrict__ mp_level, int n_mp, float r_th,
+                                                       const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_idx,
                                                        int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (m >= n_mp) return;
@@ -191,20 +248,21 @@ __global__ void __launch_bounds__(256) k_project_match(const mcv_keypoint* __res
     const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(mp_desc + (size_t)m * 32 + 16));
     const unsigned long long SENT = 999ull << 32;
     unsigned long long k0 = SENT, k1 = SENT;
-    for (int j = lane; j < n; j += 32) {
-        const float kx = kps[j].x, ky = kps[j].y;
-        // PosInGrid (src/Object.cpp:249-257): round(), cells outside [0, 30) are not in the grid at all
-        const int gx = (int)roundf(__fmul_rn(kx, winv)), gy = (int)roundf(__fmul_rn(ky, hinv));
-        if (gx < 0 || gx >= GRID_N || gy < 0 || gy >= GRID_N) continue;
-        if (gx < min_cx || gx > max_cx || gy < min_cy || gy > max_cy) continue;
-        if (!(fabsf(__fsub_rn(kx, x)) < r && fabsf(__fsub_rn(ky, y)) < r)) continue;
-        const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32));
-        const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32 + 16));
-        // candidate order: ix outer, iy inner, ascending keypoint index inside a cell
-        const unsigned long long key = ((unsigned long long)hamming256(a0, a1, b0, b1) << 32) | ((unsigned long long)(gx * GRID_N + gy) << 21) | (unsigned)j;
-        const unsigned long long hi = key > k0 ? key : k0;
-        k1 = k1 < hi ? k1 : hi;
-        k0 = k0 < key ? k0 : key;
+    for (int gx = min_cx; gx <= max_cx; ++gx) {
+        const int pb = cell_start[gx * GRID_N + min_cy], pe = cell_start[gx * GRID_N + max_cy + 1];
+        for (int p = pb + lane; p < pe; p += 32) {
+            const int j = cell_idx[p];
+            const float kx = kps[j].x, ky = kps[j].y;
+            if (!(fabsf(__fsub_rn(kx, x)) < r && fabsf(__fsub_rn(ky, y)) < r)) continue;
+            const int gy = (int)roundf(__fmul_rn(ky, hinv));
+            const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32));
+            const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32 + 16));
+            // candidate order: ix outer, iy inner, ascending keypoint index inside a cell
+            const unsigned long long key = ((unsigned long long)hamming256(a0, a1, b0, b1) << 32) | ((unsigned long long)(gx * GRID_N + gy) << 21) | (unsigned)j;
+            const unsigned long long hi = key > k0 ? key : k0;
+            k1 = k1 < hi ? k1 : hi;
+            k0 = k0 < key ? k0 : key;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -220,11 +278,13 @@ __global__ void __launch_bounds__(256) k_project_match(const mcv_keypoint* __res
 }
 
 int launch_project(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_scale, const float* d_pose,
-                   const float* d_xyz, const uint8_t* d_mp_desc, const int32_t* d_level, int n_mp, float r_th, int32_t* d_idx,
-                   int32_t* d_dist, cudaStream_t s) {
+                   const float* d_xyz, const uint8_t* d_mp_desc, const int32_t* d_level, int n_mp, float r_th, int32_t* d_cell_start,
+                   int32_t* d_cell_idx, int32_t* d_idx, int32_t* d_dist, cudaStream_t s) {
     if (n_mp <= 0) return 0;
-    k_project_match<<<(n_mp + 7) / 8, 256, 0, s>>>(d_kps, d_desc, n, w, h, d_scale, d_pose, d_xyz, d_mp_desc, d_level, n_mp, r_th, d_idx, d_dist);
-    return 1;
+    launch_grid_build(d_kps, n, w, h, d_cell_start, d_cell_idx, s);
+    k_project_match<<<(n_mp + 7) / 8, 256, 0, s>>>(d_kps, d_desc, n, w, h, d_scale, d_pose, d_xyz, d_mp_desc, d_level, n_mp, r_th, d_cell_start, d_cell_idx,
+                                                   d_idx, d_dist);
+    return 2;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -239,7 +299,7 @@ constexpr unsigned long long WM_SENT = 999ull << 32;
 template <typename Gate>
 __device__ __forceinline__ void window_knn2(const mcv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int n, int w, int h, float x,
                                             float y, float r, uint4 a0, uint4 a1, Gate gate, unsigned long long& k0, unsigned long long& k1,
-                                            unsigned& first) {
+                                            unsigned& first, const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_idx) {
     const int lane = threadIdx.x & 31;
     k0 = WM_SENT; k1 = WM_SENT; first = 0xffffffffu;
     bool ok = x >= 0.f && y >= 0.f && x < (float)w && y < (float)h;
@@ -250,21 +310,23 @@ __device__ __forceinline__ void window_knn2(const mcv_keypoint* __restrict__ kps
     const int max_cy = min(GRID_N - 1, (int)ceilf(__fmul_rn(__fadd_rn(y, r), hinv)));
     ok = ok && !(min_cx >= GRID_N || max_cx < 0 || min_cy >= GRID_N || max_cy < 0);
     if (ok) {
-        for (int j = lane; j < n; j += 32) {
-            const float kx = kps[j].x, ky = kps[j].y;
-            const int gx = (int)roundf(__fmul_rn(kx, winv)), gy = (int)roundf(__fmul_rn(ky, hinv));
-            if (gx < 0 || gx >= GRID_N || gy < 0 || gy >= GRID_N) continue;
-            if (gx < min_cx || gx > max_cx || gy < min_cy || gy > max_cy) continue;
-            if (!(fabsf(__fsub_rn(kx, x)) < r && fabsf(__fsub_rn(ky, y)) < r)) continue;
-            if (!gate(j)) continue;
-            const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32));
-            const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32 + 16));
-            const unsigned order = ((unsigned)(gx * GRID_N + gy) << 21) | (unsigned)j;
-            const unsigned long long key = ((unsigned long long)hamming256(a0, a1, b0, b1) << 32) | order;
-            const unsigned long long hi = key > k0 ? key : k0;
-            k1 = k1 < hi ? k1 : hi;
-            k0 = k0 < key ? k0 : key;
-            first = min(first, order);
+        for (int gx = min_cx; gx <= max_cx; ++gx) {
+            const int pb = cell_start[gx * GRID_N + min_cy], pe = cell_start[gx * GRID_N + max_cy + 1];
+            for (int p = pb + lane; p < pe; p += 32) {
+                const int j = cell_idx[p];
+                const float kx = kps[j].x, ky = kps[j].y;
+                if (!(fabsf(__fsub_rn(kx, x)) < r && fabsf(__fsub_rn(ky, y)) < r)) continue;
+                if (!gate(j)) continue;
+                const int gy = (int)roundf(__fmul_rn(ky, hinv));
+                const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32));
+                const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32 + 16));
+                const unsigned order = ((unsigned)(gx * GRID_N + gy) << 21) | (unsigned)j;
+                const unsigned long long key = ((unsigned long long)hamming256(a0, a1, b0, b1) << 32) | order;
+                const unsigned long long hi = key > k0 ? key : k0;
+                k1 = k1 < hi ? k1 : hi;
+                k0 = k0 < key ? k0 : key;
+                first = min(first, order);
+            }
         }
     }
 #pragma unroll
@@ -288,6 +350,7 @@ __global__ void __launch_bounds__(256) k_fuse_match(const mcv_keypoint* __restri
                                                     const float* __restrict__ par, int n_levels, const float* __restrict__ depth_left,
                                                     const float* __restrict__ xyz, const float* __restrict__ normal,
                                                     const uint8_t* __restrict__ mp_desc, const int32_t* __restrict__ mp_level, int n_mp,
+                                                    const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_idx,
                                                     int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (m >= n_mp) return;                                   // warp-uniform
@@ -329,7 +392,7 @@ __global__ void __launch_bounds__(256) k_fuse_match(const mcv_keypoint* __restri
     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(mp_desc + (size_t)m * 32));
     const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(mp_desc + (size_t)m * 32 + 16));
     unsigned long long k0, k1; unsigned first;
-    window_knn2(kps, desc, n, w, h, u, v, 10.f, a0, a1, gate, k0, k1, first);
+    window_knn2(kps, desc, n, w, h, u, v, 10.f, a0, a1, gate, k0, k1, first, cell_start, cell_idx);
     if (!ratio_threshold_pass(k0, k1)) return;
     if (lane == 0) { out_idx[m] = (int)(k0 & 0x1fffffu); out_dist[m] = (int)(k0 >> 32); }
 }
@@ -338,7 +401,8 @@ __global__ void __launch_bounds__(256) k_fuse_match(const mcv_keypoint* __restri
 // index the reference reports (candi_idxs[queryIdx] = the window's FIRST candidate), out_best = the matched candidate.
 __global__ void __launch_bounds__(256) k_wnd_track(const mcv_keypoint* __restrict__ kps1, const uint8_t* __restrict__ desc1,
                                                    const int32_t* __restrict__ q_idx, int n_q, const mcv_keypoint* __restrict__ kps2,
-                                                   const uint8_t* __restrict__ desc2, int n2, int w, int h, int32_t* __restrict__ out_idx,
+                                                   const uint8_t* __restrict__ desc2, int n2, int w, int h,
+                                                   const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_idx, int32_t* __restrict__ out_idx,
                                                    int32_t* __restrict__ out_best, int32_t* __restrict__ out_dist) {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= n_q) return;
@@ -347,25 +411,28 @@ __global__ void __launch_bounds__(256) k_wnd_track(const mcv_keypoint* __restric
     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(desc1 + (size_t)i * 32));
     const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(desc1 + (size_t)i * 32 + 16));
     unsigned long long k0, k1; unsigned first;
-    window_knn2(kps2, desc2, n2, w, h, kps1[i].x, kps1[i].y, 20.f, a0, a1, [](int) { return true; }, k0, k1, first);
+    window_knn2(kps2, desc2, n2, w, h, kps1[i].x, kps1[i].y, 20.f, a0, a1, [](int) { return true; }, k0, k1, first, cell_start, cell_idx);
     if (!ratio_threshold_pass(k0, k1)) return;
     if (lane == 0) { out_idx[q] = (int)(first & 0x1fffffu); out_best[q] = (int)(k0 & 0x1fffffu); out_dist[q] = (int)(k0 >> 32); }
 }
 
 int launch_fuse_match(const mcv_keypoint* d_kps, const uint8_t* d_desc, int n, int w, int h, const float* d_par, int n_levels,
                       const float* d_depth_left, const float* d_xyz, const float* d_normal, const uint8_t* d_mp_desc, const int32_t* d_level,
-                      int n_mp, int32_t* d_idx, int32_t* d_dist, cudaStream_t s) {
+                      int n_mp, int32_t* d_cell_start, int32_t* d_cell_idx, int32_t* d_idx, int32_t* d_dist, cudaStream_t s) {
     if (n_mp <= 0) return 0;
+    launch_grid_build(d_kps, n, w, h, d_cell_start, d_cell_idx, s);
     k_fuse_match<<<(n_mp + 7) / 8, 256, 0, s>>>(d_kps, d_desc, n, w, h, d_par, n_levels, d_depth_left, d_xyz, d_normal, d_mp_desc, d_level, n_mp,
-                                               d_idx, d_dist);
-    return 1;
+                                               d_cell_start, d_cell_idx, d_idx, d_dist);
+    return 2;
 }
 
 int launch_wnd_track(const mcv_keypoint* d_kps1, const uint8_t* d_desc1, const int32_t* d_qidx, int n_q, const mcv_keypoint* d_kps2,
-                     const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_idx, int32_t* d_best, int32_t* d_dist, cudaStream_t s) {
+                     const uint8_t* d_desc2, int n2, int w, int h, int32_t* d_cell_start, int32_t* d_cell_idx, int32_t* d_idx, int32_t* d_best,
+                     int32_t* d_dist, cudaStream_t s) {
     if (n_q <= 0) return 0;
-    k_wnd_track<<<(n_q + 7) / 8, 256, 0, s>>>(d_kps1, d_desc1, d_qidx, n_q, d_kps2, d_desc2, n2, w, h, d_idx, d_best, d_dist);
-    return 1;
+    launch_grid_build(d_kps2, n2, w, h, d_cell_start, d_cell_idx, s);
+    k_wnd_track<<<(n_q + 7) / 8, 256, 0, s>>>(d_kps1, d_desc1, d_qidx, n_q, d_kps2, d_desc2, n2, w, h, d_cell_start, d_cell_idx, d_idx, d_best, d_dist);
+    return 2;
 }
 
 // ---------------------------------------------------------------------------------------------------------
