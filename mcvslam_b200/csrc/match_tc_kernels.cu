@@ -178,16 +178,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
         const int row = quarter * 32 + lane;
         unsigned k0 = TC_SENT, k1 = TC_SENT;
         int thr = -100000;                          // dot product of the current second best: only a strictly larger one can enter
+        // One 32-column chunk of this row. Fast path: four group maxima, one compare. Slow path (some column beats the current
+        // second best): only the groups of eight whose maximum qualifies are walked — a warp takes the slow path when ANY of its
+        // 32 rows qualifies, which on short train walks (5000 rows) is nearly every chunk, so its cost is what matters there
+        // (all 32 columns unconditionally: 5000 x 5000 = 55 us; by groups: see profiles/r02_matching_pipes.md).
         auto scan = [&](const int (&v)[32], int idx0) {
-            int m = v[0];
+            int g[4];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) m = max(m, v[j]);
-            if (m > thr) {
+            for (int i = 0; i < 4; ++i) {
+                g[i] = v[8 * i];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (v[j] > thr && idx0 + j < t_end) {
-                        tc_top2(k0, k1, ((unsigned)((256 - v[j]) >> 1) << TC_IDX_BITS) | (unsigned)(idx0 + j));
-                        if (k1 != TC_SENT) thr = 256 - 2 * (int)(k1 >> TC_IDX_BITS);
+                for (int j = 1; j < 8; ++j) g[i] = max(g[i], v[8 * i + j]);
+            }
+            if (max(max(g[0], g[1]), max(g[2], g[3])) > thr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (g[i] > thr) {
+#pragma unroll
+                        for (int j = 8 * i; j < 8 * i + 8; ++j) {
+                            if (v[j] > thr && idx0 + j < t_end) {
+                                tc_top2(k0, k1, ((unsigned)((256 - v[j]) >> 1) << TC_IDX_BITS) | (unsigned)(idx0 + j));
+                                if (k1 != TC_SENT) thr = 256 - 2 * (int)(k1 >> TC_IDX_BITS);
+                            }
+                        }
                     }
                 }
             }
