@@ -36,6 +36,10 @@ constexpr unsigned TC_B_TILE = TC_N * TC_KB;            // 32 KB per K half
 constexpr unsigned TC_STAGE_BYTES = 2 * TC_B_TILE;
 constexpr unsigned TC_SMEM_BYTES = 2 * TC_A_TILE + TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory per CTA");
+#ifndef MCV_TC_SCAN_GROUP
+#define MCV_TC_SCAN_GROUP 8
+#endif
+constexpr int TC_SCAN_GROUP = MCV_TC_SCAN_GROUP;   // columns per group of the epilogue's slow path
 constexpr int TC_IDX_BITS = 22;            // same key as k_knn2_bf: distance << 22 | trainIdx
 constexpr unsigned TC_SENT = 0xffffffffu;
 
@@ -183,19 +187,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_knn2_tc(const __grid_constant
         // 32 rows qualifies, which on short train walks (5000 rows) is nearly every chunk, so its cost is what matters there
         // (all 32 columns unconditionally: 5000 x 5000 = 55 us; by groups: see profiles/r02_matching_pipes.md).
         auto scan = [&](const int (&v)[32], int idx0) {
-            int g[4];
+            constexpr int GS = TC_SCAN_GROUP, NG = 32 / GS;
+            int g[NG];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                g[i] = v[8 * i];
+            for (int i = 0; i < NG; ++i) {
+                g[i] = v[GS * i];
 #pragma unroll
-                for (int j = 1; j < 8; ++j) g[i] = max(g[i], v[8 * i + j]);
+                for (int j = 1; j < GS; ++j) g[i] = max(g[i], v[GS * i + j]);
             }
-            if (max(max(g[0], g[1]), max(g[2], g[3])) > thr) {
+            int m = g[0];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+            for (int i = 1; i < NG; ++i) m = max(m, g[i]);
+            if (m > thr) {
+#pragma unroll
+                for (int i = 0; i < NG; ++i) {
                     if (g[i] > thr) {
 #pragma unroll
-                        for (int j = 8 * i; j < 8 * i + 8; ++j) {
+                        for (int j = GS * i; j < GS * i + GS; ++j) {
                             if (v[j] > thr && idx0 + j < t_end) {
                                 tc_top2(k0, k1, ((unsigned)((256 - v[j]) >> 1) << TC_IDX_BITS) | (unsigned)(idx0 + j));
                                 if (k1 != TC_SENT) thr = 256 - 2 * (int)(k1 >> TC_IDX_BITS);
