@@ -209,7 +209,8 @@ mcv_status mcv_rig_set_chunk_frames(mcv_rig* r, int chunk_frames);
 
 /* Frame::Frame ORBE + SMatch stages for a batch of n_frames triplets. imgs: [n_frames][3][hgt][w] u8 (L, R, W), host
  * or device. Outputs (host or device): kps [n_frames*3][cap], desc [n_frames*3][cap][32], counts [n_frames*3],
- * u_right / depth_left [n_frames][cap] (Frame::u_right, Frame::depth_left, include/Frame.hpp:44-45; -1 = none). */
+ * u_right / depth_left [n_frames][cap] (Frame::u_right, Frame::depth_left, include/Frame.hpp:44-45; -1 = none). The slots behind
+ * an image's count are defined: zero keypoints / descriptors, -1 in u_right / depth_left. */
 mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, int imgs_on_device,
                            mcv_keypoint* kps_out, uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left,
                            int cap, int out_on_device);

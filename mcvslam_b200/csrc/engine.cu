@@ -1217,6 +1217,7 @@ static mcv_status rig_chunk_enqueue(mcv_rig* r, RigSlot& sl, const uint8_t* d_im
     cudaEvent_t mid = (h->profile && h->prof_calls < PROF_RING) ? h->ev[(size_t)h->prof_calls * (N_STAGES + 1) + 7] : nullptr;
     n += launch_stereo(h->plan, h->pyr.as<uint8_t>(), d_kps, d_desc, d_counts, cap, n_frames, 0, 1, 3, r->prm.bf, r->prm.baseline, d_u_right,
                        d_depth, sl.best_dist.as<int>(), nullptr, sl.st_scratch.p, h->stream, mid);
+    n += launch_fill_tails(d_kps, d_desc, d_counts, cap, 3 * n_frames, d_u_right, d_depth, 3, h->stream);   // slots behind the counts: defined values
     prof_mark(h, 8);
     if (h->profile && h->prof_calls < PROF_RING) ++h->prof_calls;
     MCV_CUDA(cudaGetLastError());

@@ -97,6 +97,8 @@ int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blu
 int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps, const uint8_t* d_desc, const int* d_counts, int cap,
                   int n_frames, int left_cam, int right_cam, int cams_per_frame, float bf, float baseline, float* d_u_right,
                   float* d_depth, int* d_best_dist, int* d_best_r, void* d_scratch, cudaStream_t s, cudaEvent_t mid = nullptr);
+int launch_fill_tails(mcv_keypoint* d_kps, uint8_t* d_desc, const int* d_counts, int cap, int n_images, float* d_u_right, float* d_depth,
+                      int cams_per_frame, cudaStream_t s);
 // bytes of d_scratch (row tables + sorted right-keypoint records) for launch_stereo / launch_stereo_pair
 size_t stereo_scratch_bytes(const Plan& P, int n_frames, int max_right);
 // stereo across two separate pyramids (mcv_stereo_match on two handles): one "frame", explicit pointers

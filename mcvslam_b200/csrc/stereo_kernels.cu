@@ -265,6 +265,29 @@ int launch_stereo(const Plan& P, const uint8_t* d_pyr, const mcv_keypoint* d_kps
     return run_stereo(A, P, n_frames, cap, cap, d_scratch, s, mid);
 }
 
+// Rig outputs are fixed-capacity records (cap slots per image); the slots behind an image's count are defined too: zero
+// keypoints / descriptors, -1 ("none", as Frame::ComputeStereoMatch initialises them, src/Frame.cpp:152-153) for u_right / depth.
+// One CTA per image; a frame's u_right / depth rows are padded by the CTA of its left image.
+__global__ void __launch_bounds__(128) k_fill_tails(mcv_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, const int* __restrict__ counts, int cap,
+                                                    float* __restrict__ u_right, float* __restrict__ depth, int cams_per_frame) {
+    const int img = blockIdx.x, n = min(counts[img], cap);
+    uint32_t* k = reinterpret_cast<uint32_t*>(kps + (size_t)img * cap + n);            // 7 words per keypoint
+    for (int i = threadIdx.x; i < (cap - n) * 7; i += blockDim.x) k[i] = 0u;
+    uint32_t* d = reinterpret_cast<uint32_t*>(desc + ((size_t)img * cap + n) * 32);    // 8 words per descriptor
+    for (int i = threadIdx.x; i < (cap - n) * 8; i += blockDim.x) d[i] = 0u;
+    if (img % cams_per_frame == 0 && u_right) {
+        const size_t f = (size_t)(img / cams_per_frame) * cap;
+        for (int i = n + threadIdx.x; i < cap; i += blockDim.x) { u_right[f + i] = -1.f; depth[f + i] = -1.f; }
+    }
+}
+
+int launch_fill_tails(mcv_keypoint* d_kps, uint8_t* d_desc, const int* d_counts, int cap, int n_images, float* d_u_right, float* d_depth,
+                      int cams_per_frame, cudaStream_t s) {
+    if (n_images <= 0) return 0;
+    k_fill_tails<<<n_images, 128, 0, s>>>(d_kps, d_desc, d_counts, cap, d_u_right, d_depth, cams_per_frame);
+    return 1;
+}
+
 int launch_stereo_pair(const Plan& P, const uint8_t* d_pyr_l, const uint8_t* d_pyr_r, const mcv_keypoint* d_kl, const uint8_t* d_dl, int nl,
                        const mcv_keypoint* d_kr, const uint8_t* d_dr, int nr, float bf, float baseline, float* d_u_right, float* d_depth,
                        int* d_best_dist, int* d_best_r, void* d_scratch, cudaStream_t s) {

@@ -179,9 +179,11 @@ def test_rig_small_chunks_replay_captured_graph(api, oracle):
                 n, k, d = orbs[c].extract(frames[f, c])
                 assert out["counts"][f, c] == n
                 assert out["kps"][f, c, :n].tobytes() == k.tobytes() and out["desc"][f, c, :n].tobytes() == d.tobytes()
+                assert not out["kps"][f, c, n:].view(np.uint8).any() and not out["desc"][f, c, n:].any()      # slots behind the count are zero
                 ks.append(k); ds.append(d)
             n, ur, dp, bd, br = oracle.stereo_match(orbs[0], orbs[1], ks[0], ds[0], ks[1], ds[1], 480, 955.40503, 1.0)
             assert out["u_right"][f, :len(ks[0])].tobytes() == ur.tobytes()
+            assert (out["u_right"][f, len(ks[0]):] == -1).all() and (out["depth_left"][f, len(ks[0]):] == -1).all()
 
     for call in range(5):
         frames = np.stack([synth.triplet(300 + 2 * call), synth.triplet(301 + 2 * call)])
