@@ -61,6 +61,12 @@ KERNEL_NAMES = {"pyramid": "k_copy_level0 + 7 x k_resize_march", "blur": "k_gaus
 I8_DENSE_TOPS = 4500.0    # B200 dense int8 tensor-core peak (NVIDIA's figure; MEASURED_PEAKS.json carries no int8 number)
 
 
+def int8_measured_equiv_tops():
+    """Dense int8 is exactly 2 x bf16 on this chip: twice the MEASURED cuBLAS bf16 burst figure is the measured-equivalent ceiling."""
+    pk = peaks()
+    return 2.0 * float(pk["bf16_tflops"]) if "bf16_tflops" in pk else None
+
+
 def make_frames(n_frames, seed0, w=W, h=H):
     from mcvslam_b200 import synth
     base = [synth.triplet(seed0 + s, w, h) for s in range(min(n_frames, 16))]
@@ -143,7 +149,9 @@ def bench_matching(A, torch, dev, stream):
     path (tcgen05 int8 GEMM of the +-1 expanded descriptors from 2^23 pairs up, the integer-pipe kernel below; 512 int8 ops per pair against the dense int8
     peak) and the integer-pipe kernel (MCV_KNN_POPC=1; 8 popc32 per pair against the live measured xor+popc peak)."""
     peak, _ = A.popc_peak(8192)
-    out = {"unit": "descriptor pairs/s", "popc32_peak_per_s": peak, "popc_peak_source": "mcv_debug_popc_peak (8 independent xor+popc+add chains per thread, whole GPU)",
+    meq = int8_measured_equiv_tops()
+    out = {"unit": "descriptor pairs/s", "int8_measured_equiv_tops": meq,
+           "int8_measured_equiv_source": "2 x MEASURED_PEAKS.json bf16_tflops (cuBLAS burst; int8 dense = 2 x bf16 on B200)", "popc32_peak_per_s": peak, "popc_peak_source": "mcv_debug_popc_peak (8 independent xor+popc+add chains per thread, whole GPU)",
            "int8_peak_tops": I8_DENSE_TOPS, "int8_peak_source": "B200 dense int8 tensor-core figure (no measured int8 peak in MEASURED_PEAKS.json)", "cases": []}
     for name, nq, nt, reps in (("configs[0] 2000x2000", 2000, 2000, 50), ("configs[3] pair 5000x5000", 5000, 5000, 50),
                                ("configs[4] shard 131072x1048576", 131072, 1048576, 3)):
@@ -156,6 +164,7 @@ def bench_matching(A, torch, dev, stream):
         tensor = nq * nt >= 1 << 23        # dispatch rule of launch_knn2_bf (match_tc_kernels.cu: knn2_tc_usable)
         out["cases"].append({"case": name, "ms": sec * 1e3, "pairs_per_s": pairs, "int8_tops": pairs * 512 / 1e12 if tensor else None,
                              "frac_of_int8_peak": pairs * 512 / 1e12 / I8_DENSE_TOPS if tensor else None,
+                             "frac_of_int8_measured_equiv": pairs * 512 / 1e12 / meq if tensor and meq else None,
                              "frac_of_popc_peak": None if tensor else pairs * 8 / peak,
                              "kernel": "k_expand_pm1 + k_knn2_tc (tcgen05.mma kind::i8)" if tensor else "k_knn2_bf + k_knn2_merge (integer pipe: below 2^23 pairs)",
                              "popc_path": {"ms": sec_p * 1e3, "pairs_per_s": pairs_p, "popc32_per_s": pairs_p * 8, "frac_of_popc_peak": pairs_p * 8 / peak,

@@ -98,7 +98,9 @@ def run_c5(args, rank, world, local_rank):
         line["steps"] = steps
         line["roofline"] = {"bound": "tensor", "kernel": "k_knn2_tc (tcgen05.mma kind::i8)", "achieved": tops / world, "peak": Bn.I8_DENSE_TOPS, "unit": "TOP/s (int8, per GPU)",
                             "frac": tops / world / Bn.I8_DENSE_TOPS, "traffic": None, "peak_source": "B200 dense int8 figure (no measured int8 peak in MEASURED_PEAKS.json)",
-                            "algorithmic_ops_per_pair": 512}
+                            "algorithmic_ops_per_pair": 512, "peak_measured_equiv": Bn.int8_measured_equiv_tops(),
+                            "frac_of_measured_equiv": (tops / world / Bn.int8_measured_equiv_tops()) if Bn.int8_measured_equiv_tops() else None,
+                            "peak_measured_equiv_source": "2 x MEASURED_PEAKS.json bf16_tflops (cuBLAS burst): int8 dense = 2 x bf16 on this chip"}
         line["e2e"] = {"value": pairs, "unit": "descriptor pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "note": "descriptors are produced on the device by extraction; the timed region holds the broadcast and the gather"}
         line["gpu_launches"] = 2 * steps
