@@ -114,12 +114,20 @@ def knn2_sharded(q, t, knn2_fn, gather=True, tile=1 << 21):
 
 def merge_top2(idx_a, dist_a, idx_b, dist_b):
     """Lexicographic (distance, index) top-2 of two top-2 tables (n, 2) — the order cv::BFMatcher / the first-party loop
-    produce. -1 entries (distance INT_MAX) lose to everything."""
-    d = torch.cat([dist_a, dist_b], 1).to(torch.int64)
-    i = torch.cat([idx_a, idx_b], 1).to(torch.int64)
-    key = (d << 32) | torch.where(i < 0, torch.full_like(i, 0xFFFFFFFF), i)
-    order = torch.argsort(key, dim=1, stable=True)[:, :2]
-    return torch.gather(i, 1, order).to(torch.int32), torch.gather(d, 1, order).to(torch.int32)
+    produce. -1 entries (distance INT_MAX) lose to everything. A four-element min / max network on packed
+    (distance << 32 | index) keys: elementwise, no sort."""
+    def keys(i, d):
+        i = i.to(torch.int64)
+        return (d.to(torch.int64) << 32) | torch.where(i < 0, torch.full_like(i, 0xFFFFFFFF), i)
+    ka, kb = keys(idx_a, dist_a), keys(idx_b, dist_b)
+    a0, a1 = torch.minimum(ka[:, 0], ka[:, 1]), torch.maximum(ka[:, 0], ka[:, 1])
+    b0, b1 = torch.minimum(kb[:, 0], kb[:, 1]), torch.maximum(kb[:, 0], kb[:, 1])
+    m0 = torch.minimum(a0, b0)
+    m1 = torch.minimum(torch.maximum(a0, b0), torch.minimum(a1, b1))
+    k = torch.stack([m0, m1], 1)
+    i = k & 0xFFFFFFFF
+    i = torch.where(i == 0xFFFFFFFF, torch.full_like(i, -1), i)
+    return i.to(torch.int32), (k >> 32).to(torch.int32)
 
 
 def broadcast_descriptors(t, n_rows, device, src=0):
