@@ -99,6 +99,11 @@ mcv_status mcv_orb_extract(mcv_orb* h, const uint8_t* img, int w, int hgt, size_
  * No seeds on this path. */
 mcv_status mcv_orb_extract_batch(mcv_orb* h, const uint8_t* imgs, int n_images, int w, int hgt, int imgs_on_device,
                                  mcv_keypoint* kps_out, uint8_t* desc_out, int32_t* counts, int cap, int out_on_device);
+/* The same with device-resident inputs and outputs, ASYNCHRONOUS on the handle's stream (the stream given to mcv_orb_create):
+ * only enqueues; order consumers after it on that stream or synchronise it. Lets several handles / streams overlap — the
+ * latency-bound quadtree of one batch beside the stencils of another. */
+mcv_status mcv_orb_extract_batch_async(mcv_orb* h, const uint8_t* d_imgs, int n_images, int w, int hgt, mcv_keypoint* d_kps,
+                                       uint8_t* d_desc, int32_t* d_counts, int cap);
 
 /* mvImagePyramid[level] of image `image_index` of the last extract call (ORBextractor.h:72; read by the stereo SAD,
  * src/Frame.cpp:239-261). Copies the un-bordered level into dst (dst_stride bytes per row); w and hgt receive the level size.

@@ -25,7 +25,7 @@ ORB_GOOD_THRESHOLD = 46  # include/Matcher.hpp:14
 
 EXPORTS = [
     "mcv_last_error", "mcv_version", "mcv_device_count", "mcv_orb_create", "mcv_orb_destroy", "mcv_orb_get_scales",
-    "mcv_orb_max_keypoints", "mcv_orb_max_keypoints_for", "mcv_rig_max_keypoints_for", "mcv_orb_extract", "mcv_orb_extract_batch", "mcv_orb_download_level", "mcv_orb_level_device",
+    "mcv_orb_max_keypoints", "mcv_orb_max_keypoints_for", "mcv_rig_max_keypoints_for", "mcv_orb_extract", "mcv_orb_extract_batch", "mcv_orb_extract_batch_async", "mcv_orb_download_level", "mcv_orb_level_device",
     "mcv_orb_distribute_octree", "mcv_knn2_bf", "mcv_bf_match", "mcv_knn2_firstparty", "mcv_knn2_candidates",
     "mcv_filter_ratio", "mcv_filter_threshold", "mcv_filter_orientation", "mcv_filter_fmatrix", "mcv_dbow_match",
     "mcv_knn2_bf_device", "mcv_knn2_pairs_device", "mcv_rig_create", "mcv_rig_destroy", "mcv_rig_max_keypoints", "mcv_rig_extractor",
@@ -69,6 +69,7 @@ def lib():
         L.mcv_orb_destroy.restype = None
         L.mcv_orb_get_scales.argtypes = [vp] * 6
         L.mcv_orb_max_keypoints.argtypes = [vp, i]
+        L.mcv_orb_extract_batch_async.argtypes = [vp, vp, i, i, i, vp, vp, vp, i]
         L.mcv_orb_max_keypoints_for.argtypes = [vp, i, i, i]
         L.mcv_rig_max_keypoints_for.argtypes = [vp, i, i]
         L.mcv_orb_extract.argtypes = [vp, vp, i, i, sz, vp, i, vp, vp, i, C.POINTER(i)]

@@ -449,6 +449,18 @@ mcv_status mcv_orb_extract_batch(mcv_orb* h, const uint8_t* imgs, int n_images, 
     return MCV_OK;
 }
 
+// Device-resident, asynchronous form of mcv_orb_extract_batch: only enqueues on the handle's stream.
+mcv_status mcv_orb_extract_batch_async(mcv_orb* h, const uint8_t* d_imgs, int n_images, int w, int hgt, mcv_keypoint* d_kps, uint8_t* d_desc,
+                                       int32_t* d_counts, int cap) {
+    if (!h || !d_imgs || n_images <= 0 || !d_kps || !d_desc || !d_counts) return MCV_ERR_BAD_ARG;
+    if (w <= 0 || hgt <= 0) return MCV_ERR_EMPTY_IMAGE;
+    MCV_CUDA(cudaSetDevice(h->device));
+    mcv_status st = ensure_workspace(h, w, hgt, n_images, 1);
+    if (st) return st;
+    if (cap < h->plan.max_quad_kp) { set_error("cap smaller than mcv_orb_max_keypoints_for(w, h)"); return MCV_ERR_CAPACITY; }
+    return enqueue_extract(h, d_imgs, (size_t)w * h->channels, (size_t)w * hgt * h->channels, n_images, nullptr, d_kps, d_desc, d_counts, cap);
+}
+
 mcv_status mcv_orb_level_device(mcv_orb* h, int image_index, int level, const uint8_t** dev_ptr, int* w, int* hgt, size_t* pitch) {
     if (!h || !h->have_plan || image_index < 0 || image_index >= h->last_images || level < 0 || level >= h->plan.n_levels) return MCV_ERR_BAD_ARG;
     const LevelGeom& g = h->plan.lv[level];

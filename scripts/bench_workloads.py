@@ -116,62 +116,83 @@ def run_c4(args, rank, world, local_rank):
     from mcvslam_b200 import shard, synth
     W, H, NF, N_FRAMES, CH = 1280, 720, 5000, 4096, 64
     L = A.lib()
-    stream = torch.cuda.Stream(device=dev)
-    E = A.ORB(NF, 1.2, 8, 28, 15, device=local_rank, stream=stream.cuda_stream)
-    cap = E.max_keypoints(0, W, H)
+    main = torch.cuda.Stream(device=dev)
     pb, pe, fb, fe = shard.consecutive_pairs(N_FRAMES, rank, world)       # this rank's pairs [pb, pe) need frames [fb, fe)
     base = [synth.scene(700 + s, W, H) for s in range(16)]
-    # one chunk of CH frames resident at a time; consecutive chunks overlap by one frame (the pair across the boundary)
+    # one chunk of CH frames resident at a time; consecutive chunks overlap by one frame (the pair across the boundary). Chunks
+    # alternate over TWO extractor handles / streams (like the rig's slots): the latency-bound quadtree of one chunk (level 0 keeps
+    # 1086 of ~4600 candidates: a ~0.9 ms serial heap replay) runs beside the stencils of the next.
     h_chunk = torch.from_numpy(np.stack([base[i % 16] for i in range(CH)])).pin_memory()
-    d_chunk = h_chunk.to(dev)
-    d_kps = torch.empty(CH * cap * 28, dtype=torch.uint8, device=dev); d_desc = torch.empty((CH, cap, 32), dtype=torch.uint8, device=dev)
-    d_cnt = torch.zeros(CH, dtype=torch.int32, device=dev)
     pq = torch.arange(0, CH - 1, dtype=torch.int32, device=dev); pt = pq + 1
-    d_idx = torch.empty((CH - 1, cap, 2), dtype=torch.int32, device=dev); d_dst = torch.empty((CH - 1, cap, 2), dtype=torch.int32, device=dev)
-    h_idx = torch.empty((CH - 1, cap, 2), dtype=torch.int32).pin_memory(); h_dst = torch.empty((CH - 1, cap, 2), dtype=torch.int32).pin_memory()
-    h_cnt = torch.zeros(CH, dtype=torch.int32).pin_memory()
     n_chunks = max(1, -(-(fe - fb - 1) // (CH - 1)))
 
-    def chunk(host):
-        if host:
-            d_chunk.copy_(h_chunk, non_blocking=True)
-        A._check(L.mcv_orb_extract_batch(E._h, d_chunk.data_ptr(), CH, W, H, 1, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, 1))
-        A._check(L.mcv_knn2_pairs_device(d_desc.data_ptr(), d_cnt.data_ptr(), CH, cap, pq.data_ptr(), pt.data_ptr(), CH - 1, d_idx.data_ptr(), d_dst.data_ptr(),
-                                         stream.cuda_stream))
-        if host:
-            h_idx.copy_(d_idx, non_blocking=True); h_dst.copy_(d_dst, non_blocking=True); h_cnt.copy_(d_cnt, non_blocking=True)
+    class Lane:
+        def __init__(self):
+            self.s = torch.cuda.Stream(device=dev)
+            self.E = A.ORB(NF, 1.2, 8, 28, 15, device=local_rank, stream=self.s.cuda_stream)
+            self.cap = self.E.max_keypoints(0, W, H)
+            cap = self.cap
+            self.d_chunk = h_chunk.to(dev)
+            self.d_kps = torch.empty(CH * cap * 28, dtype=torch.uint8, device=dev); self.d_desc = torch.empty((CH, cap, 32), dtype=torch.uint8, device=dev)
+            self.d_cnt = torch.zeros(CH, dtype=torch.int32, device=dev)
+            self.d_idx = torch.empty((CH - 1, cap, 2), dtype=torch.int32, device=dev); self.d_dst = torch.empty((CH - 1, cap, 2), dtype=torch.int32, device=dev)
+            self.h_idx = torch.empty((CH - 1, cap, 2), dtype=torch.int32).pin_memory(); self.h_dst = torch.empty((CH - 1, cap, 2), dtype=torch.int32).pin_memory()
+            self.h_cnt = torch.zeros(CH, dtype=torch.int32).pin_memory()
+
+        def chunk(self, host):
+            with torch.cuda.stream(self.s):
+                if host:
+                    self.d_chunk.copy_(h_chunk, non_blocking=True)
+                A._check(L.mcv_orb_extract_batch_async(self.E._h, self.d_chunk.data_ptr(), CH, W, H, self.d_kps.data_ptr(), self.d_desc.data_ptr(),
+                                                       self.d_cnt.data_ptr(), self.cap))
+                A._check(L.mcv_knn2_pairs_device(self.d_desc.data_ptr(), self.d_cnt.data_ptr(), CH, self.cap, pq.data_ptr(), pt.data_ptr(), CH - 1,
+                                                 self.d_idx.data_ptr(), self.d_dst.data_ptr(), self.s.cuda_stream))
+                if host:
+                    self.h_idx.copy_(self.d_idx, non_blocking=True); self.h_dst.copy_(self.d_dst, non_blocking=True); self.h_cnt.copy_(self.d_cnt, non_blocking=True)
+
+    lanes = [Lane(), Lane()]
+    cap = lanes[0].cap
+    d_cnt, d_desc, d_idx, d_dst, h_idx = lanes[0].d_cnt, lanes[0].d_desc, lanes[0].d_idx, lanes[0].d_dst, lanes[0].h_idx
 
     def job(host):
-        for _ in range(n_chunks):
-            chunk(host)
+        for ln in lanes:
+            ln.s.wait_stream(main)
+        for k in range(n_chunks):
+            lanes[k % 2].chunk(host)
+        for ln in lanes:
+            main.wait_stream(ln.s)
 
-    with torch.cuda.stream(stream):
-        for _ in range(2):
-            chunk(False)
+    with torch.cuda.stream(main):
+        for ln in lanes:
+            ln.chunk(False); ln.chunk(False); ln.chunk(False)
+        job(False)                                                           # one untimed pass over the whole batch (clocks, pools, L2)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
+        PASSES = 3
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream); job(False)
-        tot = d_cnt.sum().reshape(1)
-        if world > 1:
-            dist.all_reduce(tot)                                             # final gather of the result directory
-        e1.record(stream)
+        e0.record(main)
+        for _ in range(PASSES):
+            job(False)
+            tot = d_cnt.sum().reshape(1)
+            if world > 1:
+                dist.all_reduce(tot)                                         # final gather of the result directory
+        e1.record(main)
         torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1) / PASSES
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter(); job(True); torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         e2e_s = time.perf_counter() - t0
-        # share of the step spent matching
+        # share of the step spent matching (one lane alone)
         e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
+        e2.record(main)
         for _ in range(5):
             A._check(L.mcv_knn2_pairs_device(d_desc.data_ptr(), d_cnt.data_ptr(), CH, cap, pq.data_ptr(), pt.data_ptr(), CH - 1, d_idx.data_ptr(), d_dst.data_ptr(),
-                                             stream.cuda_stream))
-        e3.record(stream); torch.cuda.synchronize(dev)
+                                             main.cuda_stream))
+        e3.record(main); torch.cuda.synchronize(dev)
         match_ms = e2.elapsed_time(e3) / 5
     ms, e2e_s = _max_over_ranks(torch, dist, dev, world, [ms, e2e_s])
     line = None
@@ -182,8 +203,10 @@ def run_c4(args, rank, world, local_rank):
         line = _base(args, world, "frames_per_s", "frames/s", v, ms, "configs[3]: batch of 4096 synthetic 1280x720 frames, 5000 ORB x 8 levels x 1.2 each, extract + BF "
                      "Hamming 2-NN between consecutive frames, frames sharded over the GPUs", "strong",
                      {"frames_per_chunk": CH, "chunks_per_gpu": n_chunks, "keypoints_per_frame": kp, "halo": "one frame recomputed per chunk / shard boundary",
+                      "streams": "chunks alternate over two extractor handles / streams",
                       "collective": "all_reduce of the keypoint count (result directory) at the end"})
-        line["steps"] = 1
+        line["steps"] = 3
+        line["warmup"] = 1
         line["seconds_for_4096_frames"] = ms * 1e-3
         line["e2e"] = {"value": N_FRAMES / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h_chunk.numel()) * n_chunks,
                        "d2h_bytes_per_step": int(h_idx.numel() * 8 + CH * 4) * n_chunks, "how": "pinned images in, match tables (idx, dist) and counts out, per chunk"}
