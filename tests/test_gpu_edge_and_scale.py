@@ -196,3 +196,32 @@ def test_rig_small_chunks_replay_captured_graph(api, oracle):
     for call in range(3):
         frames = np.stack([synth.triplet(340 + call)])
         check(frames, rig.process(frames))
+
+
+@pytest.mark.gpu
+def test_extract_batch_async_device_resident(api, oracle):
+    """mcv_orb_extract_batch_async (device in / out, enqueue only on the handle's stream) == the oracle per image; two handles
+    on two streams running concurrently do not disturb each other."""
+    dev = torch.device("cuda", 0)
+    L = api.lib()
+    imgs = [np.stack([synth.scene(400 + 10 * k + i) for i in range(3)]) for k in range(2)]
+    lanes = []
+    for k in range(2):
+        s = torch.cuda.Stream(device=dev)
+        E = api.ORB(2000, 1.2, 8, 28, 15, device=0, stream=s.cuda_stream)
+        cap = E.max_keypoints(0, 640, 480)
+        d_img = torch.from_numpy(imgs[k]).to(dev)
+        d_k = torch.zeros(3 * cap * 28, dtype=torch.uint8, device=dev); d_d = torch.zeros((3, cap, 32), dtype=torch.uint8, device=dev)
+        d_c = torch.zeros(3, dtype=torch.int32, device=dev)
+        lanes.append((s, E, cap, d_img, d_k, d_d, d_c))
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for s, E, cap, d_img, d_k, d_d, d_c in lanes:
+            api._check(L.mcv_orb_extract_batch_async(E._h, d_img.data_ptr(), 3, 640, 480, d_k.data_ptr(), d_d.data_ptr(), d_c.data_ptr(), cap))
+    torch.cuda.synchronize()
+    O = oracle.Orb(2000, 1.2, 8, 28, 15)
+    for k, (s, E, cap, d_img, d_k, d_d, d_c) in enumerate(lanes):
+        cnt = d_c.cpu().numpy(); kps = d_k.cpu().numpy().view(api.KP_DTYPE).reshape(3, cap); desc = d_d.cpu().numpy()
+        for i in range(3):
+            n, ko, do = O.extract(imgs[k][i])
+            assert cnt[i] == n and kps[i, :n].tobytes() == ko.tobytes() and desc[i, :n].tobytes() == do.tobytes(), (k, i)
