@@ -305,9 +305,11 @@ __global__ void __launch_bounds__(32 * OCT_WARPS_MAX) k_octree(const uint32_t* _
 #ifndef MCV_OC_THREADS
 #define MCV_OC_THREADS 128
 #endif
-constexpr int OC_THREADS = MCV_OC_THREADS;   // preparation kernel (data-parallel phases)
+constexpr int OC_THREADS_BATCH = MCV_OC_THREADS;   // preparation kernel (data-parallel phases) when the tasks fill the GPU
+constexpr int OC_THREADS_FEW = 512;                // ... and when there are only a few tasks (one triplet = 24): the task's own latency counts
 constexpr int OR_THREADS = 32;               // replay kernel: one thread replays the heap, the warp picks the survivors' points
 
+template <int OC_THREADS>
 __device__ __forceinline__ int block_excl_scan(int v, int* s_part, int& total) {   // OC_THREADS threads; s_part: OC_THREADS / 32 ints
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = v;
@@ -346,6 +348,7 @@ __device__ __forceinline__ void sort8(uint32_t (&c)[8], uint16_t (&x)[8]) {
 //                  is kept as small as possible — 32 threads and ~7 KB of shared memory per task — and leaves the rest of the
 //                  SM (registers above all: the one-kernel version pinned 64 threads x 48 registers per task for the whole
 //                  replay, 98 % of the register file with all tasks resident) to the other stream's stencils.
+template <int OC_THREADS>
 __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
                                                             uint32_t* __restrict__ arena, uint32_t* __restrict__ scode_all,
                                                             uint16_t* __restrict__ sidx_all, uint16_t* __restrict__ S_all,
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __re
     for (int c = c_lo; c < c_hi; ++c) mine += cnts[c];
     for (int b = tid; b < nb; b += OC_THREADS) cur[b] = 0u;
     int M;
-    int off = block_excl_scan(mine, s_part, M);        // (its barriers also publish the zeroed histogram)
+    int off = block_excl_scan<OC_THREADS>(mine, s_part, M);        // (its barriers also publish the zeroed histogram)
     if (M > 65535) {                                   // 16-bit indices: the legacy kernel takes this task
         if (tid == 0) overflow[task] = 1;
         return;
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __re
         int sum = 0;
         for (int b = b_lo; b < b_hi; ++b) sum += (int)cur[b];
         int tot;
-        int run = block_excl_scan(sum, s_part, tot);
+        int run = block_excl_scan<OC_THREADS>(sum, s_part, tot);
         for (int b = b_lo; b < b_hi; ++b) { const int k = (int)cur[b]; S[b] = (uint16_t)run; cur[b] = (uint32_t)run; run += k; }
         if (tid == 0) S[nb] = (uint16_t)M;
     }
@@ -572,7 +575,8 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     const int di = dev & 15;
     if (!configured[di] || smem > configured_smem[di]) {
         if (smem > 48 * 1024) {
-            cudaFuncSetAttribute(k_octree_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_octree_prep<OC_THREADS_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_octree_prep<OC_THREADS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(k_octree_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         // many small CTAs that live as long as one thread's heap replay: ask for the largest shared-memory carve-out
@@ -584,7 +588,11 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     // bucket prefix sums of every task: behind the sorted-index array (enqueue_extract reserves OCT_S_BYTES per task there)
     uint16_t* d_S = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(d_oct_idx) + (((size_t)P.cand_per_image * n_images * 2 + 255) & ~(size_t)255));
     if ((size_t)nb_pad * 2 > OCT_S_BYTES) return launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, nullptr, s);
-    k_octree_prep<<<tasks, OC_THREADS, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_S, d_overflow, P, n_images, OCT_S_BYTES / 2, r0_words,
+    if (tasks <= 2 * NUM_SMS)
+        k_octree_prep<OC_THREADS_FEW><<<tasks, OC_THREADS_FEW, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_S, d_overflow, P, n_images, OCT_S_BYTES / 2,
+                                                                          r0_words, nb_pad);
+    else
+    k_octree_prep<OC_THREADS_BATCH><<<tasks, OC_THREADS_BATCH, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_S, d_overflow, P, n_images, OCT_S_BYTES / 2, r0_words,
                                                   nb_pad);
     k_octree_replay<<<tasks, OR_THREADS, smem, s>>>(d_arena_a, d_arena_b, d_oct_idx, d_S, d_out_pts, d_out_cnt, d_overflow, P, n_images, OCT_S_BYTES / 2,
                                                     r0_words, heap_alloc);
