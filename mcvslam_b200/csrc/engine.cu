@@ -716,11 +716,14 @@ mcv_status mcv_knn2_bf_device(const uint8_t* d_q, int nq, const uint8_t* d_t, in
     if (nq == 0) return MCV_OK;
     // the partial keys live in a stream-ordered allocation on the CALLER's stream: safe with any stream from any thread
     unsigned* d_part = nullptr;
-    keep_pool_cached();
-    MCV_CUDA(cudaMallocAsync((void**)&d_part, std::max<size_t>(8, knn2_bf_part_bytes(nq, nt)), (cudaStream_t)stream));
+    const size_t part_bytes = knn2_bf_part_bytes(nq, nt);  // 0: the one-launch kernel takes this size, nothing to allocate
+    if (part_bytes) {
+        keep_pool_cached();
+        MCV_CUDA(cudaMallocAsync((void**)&d_part, part_bytes, (cudaStream_t)stream));
+    }
     const int rc = launch_knn2_bf(d_q, nq, d_t, nt, train_offset, d_idx, d_dist, d_part, (cudaStream_t)stream);
     const cudaError_t le = cudaGetLastError();
-    cudaFreeAsync(d_part, (cudaStream_t)stream);
+    if (d_part) cudaFreeAsync(d_part, (cudaStream_t)stream);
     if (rc < 0) { set_error("knn2_bf_device: train set larger than 4M rows per call"); return MCV_ERR_CAPACITY; }
     MCV_CUDA(le);
     return MCV_OK;

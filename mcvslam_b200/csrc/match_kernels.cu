@@ -26,6 +26,15 @@ __device__ __forceinline__ void top2_update(unsigned& k0, unsigned& k1, unsigned
     k0 = min(k0, key);
 }
 
+__device__ __forceinline__ void warp_top2_merge(unsigned& k0, unsigned& k1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned n0 = min(k0, o0), n1 = min(max(k0, o0), min(k1, o1));
+        k0 = n0; k1 = n1;
+    }
+}
+
 // grid = (ceil(nq / BF_THREADS), n_splits). Each CTA scans train rows [split * per_split, ...) for its queries and writes
 // the partial top-2 keys to part[split][q][2].
 __global__ void __launch_bounds__(BF_THREADS) k_knn2_bf(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
@@ -75,6 +84,56 @@ __global__ void __launch_bounds__(256) k_knn2_merge(const unsigned* __restrict__
     dist[2 * qi + 1] = k1 == BF_SENT ? 0x7fffffff : (int)(k1 >> BF_IDX_BITS);
 }
 
+// Mid-sized problems (one image against another: 2000 x 2000) in ONE launch: a warp per query, 16 queries per CTA, the train set
+// streamed through shared memory 256 rows at a time (the next tile's global load is in flight while the current one is scanned),
+// lane l takes rows l, l + 32, ...; the warp's 32 partial top-2 pairs are merged by shuffles and lane 0 writes the result. With
+// k_knn2_bf such a call is 128 CTAs of one warp per scheduler plus a merge launch (22.7 us at 2000 x 2000, 31 % of the POPC peak).
+constexpr int WQ_WARPS = 16;
+constexpr int WQ_TILE = 256;
+
+__global__ void __launch_bounds__(32 * WQ_WARPS) k_knn2_wq(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
+                                                           int train_offset, int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
+    __shared__ uint4 s_lo[WQ_TILE], s_hi[WQ_TILE];         // the two halves of a row apart: consecutive rows are 16 bytes apart
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int qi = blockIdx.x * WQ_WARPS + (tid >> 5);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (qi < nq) {
+        a0 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)qi * 32));
+        a1 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)qi * 32 + 16));
+    }
+    const uint4* t4 = reinterpret_cast<const uint4*>(t);
+    unsigned k0 = BF_SENT, k1 = BF_SENT;
+    uint4 pre = tid < 2 * min(WQ_TILE, nt) ? __ldg(t4 + tid) : make_uint4(0, 0, 0, 0);
+    for (int base = 0; base < nt; base += WQ_TILE) {
+        const int n = min(WQ_TILE, nt - base);
+        __syncthreads();                                   // the previous tile has been scanned
+        ((tid & 1) ? s_hi : s_lo)[tid >> 1] = pre;
+        __syncthreads();
+        const int nb = base + WQ_TILE;
+        if (nb < nt && tid < 2 * min(WQ_TILE, nt - nb)) pre = __ldg(t4 + (size_t)nb * 2 + tid);
+#pragma unroll 4
+        for (int j = lane; j < n; j += 32) {
+            const unsigned d = (unsigned)hamming256(a0, a1, s_lo[j], s_hi[j]);
+            top2_update(k0, k1, (d << BF_IDX_BITS) + (unsigned)(base + j));
+        }
+    }
+    warp_top2_merge(k0, k1);
+    if (lane == 0 && qi < nq) {
+        const unsigned mask = (1u << BF_IDX_BITS) - 1;
+        idx[2 * qi] = k0 == BF_SENT ? -1 : (int)(k0 & mask) + train_offset;
+        dist[2 * qi] = k0 == BF_SENT ? 0x7fffffff : (int)(k0 >> BF_IDX_BITS);
+        idx[2 * qi + 1] = k1 == BF_SENT ? -1 : (int)(k1 & mask) + train_offset;
+        dist[2 * qi + 1] = k1 == BF_SENT ? 0x7fffffff : (int)(k1 >> BF_IDX_BITS);
+    }
+}
+
+// the one-launch kernel pays when a warp's share of the train set is short (measured against the split + merge pair:
+// scripts/r03/match_small.py); from 2^23 pairs up the tensor-core path takes over
+static bool wq_usable(int nq, int nt) {
+    if (getenv("MCV_KNN_NO_WQ")) return false;             // comparison runs only (scripts/r03/match_small.py); read per call
+    return nq >= 16 * WQ_WARPS && nt <= 4096 && (long long)nq * nt < (1 << 23);   // its time grows with nt alone: ~4 us + 5.2 ns per train row
+}
+
 // Split geometry of one brute-force call: enough CTAs for ~4 per SM, but at least BF_TILE train rows each.
 static void bf_splits(int nq, int nt, int& q_blocks, int& n_splits, int& per_split) {
     q_blocks = (nq + BF_THREADS - 1) / BF_THREADS;
@@ -93,6 +152,7 @@ static bool force_popc() {
 size_t knn2_bf_part_bytes(int nq, int nt) {
     if (nq <= 0) return 0;
     if (!force_popc() && knn2_tc_usable(nq, nt)) return knn2_tc_scratch_bytes(nq, nt, nq, nt, 1);
+    if (wq_usable(nq, nt)) return 0;                       // one launch, no partial keys
     int q_blocks, n_splits, per_split;
     bf_splits(nq, nt, q_blocks, n_splits, per_split);
     return (size_t)n_splits * nq * 2 * sizeof(unsigned);
@@ -102,9 +162,14 @@ size_t knn2_bf_part_bytes(int nq, int nt) {
 int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int train_offset, int32_t* d_idx, int32_t* d_dist, unsigned* d_part,
                    cudaStream_t s) {
     if (nq <= 0) return 0;
-    if (nt > (1 << BF_IDX_BITS) || !d_part) return -1;
-    if (!force_popc() && knn2_tc_usable(nq, nt))
-        return launch_knn2_tc(d_q, nq, d_t, nt, train_offset, d_idx, d_dist, d_part, 0, nullptr, nullptr, nullptr, 1, s);
+    if (nt > (1 << BF_IDX_BITS)) return -1;
+    const bool tc = !force_popc() && knn2_tc_usable(nq, nt);
+    if (!d_part && (tc || !wq_usable(nq, nt))) return -1;
+    if (tc) return launch_knn2_tc(d_q, nq, d_t, nt, train_offset, d_idx, d_dist, d_part, 0, nullptr, nullptr, nullptr, 1, s);
+    if (wq_usable(nq, nt)) {
+        k_knn2_wq<<<(nq + WQ_WARPS - 1) / WQ_WARPS, 32 * WQ_WARPS, 0, s>>>(d_q, nq, d_t, nt, train_offset, d_idx, d_dist);
+        return 1;
+    }
     int q_blocks, n_splits, per_split;
     bf_splits(nq, nt, q_blocks, n_splits, per_split);
     k_knn2_bf<<<dim3(q_blocks, n_splits), BF_THREADS, 0, s>>>(d_q, nq, d_t, nt, per_split, d_part);
@@ -115,15 +180,6 @@ int launch_knn2_bf(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t
 // ---------------------------------------------------------------------------------------------------------
 // candidate lists: one warp per query
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_top2_merge(unsigned& k0, unsigned& k1) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
-        const unsigned n0 = min(k0, o0), n1 = min(max(k0, o0), min(k1, o1));
-        k0 = n0; k1 = n1;
-    }
-}
-
 __global__ void __launch_bounds__(256) k_knn2_candidates(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t,
                                                          const int32_t* __restrict__ off, const int32_t* __restrict__ cidx,
                                                          int32_t* __restrict__ idx, int32_t* __restrict__ dist) {

@@ -15,7 +15,10 @@ def _eq_dm(a, b, fields=("queryIdx", "trainIdx", "imgIdx", "distance")):
 
 
 @pytest.mark.parametrize("nq,nt,low", [(2000, 2000, False), (300, 500, True), (1, 2001, False), (129, 1, False), (5, 0, False),
-                                       (1000, 70000, True)])
+                                       (1000, 70000, True),
+                                       # the one-launch warp-per-query kernel (nq >= 256, nt <= 4096, < 2^23 pairs): ragged tiles, ties, nt in {0, 1}
+                                       (1024, 257, True), (500, 4096, True), (2047, 4095, False), (4000, 2000, False), (1025, 1, False), (1030, 0, False), (256, 513, True),
+                                       (2000, 2000, True)])
 def test_knn2_bf(api, oracle, nq, nt, low):
     q = synth.descriptors(nq, 1, low); t = synth.descriptors(nt, 2, low)
     if low:
