@@ -1289,22 +1289,50 @@ static mcv_status rig_chunk(mcv_rig* r, RigSlot& sl, const uint8_t* d_imgs, int 
 
 // Host-buffer path: per chunk H2D -> kernels -> D2H on the slot's stream (all asynchronous), chunks rotating over the slots.
 static mcv_status rig_enqueue_host(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, int imgs_on_device, mcv_keypoint* kps_out,
-                                   uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device, int chunk, int n_slots) {
+                                   uint8_t* desc_out, int32_t* counts, float* u_right, float* depth_left, int cap, int out_on_device, int chunk, int n_slots,
+                                   const std::vector<int>* plan = nullptr) {
     const size_t img3 = (size_t)3 * w * hgt * r->slot[0].orb->channels, kb = sizeof(mcv_keypoint);
     int launches = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    size_t pi = 0;
+#ifdef MCV_EXPERIMENTS
+    // MCV_RIG_TRACE=1 (experiment builds): per chunk the times its H2D started / ended, its kernels ended and its D2H ended,
+    // relative to the first chunk's start — printed by the next call
+    static const bool trace = getenv("MCV_RIG_TRACE") != nullptr;
+    static std::vector<cudaEvent_t> tev;
+    static std::vector<int> tnf;
+    if (trace && !tev.empty()) {
+        cudaDeviceSynchronize();
+        for (size_t c = 0; c < tnf.size(); ++c) {
+            float a, b, k, d;
+            cudaEventElapsedTime(&a, tev[0], tev[4 * c]); cudaEventElapsedTime(&b, tev[0], tev[4 * c + 1]);
+            cudaEventElapsedTime(&k, tev[0], tev[4 * c + 2]); cudaEventElapsedTime(&d, tev[0], tev[4 * c + 3]);
+            fprintf(stderr, "chunk %zu (%d frames): h2d %.3f-%.3f kernels -%.3f d2h -%.3f ms\n", c, tnf[c], a, b, k, d);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        tev.clear(); tnf.clear();
+    }
+    auto mark = [&](cudaStream_t st_) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st_); tev.push_back(e); } };
+#else
+    auto mark = [&](cudaStream_t) {};
+#endif
+    for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf) {
         RigSlot& sl = r->slot[r->next_slot % n_slots];
         r->next_slot = (r->next_slot + 1) % n_slots;
         cudaStream_t s = sl.orb->stream;
-        const int nf = std::min(chunk, n_frames - f0);
+        nf = std::min(plan && pi < plan->size() ? (*plan)[pi++] : chunk, n_frames - f0);
         const size_t n_img = (size_t)3 * nf;
         mcv_status st;
         const uint8_t* d_imgs = imgs + f0 * img3;
+        mark(s);
+#ifdef MCV_EXPERIMENTS
+        if (trace) tnf.push_back(nf);
+#endif
         if (!imgs_on_device) {
             if ((st = sl.imgs.reserve(img3 * nf))) return st;
             MCV_CUDA(cudaMemcpyAsync(sl.imgs.p, imgs + f0 * img3, img3 * nf, cudaMemcpyHostToDevice, s));
             d_imgs = sl.imgs.as<uint8_t>();
         }
+        mark(s);
         mcv_keypoint* d_kps = kps_out + (size_t)3 * f0 * cap; uint8_t* d_desc = desc_out + (size_t)3 * f0 * cap * 32;
         int* d_counts = counts + 3 * f0; float* d_ur = u_right + (size_t)f0 * cap; float* d_dp = depth_left + (size_t)f0 * cap;
         if (!out_on_device) {
@@ -1318,6 +1346,7 @@ static mcv_status rig_enqueue_host(mcv_rig* r, const uint8_t* imgs, int n_frames
         }
         st = rig_chunk(r, sl, d_imgs, nf, w, hgt, d_kps, d_desc, d_counts, d_ur, d_dp, cap, &launches);
         if (st) return st;
+        mark(s);
         if (!out_on_device) {
             MCV_CUDA(cudaMemcpyAsync(kps_out + (size_t)3 * f0 * cap, d_kps, n_img * cap * kb, cudaMemcpyDeviceToHost, s));
             MCV_CUDA(cudaMemcpyAsync(desc_out + (size_t)3 * f0 * cap * 32, d_desc, n_img * cap * 32, cudaMemcpyDeviceToHost, s));
@@ -1325,6 +1354,7 @@ static mcv_status rig_enqueue_host(mcv_rig* r, const uint8_t* imgs, int n_frames
             MCV_CUDA(cudaMemcpyAsync(u_right + (size_t)f0 * cap, d_ur, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
             MCV_CUDA(cudaMemcpyAsync(depth_left + (size_t)f0 * cap, d_dp, (size_t)nf * cap * 4, cudaMemcpyDeviceToHost, s));
         }
+        mark(s);
     }
     r->last_launches = launches;
     return MCV_OK;
@@ -1505,6 +1535,8 @@ mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w,
     }
     // host side involved: per-chunk H2D -> kernels -> D2H on the slot's stream, chunks overlapping across slots
     MCV_CUDA(cudaStreamSynchronize(r->stream));
+    r->next_slot = 0;   // every slot is idle here (the call is synchronous): the same chunk of the same call shape always lands on the
+                        // same slot, so its captured graph and its workspace size are reused call after call
     mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, imgs_on_device, kps_out, desc_out, counts, u_right, depth_left, cap,
                                      out_on_device, rig_chunk_size(r, n_frames), r->use_slots);
     if (st) return st;
