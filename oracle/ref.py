@@ -70,6 +70,7 @@ def lib():
         L.ref_obj_features_in_area.argtypes = [vp, f, f, f, vp, i]
         L.ref_project_match.argtypes = [vp, vp, vp, vp, i, f, vp]
         L.ref_voc_load.argtypes = [C.c_char_p]
+        L.ref_voc_save.argtypes = [C.c_char_p]
         L.ref_obj_compute_bow.argtypes = [vp] * 7
         L.ref_distinctive.restype = None
         L.ref_distinctive.argtypes = [vp, vp, vp, i, vp, vp]
@@ -396,6 +397,39 @@ def write_dbow3_binary(voc, path):
 
 def voc_load(path):
     return lib().ref_voc_load(path.encode())
+
+
+def voc_save_uncompressed(path):
+    """Vocabulary::save(path, false) of the vocabulary the reference currently holds (DBoW3's uncompressed binary stream)."""
+    return lib().ref_voc_save(path.encode())
+
+
+def read_dbow3_binary(path):
+    """Inverse of write_dbow3_binary: DBoW3's UNCOMPRESSED binary stream (Vocabulary.cpp:935-1000 toStream) -> the flat arrays
+    mcv_voc_create / oracle.bow_transform take. Children keep the order fromStream gives them (file order)."""
+    raw = np.fromfile(path, np.uint8)
+    import struct
+    sig, = struct.unpack_from("<Q", raw, 0)
+    assert sig == 88877711233 and raw[8] == 0, "not an uncompressed DBoW3 binary vocabulary"
+    n, = struct.unpack_from("<I", raw, 9)
+    k, L, scoring, weighting = struct.unpack_from("<iiii", raw, 13)
+    rec = np.dtype([("nid", "<u4"), ("parent", "<u4"), ("weight", "<f8"), ("cols", "<i4"), ("rows", "<i4"), ("type", "<i4"), ("desc", "u1", 32)])
+    nodes = np.frombuffer(raw, rec, n - 1, 29)
+    assert (nodes["cols"] == 32).all() and (nodes["rows"] == 1).all() and (nodes["type"] == 0).all()
+    off = 29 + (n - 1) * rec.itemsize
+    nw, = struct.unpack_from("<I", raw, off)
+    words = np.frombuffer(raw, np.dtype([("wid", "<u4"), ("nid", "<u4")]), nw, off + 4)
+    node_desc = np.zeros((n, 32), np.uint8); node_desc[nodes["nid"]] = nodes["desc"]
+    weight = np.zeros(n, np.float64); weight[nodes["nid"]] = nodes["weight"]
+    word_id = np.full(n, -1, np.int32); word_id[words["nid"]] = words["wid"].astype(np.int32)
+    # children of every node in file order: a stable sort by parent keeps it
+    order = np.argsort(nodes["parent"], kind="stable")
+    child_ids = nodes["nid"][order].astype(np.uint32)
+    child_off = np.zeros(n + 1, np.int32)
+    np.cumsum(np.bincount(nodes["parent"], minlength=n), out=child_off[1:])
+    norm = {0: 1, 1: 2, 2: 1, 3: 1, 4: 1, 5: 0}[int(scoring)]   # ScoringObject.h:73-88: L1, L2, CHI_SQUARE / KL / BHATTACHARYYA (L1), DOT_PRODUCT (none)
+    return dict(child_off=child_off, child_ids=child_ids, node_desc=node_desc, word_id=word_id, weight=weight, L=int(L), K=int(k),
+                weighting=int(weighting), norm=norm, scoring=int(scoring))
 
 
 def distinctive(orb, desc, off):

@@ -280,6 +280,9 @@ int ref_project_match(void* o, const float* mp_xyz, const uint8_t* mp_desc, cons
 }
 // DBoW3 vocabulary through DBoW3's own binary loader (Vocabulary::load -> fromStream), then Object::ComputeBow.
 int ref_voc_load(const char* path) { try { Object::voc.load(std::string(path)); } catch (std::exception& e) { fprintf(stderr, "ref_voc_load: %s\n", e.what()); return -1; } catch (std::string& e) { fprintf(stderr, "ref_voc_load: %s\n", e.c_str()); return -1; } return (int)Object::voc.size(); }
+// the loaded vocabulary written back by DBoW3's own Vocabulary::save as the UNCOMPRESSED binary stream (toStream): how the test
+// side gets at the shipped, quicklz-compressed Vocabulary/orbvoc.dbow3 without a second decompressor
+int ref_voc_save(const char* path) { try { Object::voc.save(std::string(path), false); } catch (std::exception& e) { fprintf(stderr, "ref_voc_save: %s\n", e.what()); return -1; } catch (std::string& e) { fprintf(stderr, "ref_voc_save: %s\n", e.c_str()); return -1; } return 0; }
 // returns BowVector size; bow_ids / bow_vals [<= n]; FeatureVector flattened: fv_nodes, fv_off [n_fv + 1], fv_idx
 int ref_obj_compute_bow(void* o, unsigned* bow_ids, double* bow_vals, unsigned* fv_nodes, int* fv_off, int* fv_idx, int* n_fv) {
     ObjectRef obj = ((ObjBox*)o)->obj;

@@ -218,6 +218,17 @@ def test_wnd_track(api, oracle):
 
 
 @pytest.mark.gpu
+def test_bow_transform_on_the_shipped_vocabulary(api):
+    """Object::ComputeBow on the reference's own vocabulary (the part of Vocabulary/orbvoc.dbow3 the fixture's descriptors walk
+    through) against what the reference's DBoW3 computed: tests/golden/voc_golden.npz, made by tests/golden/make_voc_golden.py."""
+    from test_oracle_golden import _voc_fixture
+    voc, desc, exp = _voc_fixture()
+    g = api.Vocabulary(voc).transform(desc, 4)
+    assert np.array_equal(g["bow_ids"], exp["bow_ids"]) and g["bow_vals"].tobytes() == exp["bow_vals"].tobytes()
+    assert np.array_equal(g["fv_nodes"], exp["fv_nodes"]) and np.array_equal(g["fv_off"], exp["fv_off"]) and np.array_equal(g["fv_idx"], exp["fv_idx"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("weighting,norm,K,L,levelsup", [(0, 1, 10, 4, 2), (0, 2, 10, 3, 1), (1, 0, 8, 3, 4), (2, 1, 10, 4, 3), (3, 0, 33, 2, 1)])
 def test_bow_transform(api, oracle, weighting, norm, K, L, levelsup):
     """Object::ComputeBow = DBoW3 Vocabulary::transform (modules/DBow3/src/Vocabulary.cpp:572-672): words, nodes, and the two

@@ -346,6 +346,27 @@ def test_compute_bow_equals_reference(oracle, ref, weighting, norm, tmp_path):
     assert np.array_equal(r["fv_nodes"], o["fv_nodes"]) and np.array_equal(r["fv_off"], o["fv_off"]) and np.array_equal(r["fv_idx"], o["fv_idx"])
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/Vocabulary/orbvoc.dbow3"), reason="the shipped vocabulary lives in /root/reference")
+def test_compute_bow_on_the_shipped_vocabulary(oracle, ref, tmp_path):
+    """The WHOLE Vocabulary/orbvoc.dbow3 (971 814 words, quicklz-compressed) through DBoW3's own loader; the oracle gets the same
+    tree as flat arrays (Vocabulary::save uncompressed -> ref.read_dbow3_binary); 2000 real ORB descriptors + random ones."""
+    try:
+        assert ref.voc_load("/root/reference/Vocabulary/orbvoc.dbow3") == 971814
+        assert ref.voc_save_uncompressed(str(tmp_path / "full.bin")) == 0
+        voc = ref.read_dbow3_binary(str(tmp_path / "full.bin"))
+        assert voc["K"] == 10 and voc["L"] == 6 and voc["weighting"] == 0 and voc["norm"] == 1 and len(voc["word_id"]) == 1082073
+        n, k, d = oracle.Orb(2000, 1.2, 8, 28, 15).extract(synth.scene(31))
+        d = np.concatenate([d, synth.descriptors(300, 4)])
+        r = ref.Obj(ref.Orb(), np.zeros(len(d), oracle.KP_DTYPE), d, 640, 480).compute_bow()
+        o = oracle.bow_transform(d, voc, 4)
+        assert len(r["bow_ids"]) > 1500
+        assert np.array_equal(r["bow_ids"], o["bow_ids"]) and r["bow_vals"].tobytes() == o["bow_vals"].tobytes()
+        assert np.array_equal(r["fv_nodes"], o["fv_nodes"]) and np.array_equal(r["fv_off"], o["fv_off"]) and np.array_equal(r["fv_idx"], o["fv_idx"])
+    finally:
+        small = synth.random_vocabulary(5, K=7, L=4)      # do not leave 1 M nodes in the reference's process-wide Object::voc
+        ref.voc_load(ref.write_dbow3_binary(small, str(tmp_path / "small.dbow3")))
+
+
 def test_distinctive_equals_reference(oracle, ref):
     from test_oracle_golden import _ragged_observations
     sizes = [0, 1, 2, 3, 4, 5, 8, 33, 64, 100, 0, 7]
