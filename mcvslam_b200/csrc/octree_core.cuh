@@ -153,56 +153,77 @@ OCT_HD void heap_push(uint32_t* h, int& size, uint32_t value) {
     h[hole] = value;
 }
 
-// std::pop_heap + pop_back (bits/stl_heap.h __pop_heap -> __adjust_heap -> __push_heap), restated TOP-DOWN.
-// libstdc++ moves the hole from the root to a leaf along the larger-child path (comp(right, left) ? left : right, decided by the two
-// children alone), then bubbles the displaced last element `value` up that same path while parent < value. Counts never increase
-// along a root-to-leaf path, so "bubble up while parent < value" ends exactly where a descent that moves the chosen child up while
-// !(child < value) ends: the final array is the same, element for element, ties included — but the descent never goes back up
-// (it can stop early, and successive pops can follow each other down the tree: drain_step below).
-// One level of one pop: `hole` is the slot to fill, `len` the number of elements that stay (1-based slots 1..len), hb = h - 1.
-// Returns false when the pop is complete (value placed).
-OCT_HD bool pop_step(uint32_t* hb, uint32_t& hole, uint32_t len, uint32_t value) {
-    const uint32_t l = 2u * hole;
-    if (l <= len) {                                       // at least the left child
-        const uint32_t cl = hb[l], cr = hb[l + 1];        // (slot len + 1 exists: it held `value`)
-        const bool right = l < len && !e_less(cr, cl);    // two children and comp(right, left) false: take the right child;
-        const uint32_t c = right ? cr : cl;               // a lone left child is __adjust_heap's "(len & 1) == 0" step
-        if (!e_less(c, value)) { hb[hole] = c; hole = l + (uint32_t)right; return true; }
-    }
-    hb[hole] = value;
-    return false;
-}
-
-// The popped element is left at h[size - 1] like std::pop_heap leaves it, and returned.
+// std::pop_heap + pop_back (bits/stl_heap.h __pop_heap -> __adjust_heap -> __push_heap). The popped element is left at
+// h[size - 1] like std::pop_heap leaves it, and returned. (Fetching grandchildren speculatively, two levels per round trip, was
+// measured on B200 and bought nothing: the single thread is bound by instructions per level, not by the load latency.)
 OCT_HD uint32_t heap_pop(uint32_t* h, int& size) {
-    uint32_t* const hb = h - 1;
-    const uint32_t top = hb[1];
+    const uint32_t top = h[0];
     if (size > 1) {
-        const uint32_t len = (uint32_t)size - 1u;
-        const uint32_t value = hb[size];
-        hb[size] = top;
-        uint32_t hole = 1u;
-        while (pop_step(hb, hole, len, value)) {}
+        const int len = size - 1;
+        const uint32_t value = h[len];
+        h[len] = top;
+        const int lim = (len - 1) >> 1;   // __adjust_heap: nodes below lim have two children
+        // The heap replay runs on ONE thread, where every instruction costs its full dependent-issue latency, so the loop is
+        // written for the shortest dependent chain per level. With hb[i + 1] = h[i] and A = address of the hole's slot, the
+        // hole's children are the 8-byte pair at 2A - hb, and the next hole is that pair's left or right word.
+        int hole;
+#ifdef __CUDA_ARCH__
+        {
+            const uint32_t base = (uint32_t)__cvta_generic_to_shared(h - 1);
+            uint32_t A = base + 4u;                          // hb[1] = h[0]
+            const uint32_t A_end = base + 4u * (uint32_t)lim;    // hole < lim  <=>  A <= A_end
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p, q;\n\t"
+                ".reg .u32 pa, pb, l, r, t, v, nb;\n\t"
+                "neg.s32 nb, %2;\n\t"
+                "setp.gt.u32 q, %0, %1;\n\t"
+                "@q bra OCT_SIFT_DONE_%=;\n"
+                "OCT_SIFT_LOOP_%=:\n\t"
+                "mad.lo.u32 pa, %0, 2, nb;\n\t"            // left child slot
+                "add.u32 pb, pa, 4;\n\t"
+                "ld.shared.v2.u32 {l, r}, [pa];\n\t"
+                "or.b32 t, r, 0xffff;\n\t"
+                "setp.lt.u32 p, t, l;\n\t"                 // comp(right, left): take the left child
+                "selp.u32 v, l, r, p;\n\t"
+                "st.shared.u32 [%0], v;\n\t"
+                "selp.u32 %0, pa, pb, p;\n\t"
+                "setp.le.u32 q, %0, %1;\n\t"
+                "@q bra OCT_SIFT_LOOP_%=;\n"
+                "OCT_SIFT_DONE_%=:\n\t"
+                "}"
+                : "+r"(A) : "r"(A_end), "r"(base) : "memory");
+            hole = (int)((A - base) >> 2) - 1;
+        }
+#else
+        {
+            uint32_t* const hb = h - 1;
+            int H = 1;
+            while (H <= lim) {
+                const Pair2 p = load2(hb, 2 * H);
+                const bool r = !e_less(p.y, p.x);         // comp(right, left) false: take the right child
+                hb[H] = r ? p.y : p.x;
+                H = 2 * H + (int)r;
+            }
+            hole = H - 1;                                 // == "secondChild" of __adjust_heap after every step
+        }
+#endif
+        if ((len & 1) == 0 && hole == ((len - 2) >> 1)) {
+            const int c = 2 * (hole + 1);
+            h[hole] = h[c - 1];
+            hole = c - 1;
+        }
+        while (hole > 0) {
+            const int parent = (hole - 1) >> 1;
+            const uint32_t pv = h[parent];
+            if (!e_less(pv, value)) break;
+            h[hole] = pv;
+            hole = parent;
+        }
+        h[hole] = value;
     }
     --size;
     return top;
-}
-
-// ---- drain (ORBextractor.cc:568-578: pop everything) as a pipeline of pops ----
-// Pop k + 1 may enter the tree two levels behind pop k: in one step a pop reads the level below its hole and writes its hole, so
-// with a distance of two levels no pop reads a slot another one writes in the same step, and everything a pop reads was final
-// one step earlier. The one thing a younger pop takes from the BOTTOM of the heap is its `value` (the last live element, slot p):
-// it may only start while no older pop in flight can still write slot p, i.e. while no older hole is an ancestor of p (or p).
-OCT_HD int depth_of(uint32_t slot) {   // 1-based slot: root = depth 0
-#ifdef __CUDA_ARCH__
-    return 31 - __clz((int)slot);
-#else
-    return 31 - __builtin_clz(slot);
-#endif
-}
-OCT_HD bool is_ancestor_or_self(uint32_t hole, uint32_t p) {
-    const int dh = depth_of(hole), dp = depth_of(p);
-    return dp >= dh && (p >> (dp - dh)) == hole;
 }
 
 // start of a node's range in the sorted arrays
@@ -212,12 +233,11 @@ OCT_HD int node_lo(uint32_t node, const ST* S, int T) {
     return d <= T ? (int)S[n_x(node) << (2 * (T - d))] : (int)n_x(node);
 }
 
-// The serial part, split loop (ORBextractor.cc:549-565): roots, then "pop the most populated node, push its non-empty sons".
-// `scode` = path codes sorted ascending (only deep nodes read it), `S` = exclusive prefix sums of the bucket histogram
-// (n_ini << 2T entries + 1). Returns the heap size it ends with; the heap (count << 16 | id, node description in nodes[id]) is
-// left in h[0, size).
+// The serial part (ORBextractor.cc:549-578): roots, split loop, drain. `scode` = path codes sorted ascending (only deep nodes
+// read it), `S` = exclusive prefix sums of the bucket histogram (n_ini << 2T entries + 1). Returns the number of final nodes; the i-th popped node
+// (= i-th output keypoint) is left at heap[total - 1 - i] (count << 16 | id, node description in nodes[id]).
 template <typename ST>
-OCT_HD int replay_split(const uint32_t* scode, const ST* S, const Geom& g, uint32_t* heap, uint32_t* nodes) {
+OCT_HD int replay(const uint32_t* scode, const ST* S, const Geom& g, uint32_t* heap, uint32_t* nodes, long long* clk_split_done = nullptr) {
     const int T = g.T;
     int size = 0, n_nodes = 0;
     for (int r = 0; r < g.n_ini; ++r) {   // ORBextractor.cc:549-555: empty roots are dropped
@@ -234,7 +254,7 @@ OCT_HD int replay_split(const uint32_t* scode, const ST* S, const Geom& g, uint3
         const uint32_t node = nodes[id];
         const int d = n_depth(node);
         if (d >= DIGITS) break;
-        // the child counts depend on the popped node alone: their loads are issued before the pop's dependent descent
+        heap_pop(heap, size);
         uint32_t c0, c1, c2, c3, x0, xs;   // child counts; child k's X = x0 + k * xs (table) or running range start (deep)
         if (d < T) {
             const int sh = 2 * (T - 1 - d);
@@ -251,39 +271,24 @@ OCT_HD int replay_split(const uint32_t* scode, const ST* S, const Geom& g, uint3
             c0 = (uint32_t)acc & 0xffffu; c1 = (uint32_t)(acc >> 16) & 0xffffu; c2 = (uint32_t)(acc >> 32) & 0xffffu; c3 = (uint32_t)(acc >> 48);
             xs = 0;
         }
-        heap_pop(heap, size);
-        // sons in DivideNode's order n1..n4 (ORBextractor.cc:516-519); the popped node's slot is reused by the first one.
-        // A son that is not larger than its parent slot's element stays where push_back put it: the (up to three) parent slots of
-        // the four new leaves are fetched together, and only a son that has to climb takes the step-by-step __push_heap (after
-        // which the prefetched parents are stale for the rest of this iteration).
-        bool reuse = true, fresh = size >= 4;
+        // sons in DivideNode's order n1..n4 (ORBextractor.cc:516-519); the popped node's slot is reused by the first one
+        bool reuse = true;
         uint32_t at = x0;
-        const int q = (size - 1) >> 1;                    // parent slot (0-based) of leaf `size`; leaves size..size+3 -> q..q+2
-        const uint32_t par0 = fresh ? heap[q] : 0u, par1 = fresh ? heap[q + 1] : 0u, par2 = fresh ? heap[q + 2] : 0u;
 #define OCT_PUSH_SON(ck, k)                                                     \
         if (ck) {                                                               \
             const uint32_t nid = reuse ? id : (uint32_t)n_nodes++;              \
             reuse = false;                                                      \
             nodes[nid] = make_node(d + 1, xs ? x0 + k : at);                    \
-            const uint32_t v = ((ck) << 16) | nid;                              \
-            const int pq = ((size - 1) >> 1) - q;                               \
-            const uint32_t par = pq == 0 ? par0 : pq == 1 ? par1 : par2;        \
-            if (fresh && !e_less(par, v)) heap[size++] = v;                     \
-            else { heap_push(heap, size, v); fresh = false; }                   \
+            heap_push(heap, size, ((ck) << 16) | nid);                          \
         }                                                                       \
         at += ck;
         OCT_PUSH_SON(c0, 0) OCT_PUSH_SON(c1, 1) OCT_PUSH_SON(c2, 2) OCT_PUSH_SON(c3, 3)
 #undef OCT_PUSH_SON
     }
-    return size;
-}
-
-// Split loop + serial drain (the CPU form; the kernel drains with the pipelined pops of drain_step). Returns the number of final
-// nodes; the i-th popped node (= i-th output keypoint) is left at heap[total - 1 - i].
-template <typename ST>
-OCT_HD int replay(const uint32_t* scode, const ST* S, const Geom& g, uint32_t* heap, uint32_t* nodes) {
-    int size = replay_split(scode, S, g, heap, nodes);
     const int total = size;
+#ifdef __CUDA_ARCH__
+    if (clk_split_done) *clk_split_done = clock64();
+#endif
     while (size > 0) heap_pop(heap, size);
     return total;
 }

@@ -343,15 +343,18 @@ __device__ __forceinline__ void sort8(uint32_t (&c)[8], uint16_t (&x)[8]) {
 //  k_octree_prep   (OC_THREADS threads): gather in reference order, path codes, counting sort by depth-T bucket, per-bucket
 //                  sort; leaves `arena` (candidates in reference order), `scode` / `sidx` (path codes and original indices
 //                  sorted by code) and the bucket prefix sums S (u16 x nb_pad per task) in global memory (L2-resident).
-//  k_octree_replay (one warp): S into shared memory, thread 0 replays the split loop on counts (oct::replay_split), the warp drains
-//                  the final heap as a pipeline of top-down pops two levels apart (drain_pipelined) and picks every surviving
-//                  node's first-maximum-response point. This kernel lasts as long as its longest heap replay, so it
+//  k_octree_replay (one warp): S into shared memory, thread 0 replays the heap on counts (octree_core.cuh), the warp picks every
+//                  surviving node's first-maximum-response point. This kernel lasts as long as its longest heap replay, so it
 //                  is kept as small as possible — 32 threads and ~7 KB of shared memory per task — and leaves the rest of the
 //                  SM (registers above all: the one-kernel version pinned 64 threads x 48 registers per task for the whole
 //                  replay, 98 % of the register file with all tasks resident) to the other stream's stencils.
-//                  Measured on the level-0 task of a 640x480 image (434 nodes, B200, one triplet per call): split loop 285 k
-//                  cycles, drain 279 k (one pop after the other with the bounce-back sift of libstdc++: 312 k), selection 18 k —
-//                  a lone warp issues one dependent instruction every ~6.5 cycles, and that, not memory, is the floor here.
+//                  Measured on the level-0 task of a 640x480 image (434 nodes, B200, one triplet per call, scripts/r03/oct_clocks_b1.py):
+//                  split loop 271 k cycles, drain 312 k, selection 18 k — a lone warp issues one dependent instruction every ~6.5
+//                  cycles, and that, not memory, is the floor. Tried in round 2 and NOT kept (all bit-exact): a top-down pop that
+//                  stops early instead of libstdc++'s sift-to-leaf + bubble-up (same arrays, but more instructions per level than the
+//                  hand-scheduled loop in octree_core.cuh: drain 340 k); pushing sons that stay put without the sift loop (split 284 k);
+//                  a warp-wide drain with pops following each other down the tree two levels apart, one lane each (drain 279 k for one
+//                  task, but more instructions in total: the batched quadtree stage went 0.531 -> 0.549 ms).
 template <int OC_THREADS>
 __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
                                                             uint32_t* __restrict__ arena, uint32_t* __restrict__ scode_all,
@@ -471,53 +474,6 @@ __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __re
     for (int b = tid; b <= nb; b += OC_THREADS) Sg[b] = S[b];
 }
 
-// Drain of the final heap by the whole warp (ORBextractor.cc:568-578), see oct::pop_step: pop k runs on lane k % 32, enters the
-// tree two steps after pop k - 1 and sinks one level per step; out[k] = the k-th popped entry. Every step all lanes in flight
-// advance together, so the heap's levels are worked on concurrently instead of one dependent shared-memory round trip at a time
-// (level 0 of a 640x480 image: 434 pops x ~7 levels, 312 k cycles on one thread).
-__device__ __forceinline__ void drain_pipelined(uint32_t* heap, int n, uint32_t* out, int lane) {
-    uint32_t* const hb = heap - 1;
-    const uint32_t hb_s = (uint32_t)__cvta_generic_to_shared(hb);
-    uint32_t hole = 1, len = 0, value = 0;                 // len == 0: the lane is idle (2 * hole > len, nothing stored)
-    bool active = false;
-    int next = 0, since = 2;                               // next pop to start; steps since the last start (both warp-uniform)
-    while (true) {
-        if (next < n && since >= 2) {
-            const uint32_t size = (uint32_t)(n - next);   // this pop's heap: slots 1..size; its `value` is the element in slot `size`
-            const int up = __clz((int)hole) - __clz((int)size);                   // depth(size) - depth(hole)
-            const bool hazard = active && up >= 0 && (size >> up) == hole;       // an older pop may still write that slot
-            if (!__any_sync(0xffffffffu, hazard)) {
-                if (lane == (next & 31)) {                 // at most 9 pops are in flight (<= 16 levels, two steps apart): the lane is free
-                    out[next] = hb[1];
-                    value = hb[size]; len = size - 1u; hole = 1u; active = size > 1u;
-                }
-                ++next; since = 0;
-            }
-        }
-        if (!__any_sync(0xffffffffu, active)) {
-            if (next >= n) break;
-            since = 2;                                     // nothing in flight: the next pop starts at once
-            continue;
-        }
-        // one level of every pop in flight (oct::pop_step without branches; a lone left child is moved up like a chosen child and
-        // the value lands in its leaf slot one step later). Idle lanes read slots 2, 3 and store nothing.
-        {
-            const uint32_t l = 2u * hole;
-            const bool kids = active && l <= len;          // at least the left child
-            uint32_t cl, cr;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cl), "=r"(cr) : "r"(hb_s + 4u * (kids ? l : 2u)));
-            const bool right = l < len && !oct::e_less(cr, cl);   // two children and comp(right, left) false
-            const uint32_t c = right ? cr : cl;
-            const bool move = kids && !oct::e_less(c, value);
-            if (active) asm volatile("st.shared.u32 [%0], %1;" :: "r"(hb_s + 4u * hole), "r"(move ? c : value) : "memory");
-            hole = move ? l + (uint32_t)right : hole;
-            active = move;
-        }
-        ++since;
-        __syncwarp();                                      // this step's writes are visible to the next step's reads
-    }
-}
-
 #ifndef MCV_OR_MINB
 #define MCV_OR_MINB 1
 #endif
@@ -525,7 +481,7 @@ __global__ void __launch_bounds__(OR_THREADS, MCV_OR_MINB) k_octree_replay(const
                                                               const uint16_t* __restrict__ sidx_all, const uint16_t* __restrict__ S_all,
                                                               uint32_t* __restrict__ out_pts, int* __restrict__ out_cnt,
                                                               const int* __restrict__ overflow, const __grid_constant__ Plan P, int n_images,
-                                                              int nb_pad, int r0_words, int heap_alloc, int pop_off) {
+                                                              int nb_pad, int r0_words, int heap_alloc) {
     extern __shared__ __align__(16) unsigned char oc_smem[];
     __shared__ int s_total;
     const int tid = threadIdx.x;
@@ -534,8 +490,7 @@ __global__ void __launch_bounds__(OR_THREADS, MCV_OR_MINB) k_octree_replay(const
     const int level = task / n_images, img = task - level * n_images;
     const LevelGeom& lg = P.lv[level];
     uint32_t* cur = reinterpret_cast<uint32_t*>(oc_smem);
-    uint32_t* heap = cur + 1;                                  // heap - 1 is 16-byte aligned (oct::load2)
-    uint32_t* popped = heap + pop_off;                         // entries in pop order (the upper half of the heap allocation)
+    uint32_t* heap = cur + 1;                                  // heap - 1 is 16-byte aligned (oct::load2 / load4)
     uint32_t* nodes = cur + heap_alloc;
     uint16_t* S = reinterpret_cast<uint16_t*>(cur + r0_words);
     const size_t task_off = (size_t)img * P.cand_per_image + lg.cand_off;
@@ -550,19 +505,16 @@ __global__ void __launch_bounds__(OR_THREADS, MCV_OR_MINB) k_octree_replay(const
     if (clk && tid == 0) clk[6] = clock64();
     for (int b = tid; b <= nb; b += OR_THREADS) S[b] = Sg[b];
     __syncthreads();
-    // -- serial split loop on counts (one thread), then the drain by the whole warp
+    // -- serial heap replay on counts
     if (tid == 0) {
-        s_total = oct::replay_split(scode, S, g, heap, nodes);
-        if (clk) clk[3] = clock64();
+        s_total = oct::replay(scode, S, g, heap, nodes, clk ? clk + 3 : nullptr);
+        if (clk) clk[4] = clock64();
     }
     __syncthreads();
     const int total = s_total;
-    drain_pipelined(heap, total, popped, tid);
-    __syncthreads();
-    if (clk && tid == 0) clk[4] = clock64();
     const int n_out = min(total, lg.out_cap);
     uint32_t* out = out_pts + (size_t)img * P.out_per_image + lg.out_off;
-    for (int i = tid; i < n_out; i += OR_THREADS) out[i] = oct::select_best(popped[i], nodes, S, g.T, pts, sidx);
+    for (int i = tid; i < n_out; i += OR_THREADS) out[i] = oct::select_best(heap[total - 1 - i], nodes, S, g.T, pts, sidx);
     if (tid == 0) {
         out_cnt[(size_t)img * P.n_levels + level] = n_out;
         if (clk) clk[5] = clock64();
@@ -617,8 +569,7 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
         nb = std::max(nb, g.n_ini << (2 * oct::tier_for(g.n_ini)));
         can_overflow |= g.cand_cap > 65535;
     }
-    const int heap_alloc = (2 * (max_heap + 1) + 8 + 3) & ~3;              // the slot before the heap | heap | entries in pop order
-    const int pop_off = max_heap + 2;                                      // (in words from heap[0]; pop_off + max_heap < heap_alloc - 1)
+    const int heap_alloc = (2 * (max_heap + 1) + 8 + 3) & ~3;              // oct::heap_pop's speculative reach (+ the slot before the heap)
     const int r0_words = (std::max(nb, heap_alloc + max_heap + 4) + 3) & ~3;
     const int nb_pad = (nb + 1 + 7) & ~7;
     const size_t smem = (size_t)r0_words * 4 + (size_t)nb_pad * 2;
@@ -652,7 +603,7 @@ int launch_octree(const Plan& P, const uint32_t* d_cell_pts, const int* d_cell_c
     k_octree_prep<OC_THREADS_BATCH><<<tasks, OC_THREADS_BATCH, smem, s>>>(d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_oct_idx, d_S, d_overflow, P, n_images, OCT_S_BYTES / 2, r0_words,
                                                   nb_pad);
     k_octree_replay<<<tasks, OR_THREADS, smem, s>>>(d_arena_a, d_arena_b, d_oct_idx, d_S, d_out_pts, d_out_cnt, d_overflow, P, n_images, OCT_S_BYTES / 2,
-                                                    r0_words, heap_alloc, pop_off);
+                                                    r0_words, heap_alloc);
     if (!can_overflow) return 2;
     return 2 + launch_octree_legacy(P, d_cell_pts, d_cell_cnt, d_arena_a, d_arena_b, d_out_pts, d_out_cnt, n_images, d_overflow, s);
 }

@@ -20,22 +20,15 @@ def core():
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-x", "c++", SRC, "-o", SO], check=True)
     L = C.CDLL(SO)
     L.octcore_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
-    L.octcore_distribute_pipelined.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     return L
 
 
 def run_core(L, x, y, r, bw, bh, N):
-    """Serial form (split loop + one pop after the other) and the kernel's pipelined drain with its 32 lanes emulated in three
-    different visiting orders: all four must agree (and the emulation reports any slot two pops touch in the same step)."""
     pts = (x.astype(np.uint32) | (y.astype(np.uint32) << 12) | (r.astype(np.uint32) << 24)).astype(np.uint32)
     out = np.zeros(N + 8, np.uint32)
     n = L.octcore_distribute(pts.ctypes.data, len(pts), bw, bh, N, out.ctypes.data, len(out))
     assert n >= 0, n
     out = out[:n]
-    for order in (0, 1, 2):
-        o2 = np.zeros(N + 8, np.uint32)
-        n2 = L.octcore_distribute_pipelined(pts.ctypes.data, len(pts), bw, bh, N, o2.ctypes.data, len(o2), order)
-        assert n2 == n and np.array_equal(o2[:n], out), ("pipelined drain differs", order, n2, n)
     return np.stack([out & 0xfff, (out >> 12) & 0xfff, out >> 24], 1).astype(np.int64)
 
 
@@ -84,7 +77,7 @@ def test_core_dense_block_and_row_order(core, oracle):
 
 
 def test_heap_primitives_match_libstdcxx(core):
-    """oct::heap_push / the top-down oct::heap_pop / the pipelined drain against std::push_heap / std::pop_heap on the same
+    """oct::heap_push / oct::heap_pop against std::push_heap / std::pop_heap on the same
     entries: every heap size from 1 to 70 (all tree shapes, lone-child cases), larger ones, count ranges from all-equal to wide."""
     core.octcore_heap_check.argtypes = [C.c_uint, C.c_int, C.c_int]
     for n in list(range(1, 71)) + [127, 128, 129, 434, 1000, 2003]:
