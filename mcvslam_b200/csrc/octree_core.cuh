@@ -226,6 +226,29 @@ OCT_HD uint32_t heap_pop(uint32_t* h, int& size) {
     return top;
 }
 
+// ---- drain of a heap whose elements all compare equal (every node holds one point: the tail of every drain, and the whole
+// drain when a level has fewer candidates than its quota — the reference's shipped single-level configuration) ----
+// With equal keys std::pop_heap decides nothing from the data: comp(right, left) is false, so the hole runs down the right-most
+// spine 1, 3, 7, ... (1-based slots 2^(j+1) - 1) while a right child exists, takes a lone left child if that is what is left,
+// and the displaced last element stays where the hole ends (no parent is smaller). One pop is therefore the same data movement
+// for every heap of that size, and the spine's levels can move at the same time: "lane" j plans the write(s) of spine level j
+// from the array as it is BEFORE the pop; all plans are read first, then written. hb = h - 1, s = current size; the popped
+// element is left in slot s like heap_pop leaves it.
+struct EqPlan { uint32_t a0, v0, a1, v1; };              // up to two writes hb[a] = v (a == 0: none)
+constexpr int EQ_LANES = 17;                             // spine levels of a heap of < 2^16 elements, + the slot-s writer
+OCT_HD EqPlan equal_pop_plan(const uint32_t* hb, uint32_t s, int lane) {
+    EqPlan p{0u, 0u, 0u, 0u};
+    if (lane >= EQ_LANES) return p;
+    const uint32_t len = s - 1u;                          // elements that stay
+    const uint32_t pj = (2u << lane) - 1u, pn = (4u << lane) - 1u, pp = (1u << lane) - 1u;   // this, next and previous spine slot
+    if (pn <= len) { p.a0 = pj; p.v0 = hb[pn]; }          // the right child moves up
+    else if (pj <= len) {                                 // the spine ends here
+        if (2u * pj == len) { p.a0 = pj; p.v0 = hb[len]; p.a1 = len; p.v1 = hb[s]; }   // lone left child moves up, the value takes its slot
+        else { p.a0 = pj; p.v0 = hb[s]; }
+    } else if (lane == 0 || pp <= len) { p.a0 = s; p.v0 = hb[1]; }   // first lane past the spine: the popped top goes to slot s
+    return p;
+}
+
 // start of a node's range in the sorted arrays
 template <typename ST>
 OCT_HD int node_lo(uint32_t node, const ST* S, int T) {
@@ -235,9 +258,11 @@ OCT_HD int node_lo(uint32_t node, const ST* S, int T) {
 
 // The serial part (ORBextractor.cc:549-578): roots, split loop, drain. `scode` = path codes sorted ascending (only deep nodes
 // read it), `S` = exclusive prefix sums of the bucket histogram (n_ini << 2T entries + 1). Returns the number of final nodes; the i-th popped node
-// (= i-th output keypoint) is left at heap[total - 1 - i] (count << 16 | id, node description in nodes[id]).
+// (= i-th output keypoint) is left at heap[total - 1 - i] (count << 16 | id, node description in nodes[id]) — once the caller has
+// drained the equal-key tail, if it asked for one.
 template <typename ST>
-OCT_HD int replay(const uint32_t* scode, const ST* S, const Geom& g, uint32_t* heap, uint32_t* nodes, long long* clk_split_done = nullptr) {
+OCT_HD int replay(const uint32_t* scode, const ST* S, const Geom& g, uint32_t* heap, uint32_t* nodes, long long* clk_split_done = nullptr,
+                  int* equal_tail = nullptr) {
     const int T = g.T;
     int size = 0, n_nodes = 0;
     for (int r = 0; r < g.n_ini; ++r) {   // ORBextractor.cc:549-555: empty roots are dropped
@@ -254,20 +279,30 @@ OCT_HD int replay(const uint32_t* scode, const ST* S, const Geom& g, uint32_t* h
         const uint32_t node = nodes[id];
         const int d = n_depth(node);
         if (d >= DIGITS) break;
-        heap_pop(heap, size);
+        // The child counts depend on the popped node alone, so their loads are ISSUED before the pop and consumed after it: the
+        // pop's dependent sift (hundreds of cycles on a lone thread) then covers the latency of the sorted codes, which live in
+        // global memory (an L2 round trip per deep split: 749 of the 1084 splits of a 512x512 single-level image).
         uint32_t c0, c1, c2, c3, x0, xs;   // child counts; child k's X = x0 + k * xs (table) or running range start (deep)
         if (d < T) {
             const int sh = 2 * (T - 1 - d);
             x0 = n_x(node) << 2;
             const ST* s = S + ((size_t)x0 << sh);
             const uint32_t s0 = s[0], s1 = s[(size_t)1 << sh], s2 = s[(size_t)2 << sh], s3 = s[(size_t)3 << sh], s4 = s[(size_t)4 << sh];
+            heap_pop(heap, size);
             c0 = s1 - s0; c1 = s2 - s1; c2 = s3 - s2; c3 = s4 - s3;
             xs = 1;
         } else {
             x0 = d == T ? (uint32_t)S[n_x(node)] : n_x(node);
             const int sh = 2 * (DIGITS - 1 - d);
+            constexpr uint32_t PRE = 6;   // codes fetched ahead (deep nodes hold few points)
+            uint32_t pre[PRE];
+#pragma unroll
+            for (uint32_t j = 0; j < PRE; ++j) pre[j] = j < cnt ? scode[x0 + j] : 0u;
+            heap_pop(heap, size);
             unsigned long long acc = 0;   // four 16-bit counters
-            for (uint32_t j = 0; j < cnt; ++j) acc += 1ull << (16 * ((scode[x0 + j] >> sh) & 3u));
+#pragma unroll
+            for (uint32_t j = 0; j < PRE; ++j) if (j < cnt) acc += 1ull << (16 * ((pre[j] >> sh) & 3u));
+            for (uint32_t j = PRE; j < cnt; ++j) acc += 1ull << (16 * ((scode[x0 + j] >> sh) & 3u));
             c0 = (uint32_t)acc & 0xffffu; c1 = (uint32_t)(acc >> 16) & 0xffffu; c2 = (uint32_t)(acc >> 32) & 0xffffu; c3 = (uint32_t)(acc >> 48);
             xs = 0;
         }
@@ -289,6 +324,13 @@ OCT_HD int replay(const uint32_t* scode, const ST* S, const Geom& g, uint32_t* h
 #ifdef __CUDA_ARCH__
     if (clk_split_done) *clk_split_done = clock64();
 #endif
+    // with `equal_tail` the serial drain stops as soon as the top holds one point — then every remaining element does — and leaves
+    // that many elements in heap[0, *equal_tail) for the caller's equal-key drain (equal_pop_plan)
+    if (equal_tail) {
+        while (size > 0 && e_cnt(heap[0]) > 1) heap_pop(heap, size);
+        *equal_tail = size;
+        return total;
+    }
     while (size > 0) heap_pop(heap, size);
     return total;
 }

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(OR_THREADS, MCV_OR_MINB) k_octree_replay(const
                                                               const int* __restrict__ overflow, const __grid_constant__ Plan P, int n_images,
                                                               int nb_pad, int r0_words, int heap_alloc) {
     extern __shared__ __align__(16) unsigned char oc_smem[];
-    __shared__ int s_total;
+    __shared__ int s_total, s_tail;
     const int tid = threadIdx.x;
     const int task = blockIdx.x;                       // level-major: the long level-0 tasks start first
     if (overflow[task]) return;                        // the legacy kernel takes this task
@@ -505,13 +505,22 @@ __global__ void __launch_bounds__(OR_THREADS, MCV_OR_MINB) k_octree_replay(const
     if (clk && tid == 0) clk[6] = clock64();
     for (int b = tid; b <= nb; b += OR_THREADS) S[b] = Sg[b];
     __syncthreads();
-    // -- serial heap replay on counts
-    if (tid == 0) {
-        s_total = oct::replay(scode, S, g, heap, nodes, clk ? clk + 3 : nullptr);
-        if (clk) clk[4] = clock64();
-    }
+    // -- serial heap replay on counts; the tail of the drain (all nodes down to one point: keys equal) by the warp, one lane per
+    //    level of the heap's right-most spine (oct::equal_pop_plan)
+    if (tid == 0) s_total = oct::replay(scode, S, g, heap, nodes, clk ? clk + 3 : nullptr, &s_tail);
     __syncthreads();
     const int total = s_total;
+    {
+        uint32_t* const hb = heap - 1;
+        for (uint32_t sz = (uint32_t)s_tail; sz >= 1u; --sz) {
+            const oct::EqPlan p = oct::equal_pop_plan(hb, sz, tid);
+            __syncwarp();                                  // every lane has read the array as it was before this pop
+            if (p.a0) hb[p.a0] = p.v0;
+            if (p.a1) hb[p.a1] = p.v1;
+            __syncwarp();
+        }
+    }
+    if (clk && tid == 0) clk[4] = clock64();
     const int n_out = min(total, lg.out_cap);
     uint32_t* out = out_pts + (size_t)img * P.out_per_image + lg.out_off;
     for (int i = tid; i < n_out; i += OR_THREADS) out[i] = oct::select_best(heap[total - 1 - i], nodes, S, g.T, pts, sidx);

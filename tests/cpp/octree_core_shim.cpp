@@ -12,6 +12,19 @@
 using namespace mcv::oct;
 using std::max;
 
+static void equal_drain_emulated(uint32_t* heap, int size, int order) {
+    uint32_t* const hb = heap - 1;
+    for (uint32_t s = (uint32_t)size; s >= 1u; --s) {
+        EqPlan plan[32];
+        for (int l = 0; l < 32; ++l) plan[l] = equal_pop_plan(hb, s, l);
+        for (int i = 0; i < 32; ++i) {
+            const EqPlan& p = plan[order ? 31 - i : i];
+            if (p.a0) hb[p.a0] = p.v0;
+            if (p.a1) hb[p.a1] = p.v1;
+        }
+    }
+}
+
 static int distribute_impl(const uint32_t* pts, int M, int box_w, int box_h, int N, uint32_t* out, int out_cap, int drain_order) {
     const int n_ini = (int)roundf((float)box_w / (float)box_h);   // ORBextractor.cc:527
     if (n_ini < 1 || n_ini > MAX_ROOTS || M > 65535) return -1;
@@ -32,8 +45,15 @@ static int distribute_impl(const uint32_t* pts, int M, int box_w, int box_h, int
     std::vector<uint32_t> heap_store(2 * (std::max(N + 3, n_ini) + 1) + 8 + 2), nodes(std::max(N + 3, n_ini) + 4);
     uint32_t* heap = heap_store.data() + 1;
     std::vector<uint16_t> S16(S.begin(), S.end());   // the kernel keeps the table in 16 bits
-    (void)drain_order;
-    const int total = replay(scode.data(), S16.data(), g, heap, nodes.data());
+    // drain_order >= 0: the kernel's form — serial replay up to the equal-key tail, then equal_pop_plan with the lanes emulated
+    // (all plans made from the array as it is before the pop, then written; written in ascending or descending lane order)
+    int total;
+    if (drain_order < 0) total = replay(scode.data(), S16.data(), g, heap, nodes.data());
+    else {
+        int tail = 0;
+        total = replay(scode.data(), S16.data(), g, heap, nodes.data(), nullptr, &tail);
+        equal_drain_emulated(heap, tail, drain_order);
+    }
     for (int i = 0; i < total && i < out_cap; ++i) out[i] = select_best(heap[total - 1 - i], nodes.data(), S16.data(), g.T, pts, sidx.data());
     return total;
 }
@@ -45,6 +65,11 @@ extern "C" int octcore_distribute(const uint32_t* pts, int M, int box_w, int box
 // Heap primitives alone against libstdc++: a random heap of n entries with counts in [1, max_count] (small ranges = tie-heavy) is
 // built with std::push_heap / oct::heap_push, then drained by std::pop_heap and by oct::heap_pop (the replay's hand-scheduled sift).
 // Returns the number of disagreements (entry order or array contents).
+// split loop + serial drain down to the equal-key tail + the kernel's equal-key drain with its lanes emulated
+extern "C" int octcore_distribute_kernel_form(const uint32_t* pts, int M, int box_w, int box_h, int N, uint32_t* out, int out_cap, int drain_order) {
+    return distribute_impl(pts, M, box_w, box_h, N, out, out_cap, drain_order);
+}
+
 extern "C" int octcore_heap_check(unsigned seed, int n, int max_count) {
     auto cmp = [](uint32_t a, uint32_t b) { return (a >> 16) < (b >> 16); };
     std::vector<uint32_t> ref, mine_store(2 * n + 16, 0u);
@@ -58,6 +83,13 @@ extern "C" int octcore_heap_check(unsigned seed, int n, int max_count) {
         heap_push(mine, size, e);
     }
     for (int i = 0; i < n; ++i) bad += ref[i] != mine[i];
+    if (max_count == 1) {                                  // equal keys: the lane-parallel drain must leave exactly what n x heap_pop leaves
+        std::vector<uint32_t> eq_store(mine_store), ser_store(mine_store);
+        equal_drain_emulated(eq_store.data() + 1, n, (int)(seed & 1u));
+        int sz = n;
+        while (sz > 0) heap_pop(ser_store.data() + 1, sz);
+        for (int i = 0; i < n; ++i) bad += eq_store[1 + i] != ser_store[1 + i];
+    }
     for (int k = 0; k < n; ++k) {
         std::pop_heap(ref.begin(), ref.end(), cmp);
         const uint32_t a = ref.back(); ref.pop_back();

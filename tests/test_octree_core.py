@@ -20,6 +20,7 @@ def core():
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-x", "c++", SRC, "-o", SO], check=True)
     L = C.CDLL(SO)
     L.octcore_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.octcore_distribute_kernel_form.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     return L
 
 
@@ -29,6 +30,10 @@ def run_core(L, x, y, r, bw, bh, N):
     n = L.octcore_distribute(pts.ctypes.data, len(pts), bw, bh, N, out.ctypes.data, len(out))
     assert n >= 0, n
     out = out[:n]
+    for order in (0, 1):     # the kernel's form: equal-key tail of the drain by emulated lanes, writes in either lane order
+        o2 = np.zeros(N + 8, np.uint32)
+        n2 = L.octcore_distribute_kernel_form(pts.ctypes.data, len(pts), bw, bh, N, o2.ctypes.data, len(o2), order)
+        assert n2 == n and np.array_equal(o2[:n], out), ("equal-key drain differs", order, n2, n)
     return np.stack([out & 0xfff, (out >> 12) & 0xfff, out >> 24], 1).astype(np.int64)
 
 
@@ -53,7 +58,7 @@ def unique_points(rng, n, bw, bh, cluster=False):
 
 
 CASES = [(602, 442, 434, 1468), (602, 442, 434, 300), (495, 362, 362, 1130), (141, 96, 122, 565), (602, 442, 2000, 5000), (1242, 682, 1086, 4612),
-         (900, 200, 300, 1200), (1500, 100, 200, 900), (100, 100, 50, 49), (100, 100, 3, 1), (37, 51, 40, 300), (4000, 3000, 700, 3000)]
+         (900, 200, 300, 1200), (480, 480, 2000, 1511), (480, 480, 1500, 1511), (1500, 100, 200, 900), (100, 100, 50, 49), (100, 100, 3, 1), (37, 51, 40, 300), (4000, 3000, 700, 3000)]
 
 
 @pytest.mark.parametrize("bw,bh,N,M", CASES)
@@ -80,7 +85,7 @@ def test_heap_primitives_match_libstdcxx(core):
     """oct::heap_push / oct::heap_pop against std::push_heap / std::pop_heap on the same
     entries: every heap size from 1 to 70 (all tree shapes, lone-child cases), larger ones, count ranges from all-equal to wide."""
     core.octcore_heap_check.argtypes = [C.c_uint, C.c_int, C.c_int]
-    for n in list(range(1, 71)) + [127, 128, 129, 434, 1000, 2003]:
+    for n in list(range(1, 140)) + [255, 256, 257, 434, 1000, 1511, 2003, 4095, 4096, 4097]:
         for max_count in (1, 2, 3, 8, 1000):
             for seed in range(3):
                 assert core.octcore_heap_check(seed + 10 * n, n, max_count) == 0, (n, max_count, seed)
