@@ -280,10 +280,11 @@ def pin_to_gpu_numa(local_rank):
 
 
 class RigBuffers:
-    """Device-resident inputs, N_SETS device output sets (consecutive in-flight mcv_rig_process_async calls never share outputs,
-    include/mcv_b200.h) and `nf` pinned host output sets for a batch of B frames."""
+    """Device-resident inputs, N_SETS device output sets (in-flight mcv_rig_process_async calls never share outputs,
+    include/mcv_b200.h: the engine rotates calls over at most 6 streams, so a set is reused by the 6th following call at the
+    earliest, and that call is ordered behind the set's previous user) and `nf` pinned host output sets for a batch of B frames."""
 
-    N_SETS = 2
+    N_SETS = 6
 
     def __init__(self, torch, dev, frames_np, cap, nf):
         self.B = B = len(frames_np)

@@ -221,9 +221,10 @@ mcv_status mcv_rig_process(mcv_rig* r, const uint8_t* imgs, int n_frames, int w,
                            int cap, int out_on_device);
 /* As mcv_rig_process with device-resident inputs and outputs, but only ENQUEUES the work (async): it runs on the rig's
  * internal streams, ordered after everything already on the rig's stream, and consecutive calls overlap (the latency-bound
- * quadtree stage of one call runs beside the stencils of the next). The results are complete after mcv_rig_sync() (host
- * wait) or, for work queued on the rig's stream afterwards, after mcv_rig_join(). Do not reuse the output buffers of a call
- * before one of the two. */
+ * quadtree stage of one call runs beside the stencils of the next ones): calls of up to the engine's device chunk (128 frames)
+ * rotate over 3 internal streams (env MCV_RIG_SLOTS_DEV). The results are complete after mcv_rig_sync() (host wait) or, for
+ * work queued on the rig's stream afterwards, after mcv_rig_join(). Do not reuse the output buffers of a call before one of
+ * the two — a caller that keeps calls in flight gives each of them its own output set. */
 mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames, int w, int hgt, mcv_keypoint* d_kps,
                                  uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth_left, int cap);
 /* As mcv_rig_process with HOST inputs and outputs (pinned memory, or the copies degrade to synchronous ones), but only ENQUEUES

@@ -1205,10 +1205,12 @@ struct mcv_rig {
     int use_slots = RIG_SLOTS;      // synchronous host path: slots in rotation (env MCV_RIG_SLOTS). B200, 128 frames per mcv_rig_process call:
                                     // 3 slots 25.1 k frames/s, 4 slots 27.7 k, 6 slots 29.4 k (a chunk no longer waits for the D2H of the chunk
                                     // that used its slot before); mcv_rig_submit keeps whole steps in flight and rotates over three
-    int use_slots_dev = 2;          // device-resident path (env MCV_RIG_SLOTS_DEV): consecutive calls alternate between two
+    int use_slots_dev = 3;          // device-resident path (env MCV_RIG_SLOTS_DEV): consecutive calls rotate over three
                                     // streams, so the latency-bound quadtree of one batch runs beside the stencils of the next
-                                    // (B200, current kernels: 34.0k frames/s on one stream, 37.3k on two, 37.3k on three; a
-                                    // dedicated high-priority quadtree stream, MCV_RIG_QUAD_PRIORITY=1, changes nothing)
+                                    // ones. B200, 128-frame calls: BASELINE config one stream 36.4 k frames/s, two 41.1 k, three
+                                    // 41.9 k, four 39.8 k; the reference's shipped single-level 512 x 512 config (the quadtree is
+                                    // 1.7 of a call's 1.9 ms) two 67.5 k, three 81.1 k, four 81.9 k, six 53.0 k. A dedicated
+                                    // high-priority quadtree stream (MCV_RIG_QUAD_PRIORITY=1) changes nothing.
     cudaEvent_t last_front = nullptr;   // front-half event of the most recently enqueued chunk
     bool no_stagger = true;             // the slots' streams run free; env MCV_RIG_STAGGER=1 makes a chunk's front half wait for
                                         // the previous chunk's (B200, current kernels: free 38.5k frames/s, staggered 37.3k)

@@ -16,16 +16,18 @@ for nlevels in (1, 8):
         cap = rig.cap
         base = [synth.triplet(50 + i, W, H) for i in range(min(nb, 16))]
         fr = torch.from_numpy(np.stack([base[i % len(base)] for i in range(nb)])).to(dev)
-        k = torch.empty(nb * 3 * cap * 28, dtype=torch.uint8, device=dev); d = torch.empty(nb * 3 * cap * 32, dtype=torch.uint8, device=dev)
-        c = torch.zeros(nb * 3, dtype=torch.int32, device=dev); u = torch.empty(nb * cap, dtype=torch.float32, device=dev); z = torch.empty(nb * cap, dtype=torch.float32, device=dev)
+        sets = [(torch.empty(nb * 3 * cap * 28, dtype=torch.uint8, device=dev), torch.empty(nb * 3 * cap * 32, dtype=torch.uint8, device=dev),
+                 torch.zeros(nb * 3, dtype=torch.int32, device=dev), torch.empty(nb * cap, dtype=torch.float32, device=dev),
+                 torch.empty(nb * cap, dtype=torch.float32, device=dev)) for _ in range(6)]     # calls in flight never share outputs
+        k, d, c, u, z = sets[0]
         with torch.cuda.stream(s):
             for _ in range(5):
                 rig.process_async(fr.data_ptr(), nb, W, H, k.data_ptr(), d.data_ptr(), c.data_ptr(), u.data_ptr(), z.data_ptr()); rig.join()
             torch.cuda.synchronize()
             reps = 30
             t0 = time.perf_counter()
-            for _ in range(reps):
-                rig.process_async(fr.data_ptr(), nb, W, H, k.data_ptr(), d.data_ptr(), c.data_ptr(), u.data_ptr(), z.data_ptr())
+            for i in range(reps):
+                rig.process_async(fr.data_ptr(), nb, W, H, *(t.data_ptr() for t in sets[i % 6]))
             rig.join(); torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / reps
             rig.set_profiling(True)
