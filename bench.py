@@ -484,6 +484,43 @@ def main():
                 del sb
             torch.cuda.empty_cache()
 
+        # the reference's SHIPPED configuration (config/extractor.yaml: nkeypoints 2000, nlevels 1, on its 512 x 512 cameras,
+        # config/camleft.yaml): not a BASELINE config, reported beside it because it is what the reference itself runs. Fewer FAST
+        # candidates than quota on the single level, so the quadtree splits down to single points and the serial heap replay is
+        # most of a call.
+        shipped = None
+        if rank == 0 and not args.no_sweep:
+            s_orb = dict(ORB, nlevels=1)
+            s_rig = A.Rig(bf=BF, baseline=BASELINE, device=local_rank, stream=stream.cuda_stream, **s_orb)
+            shipped = {"config": "config/extractor.yaml as shipped (2000 ORB, nlevels 1, FAST 28/15) on 512x512 triplets", "cases": []}
+            for nb in (1, 128):
+                sb = RigBuffers(torch, dev, make_frames(nb, 77, 512, 512), s_rig.cap, 1)
+                def s_step():
+                    s_rig.process_async(sb.d_imgs.data_ptr(), sb.B, 512, 512, *sb.ptrs(sb.next_dev()))
+                for _ in range(3):
+                    s_step()
+                s_rig.join()
+                reps = 200 if nb == 1 else 30
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                e0.record(stream)
+                for _ in range(reps):
+                    s_step()
+                s_rig.join()
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                d_ms = e0.elapsed_time(e1) / reps
+                lat = []
+                for _ in range(30 if nb == 1 else 5):
+                    t0 = time.perf_counter()
+                    s_rig.process_ptrs(sb.h_imgs.data_ptr(), sb.B, 512, 512, *sb.ptrs(sb.h_out[0]), False)
+                    lat.append(time.perf_counter() - t0)
+                shipped["cases"].append({"frames_per_call": nb, "device_frames_per_s": nb / (d_ms * 1e-3), "device_ms_per_call": d_ms,
+                                         "sync_call_ms": 1e3 * float(np.median(lat)), "keypoints_per_image": float(sb.d_out[1]["cnt"].float().mean().item())})
+                del sb
+            s_rig.close()
+            torch.cuda.empty_cache()
+
     # second headline metric (BASELINE.json): Hamming matches/s = query x train descriptor pairs per second of the brute-force
     # 2-NN, device-resident: tensor-core path against the int8 peak, integer-pipe path against the measured xor+popc peak
     matching = None
@@ -546,6 +583,7 @@ def main():
             "stage_ms_per_step": {k: v / max(1, n_calls) for k, v in stage_ms.items()},
             "stage_ms_note": "per-kernel CUDA-event durations from %d extra steps run unchunked on one stream right after the timed region" % n_calls,
             "batch_sweep": sweep,
+            "shipped_config": shipped,
             "latency_ms": next((s["sync_call_ms"] for s in sweep if s["frames_per_call"] == 1), None),
             "latency_note": "one synchronous mcv_rig_process call on ONE triplet with host buffers (the reference's Frame-per-call pattern), median",
             "clocks": clocks,
@@ -553,6 +591,12 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            if shipped is not None and ref_available():
+                from oracle import ref as R
+                cfg1 = (ORB["nkeypoints"], ORB["scale_factor"], 1, ORB["ini_th_fast"], ORB["min_th_fast"], BF, BASELINE)
+                v, n, _ = R.bench_frames(cfg1, 1, 8, 77, 512, 512, 4)
+                shipped["reference_frames_per_s_one_process"] = v
+                shipped["reference_sample"] = "%d triplets, one process of the reference's own Frame constructor (its 3 extractor threads), oracle/_ref" % n
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
