@@ -354,7 +354,11 @@ __device__ __forceinline__ void sort8(uint32_t (&c)[8], uint16_t (&x)[8]) {
 //                  stops early instead of libstdc++'s sift-to-leaf + bubble-up (same arrays, but more instructions per level than the
 //                  hand-scheduled loop in octree_core.cuh: drain 340 k); pushing sons that stay put without the sift loop (split 284 k);
 //                  a warp-wide drain with pops following each other down the tree two levels apart, one lane each (drain 279 k for one
-//                  task, but more instructions in total: the batched quadtree stage went 0.531 -> 0.549 ms).
+//                  task, but more instructions in total: the batched quadtree stage went 0.531 -> 0.549 ms); a pop by the whole warp
+//                  (the hole's way through a 5-level subtree decided by 31 lanes at once and walked on ballot masks, moves one lane
+//                  per level: split 279 k, drain 291 k — no better than the serial sift). Kept: the equal-key tail of the drain by
+//                  lanes (below) and the child-count loads issued ahead of the pop, which matter when a level has fewer candidates
+//                  than its quota — the reference's shipped single-level configuration, 1989 -> 1656 us per 512x512 triplet.
 template <int OC_THREADS>
 __global__ void __launch_bounds__(OC_THREADS) k_octree_prep(const uint32_t* __restrict__ cell_pts, const int* __restrict__ cell_cnt,
                                                             uint32_t* __restrict__ arena, uint32_t* __restrict__ scode_all,
