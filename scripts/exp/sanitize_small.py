@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, ".")
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
 import mcvslam_b200.api as A
 from mcvslam_b200 import synth
@@ -22,6 +22,15 @@ print("distinctive", bi)
 # matcher family: integer-pipe kernel (small), tensor-core kernel (>= 2^20 pairs, split + merge), batched image pairs
 q = synth.descriptors(300, 1); t = synth.descriptors(500, 2)
 print("knn popc", int(A.Matcher.KnnMatch(q, t).knn["distance"].min()))
+q = synth.descriptors(700, 7); t = synth.descriptors(1300, 8)          # one-launch warp-per-query kernel (k_knn2_wq), ragged last tile
+print("knn one-launch", int(A.Matcher.KnnMatch(q, t).knn["distance"].min()))
+# the reference's shipped single-level configuration: fewer candidates than quota, equal-key drain by lanes
+E1 = A.ORB(2000, 1.2, 1, 28, 15)
+n1, k1, d1 = E1.Extract(synth.scene(9, 512, 512))
+print("extract shipped config", n1)
+from test_oracle_golden import _voc_fixture
+voc, vdesc, vexp = _voc_fixture()
+print("bow real vocabulary", len(A.Vocabulary(voc).transform(vdesc, 4)["bow_ids"]))
 q = synth.descriptors(1000, 3); t = synth.descriptors(9000, 4)
 print("knn tensor", int(A.Matcher.KnnMatch(q, t).knn["distance"].min()))
 import torch
