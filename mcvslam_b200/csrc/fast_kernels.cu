@@ -336,12 +336,20 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) k_cell_order(const uint32_t* _
         const bool ini = lane < n && pt_r(p) >= P.ini_th;
         const int th = __any_sync(0xffffffffu, ini) ? P.ini_th : P.min_th;
         const bool keep = lane < n && pt_r(p) >= th;
-        const unsigned key = keep ? (p & 0xffffffu) : 0xffffffffu;
-        int rank = 0;
+        // bitonic sort over the warp of the point rotated so that the key (y, x) leads and the response trails: keys are unique,
+        // dropped entries (all ones) sink to the end; 15 compare-exchange steps instead of a 32-step rank count
+        unsigned v = keep ? __funnelshift_l(p, p, 8) : 0xffffffffu;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) rank += __shfl_sync(0xffffffffu, key, j) < key;
-        if (keep) out[rank] = p;
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const unsigned o = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool up = ((lane & k) == 0) == ((lane & j) == 0);   // this lane keeps the smaller of the pair
+                v = up ? min(v, o) : max(v, o);
+            }
+        }
         const int kept = __popc(__ballot_sync(0xffffffffu, keep));
+        if (lane < kept) out[lane] = __funnelshift_r(v, v, 8);
         if (lane == 0) *cnt_p = kept;
         return;
     }
@@ -404,18 +412,30 @@ __global__ void __launch_bounds__(32 * FB_WARPS) k_cell_fallback(const uint8_t* 
         __syncwarp();
         if (cw > 0 && ch > 0) {
             const int n_px = cw * ch;
-            for (int i0 = 0; i0 < n_px; i0 += 32) {
-                const int i = i0 + lane;
-                if (i < n_px) {
+            // four pixels per lane and round: their 20 byte loads are in flight together (one warp walks a whole cell, so the
+            // kernel lasts as long as one cell's chain of global round trips)
+            constexpr int FB_U = 4;
+            for (int i0 = 0; i0 < n_px; i0 += 32 * FB_U) {
+                const uint8_t* cp[FB_U];
+                int v[FB_U], up[FB_U], dn[FB_U], lf[FB_U], rt[FB_U], ryx[FB_U];
+#pragma unroll
+                for (int u = 0; u < FB_U; ++u) {
+                    const int i = min(i0 + 32 * u + lane, n_px - 1);                     // clamped: the tail repeats the last pixel
                     const int ry = i / cw, rx = i - ry * cw;
                     const uint8_t* c = src + (size_t)(y0 + ry) * pitch + (x0 + rx);
-                    // same necessary condition as the dense pass: two compass points 90 degrees apart differ by more than T
-                    const int v = c[0];
-                    const bool vert = abs((int)c[-3 * pitch] - v) > Tm || abs((int)c[3 * pitch] - v) > Tm;
-                    const bool horz = abs((int)c[-3] - v) > Tm || abs((int)c[3] - v) > Tm;
-                    if (vert && horz) {
-                        const int sc = fast_score16(c, pitch);
-                        if (sc >= Tm) tile[(ry + 1) * FB_TP + rx + 1] = (uint8_t)sc;
+                    cp[u] = c; ryx[u] = (ry + 1) * FB_TP + rx + 1;
+                    v[u] = c[0]; up[u] = c[-3 * pitch]; dn[u] = c[3 * pitch]; lf[u] = c[-3]; rt[u] = c[3];
+                }
+#pragma unroll
+                for (int u = 0; u < FB_U; ++u) {
+                    if (i0 + 32 * u + lane < n_px) {
+                        // same necessary condition as the dense pass: two compass points 90 degrees apart differ by more than T
+                        const bool vert = abs(up[u] - v[u]) > Tm || abs(dn[u] - v[u]) > Tm;
+                        const bool horz = abs(lf[u] - v[u]) > Tm || abs(rt[u] - v[u]) > Tm;
+                        if (vert && horz) {
+                            const int sc = fast_score16(cp[u], pitch);
+                            if (sc >= Tm) tile[ryx[u]] = (uint8_t)sc;
+                        }
                     }
                 }
             }
