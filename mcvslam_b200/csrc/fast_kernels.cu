@@ -75,10 +75,13 @@ __device__ __noinline__ int fast_score16(const uint8_t* c, int pitch) {
     return max(A, B) - 1;
 }
 
-// per-byte (a > T) for four packed bytes, result in bit 7 of each byte. add = 255 - T.
-__device__ __forceinline__ unsigned gt4(unsigned a, unsigned add_lo7, bool add_hi) {
-    const unsigned s = (a & 0x7f7f7f7fu) + add_lo7;     // no carry across bytes: 127 + 127 < 256
-    return add_hi ? (a | s) : (a & s);                  // carry out of bit 7 of a + add, add's bit 7 being a constant
+// per-byte (a1 > T || a2 > T) for two words of four packed bytes, result in bit 7 of each byte. add = 255 - T; add_lo7 = its low
+// seven bits in every byte, HI = its bit 7: a byte exceeds T iff a + add carries out of bit 7, i.e. HI ? (a | s) : (a & s) with
+// s = (a & 0x7f) + (add & 0x7f) (no carry across bytes: 127 + 127 < 256). The ORs of the two operands fold into 3-input LOP3s.
+template <bool HI>
+__device__ __forceinline__ unsigned gt4_or(unsigned a1, unsigned a2, unsigned add_lo7) {
+    const unsigned s1 = (a1 & 0x7f7f7f7fu) + add_lo7, s2 = (a2 & 0x7f7f7f7fu) + add_lo7;
+    return HI ? (a1 | s1 | a2 | s2) : ((a1 & s1) | (a2 & s2));
 }
 
 // Edge record of a strip: the scores on its first / last row (128 bytes each, by strip column) and first / last column
@@ -86,18 +89,20 @@ __device__ __forceinline__ unsigned gt4(unsigned a, unsigned add_lo7, bool add_h
 constexpr int FE_TOP = 0, FE_BOT = 128, FE_LEFT = 256, FE_RIGHT = 256 + FS_ROWS;
 static_assert(FS_EDGE_BYTES >= 256 + 2 * FS_ROWS && FS_EDGE_BYTES % 16 == 0, "edge record layout");
 
+// Queue entry of a candidate: b | lane << 5 | yb << 16 — bit b of lane `lane`'s candidate word of the 7-row block whose last
+// row + 1 is yb. Bit b = 8 k + 7 - j stands for row j of the block and column k of a lane's word; row j's bits were handed
+// (k_fast_score) to the lane 5 j places down, so the pixel's own lane is (lane + 5 j) & 31.
+constexpr int FS_ROT = 5;
+
 // Scores queued pixels 32 at a time (one lane each) while at least `keep_below` + 1 are queued. Pixels with score >= Tm go,
 // packed x | y << 12 | score << 24 (level coordinates), to the strip's list, and to the strip's edge record when they lie on
 // one of its border lines (sxy = the strip's first column | first row << 16; its last row follows from the level's y_hi).
 // Returns (list fill << 8) | queue fill.
-__device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_below, const uint8_t* src, uint8_t* __restrict__ edges, const unsigned* nz_base,
+__device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_below, const uint8_t* src, uint8_t* __restrict__ edge,
                                         int pitch, int Tm, unsigned* __restrict__ list, int ln, unsigned sxy, int y_hi) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     const int sx0 = (int)(sxy & 0xffffu), sy0 = (int)(sxy >> 16), y_last = min(sy0 + FS_ROWS, y_hi) - 1;
-    // the strip's edge record, located from its list segment (both are indexed by image * strips + strip): keeps the caller's
-    // marching loop free of one more live pointer
-    uint8_t* edge = edges + (size_t)((list - nz_base) / FS_SEG) * FS_EDGE_BYTES;
     __syncwarp();
     while (qn > keep_below) {
         const int n = min(qn, 32);
@@ -105,14 +110,18 @@ __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_belo
         unsigned packed = 0;
         if (lane < n) {
             const unsigned e = q[qn - n + lane];
-            const int x = (int)(e & 0xffffu), y = (int)(e >> 16);
+            const int jr = (int)(e & 7u);                                  // 7 - j
+            const int cx = 4 * (int)(((e >> 5) + FS_ROT * (7 - jr)) & 31u) + (int)((e >> 3) & 3u);   // strip column
+            const int x = sx0 + cx, y = (int)(e >> 16) - jr, cy = y - sy0;
             const int sc = fast_score16(src + y * pitch + x, pitch);
             if (sc >= Tm) {
                 hit = true; packed = pack_pt(x, y, sc);
-                if (y == sy0) edge[FE_TOP + x - sx0] = (uint8_t)sc;
-                if (y == y_last) edge[FE_BOT + x - sx0] = (uint8_t)sc;
-                if (x == sx0) edge[FE_LEFT + y - sy0] = (uint8_t)sc;
-                if (x == sx0 + 127) edge[FE_RIGHT + y - sy0] = (uint8_t)sc;
+                uint8_t* ec = edge + cx;
+                uint8_t* er = edge + FE_LEFT + cy;
+                if (cy == 0) ec[FE_TOP] = (uint8_t)sc;
+                if (y == y_last) ec[FE_BOT] = (uint8_t)sc;
+                if (cx == 0) er[0] = (uint8_t)sc;
+                if (cx == 127) er[FS_ROWS] = (uint8_t)sc;
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -124,6 +133,7 @@ __device__ __noinline__ int drain_queue(const unsigned* q, int qn, int keep_belo
     return (ln << 8) | qn;
 }
 
+template <bool HI>
 __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ edges,
                                                                unsigned* __restrict__ nz_list, int* __restrict__ nz_cnt,
                                                                const __grid_constant__ Plan P, const __grid_constant__ StripTable T, int Tm) {
@@ -139,56 +149,64 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
     const int y0 = EDGE_THRESHOLD + (t / T.strips_x[level]) * FS_ROWS;
     const int w = g.w, h = g.h, pitch = g.pitch;
     const uint8_t* src = pyr + (size_t)img * P.pyr_bytes + g.img_off;
-    if (lane < FS_EDGE_BYTES / 16)
-        reinterpret_cast<uint4*>(edges + ((size_t)img * P.n_fast_strips + sid) * FS_EDGE_BYTES)[lane] = make_uint4(0u, 0u, 0u, 0u);   // ordered before the scores by drain_queue's __syncwarp
+    uint8_t* edge = edges + ((size_t)img * P.n_fast_strips + sid) * FS_EDGE_BYTES;   // this strip's edge record
+    if (lane < FS_EDGE_BYTES / 16) reinterpret_cast<uint4*>(edge)[lane] = make_uint4(0u, 0u, 0u, 0u);   // ordered before the scores by drain_queue's __syncwarp
     unsigned* list = nz_list + ((size_t)img * P.n_fast_strips + sid) * FS_SEG;   // this strip's own segment
     int ln = 0;                                             // its fill (warp-uniform)
     const int x_lo = EDGE_THRESHOLD, x_hi = w - EDGE_THRESHOLD, y_hi = h - EDGE_THRESHOLD;   // detection region [19, n-19)
-    const bool in_row = x0 < pitch;                         // word exists in memory
-    const int ex = lane == 0 ? x0 - 4 : x0 + 4;             // lanes 0 / 31 fetch the strip's outer neighbour words
-    const bool edge = lane == 0 || (lane == 31 && x0 + 4 < pitch);
+    // Every lane loads a word of every row, with no predicate: lanes past the end of the row read the row's last word instead
+    // (their own columns are masked out, and the columns of their left neighbour that would look at it are outside the region
+    // too: x + 3 >= pitch > x_hi + 3). Lanes 0 / 31 also fetch the strip's outer neighbour words; lanes 1-30 ride along on lane
+    // 0's address (a broadcast).
+    const int lx = min(x0, pitch - 4);
+    const int ex = lane == 31 ? min(x0 + 4, pitch - 4) : x0 - lane * 4 - 4;
     unsigned colmask = 0;                                   // bit 7 of byte k set iff column x0 + k is inside the region
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (x0 + k >= x_lo && x0 + k < x_hi) colmask |= 0x80u << (8 * k);
-    const unsigned add = 255u - (unsigned)Tm, add_lo7 = (add & 0x7fu) * 0x01010101u;
-    const bool add_hi = (add & 0x80u) != 0;
+    unsigned add_lo7 = ((255u - (unsigned)Tm) & 0x7fu) * 0x01010101u;
+    asm volatile("" : "+r"(add_lo7));                       // a register, not a multiply rematerialised at every use
     unsigned* q = s_q[warp];
     int qn = 0;                                             // warp-uniform queue fill
 
     // rows past the level's end feed no output row (row_ok is false for them); they are read unclamped — the next level / image
-    // follows in the same buffer and the allocation ends with FS_ROWS + 8 spare rows (enqueue_extract)
-    unsigned pw[7], pe[7], ring[7], ering[7];
+    // follows in the same buffer and the allocation ends with FS_ROWS + 8 spare rows (enqueue_extract).
+    // pw / pe: words requested seven iterations ahead. Iteration r consumes input row y0 - 3 + r into the ring and has input row
+    // r - 3 as its centre, so the outer neighbour word is requested for the row that will be the CENTRE seven iterations on.
+    unsigned pw[7], pe[7], ring[7];
 #pragma unroll
     for (int d = 0; d < 7; ++d) {
-        const uint8_t* row = src + (y0 - 3 + d) * pitch;
-        pw[d] = in_row ? __ldg(reinterpret_cast<const unsigned*>(row + x0)) : 0u;
-        pe[d] = edge ? __ldg(reinterpret_cast<const unsigned*>(row + ex)) : 0u;
-        ring[d] = 0u; ering[d] = 0u;
+        pw[d] = __ldg(reinterpret_cast<const unsigned*>(src + (y0 - 3 + d) * pitch + lx));
+        pe[d] = __ldg(reinterpret_cast<const unsigned*>(src + (y0 - 6 + d) * pitch + ex));
+        ring[d] = 0u;
     }
-    const uint8_t* lp = src + (size_t)(y0 + 4) * pitch + x0;              // input row y0 - 3 + (r + 7) for r = 0
-    const uint8_t* lpe = lp + (ex - x0);
+    const uint8_t* lp = src + (size_t)(y0 + 4) * pitch + lx;              // input row y0 - 3 + (r + 7) for r = 0
+    const uint8_t* lpe = src + (size_t)(y0 + 1) * pitch + ex;             // centre row of iteration r + 7 for r = 0
 #pragma unroll 1
     for (int rb = 0; rb < FS_ROWS + 6; rb += 7) {
-        // candidates of the block's 7 rows: row j's four pass bits (bit 7 of each byte) shifted right by j never collide
+        // candidates of the block's 7 rows: row j's four pass bits (bit 7 of each byte) shifted right by j never collide.
+        // Corners come in clusters, and a lane that kept its own seven rows would have many times the average to emit (the warp
+        // waits for the slowest lane): row j's bits go to the lane FS_ROT * j places down instead, which spreads a cluster over
+        // seven lanes.
         unsigned acc = 0u;
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
             const int r = rb + j;                           // input row y0 - 3 + r; completes the window of output row y0 + r - 6
-            ring[j] = pw[j]; ering[j] = pe[j];
-            pw[j] = in_row ? __ldg(reinterpret_cast<const unsigned*>(lp)) : 0u;
-            pe[j] = edge ? __ldg(reinterpret_cast<const unsigned*>(lpe)) : 0u;
+            ring[j] = pw[j];
+            const unsigned we = pe[j];
+            pw[j] = __ldg(reinterpret_cast<const unsigned*>(lp));
+            pe[j] = __ldg(reinterpret_cast<const unsigned*>(lpe));
             lp += pitch; lpe += pitch;
             const int y = y0 + r - 6;
-            const unsigned v4 = ring[(j + 4) % 7], top = ring[(j + 1) % 7], bot = ring[j], we = ering[(j + 4) % 7];
+            const unsigned v4 = ring[(j + 4) % 7], top = ring[(j + 1) % 7], bot = ring[j];
             unsigned w0 = __shfl_up_sync(0xffffffffu, v4, 1), w2 = __shfl_down_sync(0xffffffffu, v4, 1);
             w0 = lane == 0 ? we : w0;
             w2 = lane == 31 ? we : w2;
             const unsigned lft = __funnelshift_r(w0, v4, 8), rgt = __funnelshift_r(v4, w2, 24);   // pixels x-3.., x+3..
-            const unsigned mt = gt4(__vabsdiffu4(v4, top), add_lo7, add_hi), mb = gt4(__vabsdiffu4(v4, bot), add_lo7, add_hi);
-            const unsigned ml = gt4(__vabsdiffu4(v4, lft), add_lo7, add_hi), mr = gt4(__vabsdiffu4(v4, rgt), add_lo7, add_hi);
             const bool row_ok = r >= 6 && r < FS_ROWS + 6 && y < y_hi;   // warp-uniform; every row belongs to exactly one strip
                                                                          // (a pixel listed twice would survive NMS twice)
-            const unsigned pass = row_ok ? ((mt | mb) & (ml | mr) & colmask) : 0u;
+            unsigned pass = gt4_or<HI>(__vabsdiffu4(v4, top), __vabsdiffu4(v4, bot), add_lo7) &
+                            gt4_or<HI>(__vabsdiffu4(v4, lft), __vabsdiffu4(v4, rgt), add_lo7) & (row_ok ? colmask : 0u);
+            if (j) pass = __shfl_sync(0xffffffffu, pass, lane + FS_ROT * j);   // source lane taken modulo 32
             acc |= pass >> j;
         }
         if (__any_sync(0xffffffffu, acc != 0u)) {
@@ -197,18 +215,19 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
-            int pos = qn + incl - cnt;
+            unsigned* qp = q + qn + incl - cnt;
             qn += __shfl_sync(0xffffffffu, incl, 31);
-            const int yb = y0 + rb - 6 + 7;                 // bit b: column byte b >> 3, row j = 7 - (b & 7)
+            const unsigned cb = ((unsigned)(y0 + rb + 1) << 16) | ((unsigned)lane << 5);   // yb = last row of the block + 1
             while (acc) {
-                const int b = __ffs(acc) - 1;
-                acc &= acc - 1u;
-                q[pos++] = (unsigned)(x0 + (b >> 3)) | ((unsigned)(yb - (b & 7)) << 16);
+                unsigned b;
+                asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(acc));   // highest set bit (one FLO; 31 - __clz costs three instructions)
+                acc ^= 1u << b;
+                *qp++ = cb + b;
             }
-            if (qn >= 32) { const int r2 = drain_queue(q, qn, 31, src, edges, nz_list, pitch, Tm, list, ln, (unsigned)(x0 - lane * 4) | ((unsigned)y0 << 16), y_hi); qn = r2 & 0xff; ln = r2 >> 8; }
+            if (qn >= 32) { const int r2 = drain_queue(q, qn, 31, src, edge, pitch, Tm, list, ln, (unsigned)(x0 - lane * 4) | ((unsigned)y0 << 16), y_hi); qn = r2 & 0xff; ln = r2 >> 8; }
         }
     }
-    ln = drain_queue(q, qn, 0, src, edges, nz_list, pitch, Tm, list, ln, (unsigned)(x0 - lane * 4) | ((unsigned)y0 << 16), y_hi) >> 8;
+    ln = drain_queue(q, qn, 0, src, edge, pitch, Tm, list, ln, (unsigned)(x0 - lane * 4) | ((unsigned)y0 << 16), y_hi) >> 8;
     if (lane == 0) nz_cnt[(size_t)img * P.n_fast_strips + sid] = ln;
 }
 
@@ -489,9 +508,12 @@ int launch_fast_cells(const Plan& P, const uint8_t* d_pyr, uint8_t* d_edges, uns
     const bool two_pass = d_fallback && P.ini_th > P.min_th && P.max_cell_w <= FB_MAX_CELL && P.max_cell_h <= FB_MAX_CELL;
     cudaMemsetAsync(d_cell_cnt, 0, (size_t)n_images * P.cells_per_image * sizeof(int), s);
     if (two_pass) cudaMemsetAsync(d_fallback, 0, sizeof(int), s);
-    if (n > 0)
-        k_fast_score<<<dim3((n + FS_WARPS - 1) / FS_WARPS, n_images), 32 * FS_WARPS, 0, s>>>(d_pyr, d_edges, d_nz_list, d_nz_cnt, P, T,
-                                                                                             two_pass ? P.ini_th : P.min_th);
+    if (n > 0) {
+        const int Tm = two_pass ? P.ini_th : P.min_th;
+        const dim3 grid((n + FS_WARPS - 1) / FS_WARPS, n_images);
+        if ((255 - Tm) & 0x80) k_fast_score<true><<<grid, 32 * FS_WARPS, 0, s>>>(d_pyr, d_edges, d_nz_list, d_nz_cnt, P, T, Tm);
+        else k_fast_score<false><<<grid, 32 * FS_WARPS, 0, s>>>(d_pyr, d_edges, d_nz_list, d_nz_cnt, P, T, Tm);
+    }
     if (after_score) cudaEventRecord(after_score, s);   // stage boundary for mcv_rig_stage_ms
     if (n > 0)
         k_nms_sparse<<<dim3((n + NMS_WARPS - 1) / NMS_WARPS, n_images), 32 * NMS_WARPS, 0, s>>>(d_edges, d_nz_list, d_nz_cnt, d_cell_raw, d_cell_cnt, P, T);
