@@ -39,7 +39,7 @@ namespace mcv {
 
 constexpr int FS_WARPS = 4;
 #ifndef FS_MINB
-#define FS_MINB 5                 // resident CTAs per SM the register allocation aims at (95 registers, no spills)
+#define FS_MINB 7                 // resident CTAs per SM the register allocation aims at (72 registers; B200: 5 -> 0.717, 6 -> 0.674, 7 -> 0.668, 8 -> 0.716, 10 -> 0.733 ms)
 #endif
 constexpr int FS_QCAP = 32 + 7 * 128;   // leftover (< 32) + every pixel of a 7-row block
 
@@ -49,26 +49,24 @@ __device__ __noinline__ int fast_score16(const uint8_t* c, int pitch) {
     // borrows because 256 + v - p >= 1).
     const unsigned v = c[0];
     const unsigned C = (256u + v) | ((256u - v) << 16);
+    // the six other rows by a chain of 64-bit adds (two instructions each; indexing c[k * pitch + d] costs ptxas twice that)
+    const ptrdiff_t sp = pitch;
+    const uint8_t *d1 = c + sp, *d2 = d1 + sp, *d3 = d2 + sp, *u1 = c - sp, *u2 = u1 - sp, *u3 = u2 - sp;
     unsigned p[16];
-    p[0] = c[3 * pitch] * 0xFFFFu + C;          p[1] = c[3 * pitch + 1] * 0xFFFFu + C;   p[2] = c[2 * pitch + 2] * 0xFFFFu + C;
-    p[3] = c[pitch + 3] * 0xFFFFu + C;          p[4] = c[3] * 0xFFFFu + C;               p[5] = c[-pitch + 3] * 0xFFFFu + C;
-    p[6] = c[-2 * pitch + 2] * 0xFFFFu + C;     p[7] = c[-3 * pitch + 1] * 0xFFFFu + C;  p[8] = c[-3 * pitch] * 0xFFFFu + C;
-    p[9] = c[-3 * pitch - 1] * 0xFFFFu + C;     p[10] = c[-2 * pitch - 2] * 0xFFFFu + C; p[11] = c[-pitch - 3] * 0xFFFFu + C;
-    p[12] = c[-3] * 0xFFFFu + C;                p[13] = c[pitch - 3] * 0xFFFFu + C;      p[14] = c[2 * pitch - 2] * 0xFFFFu + C;
-    p[15] = c[3 * pitch - 1] * 0xFFFFu + C;
-    // min over every window of 9 consecutive (circular) values by doubling (2, 4, then 4 + 4 + 1 with a 3-input min),
-    // VIMNMX.S16x2 / VIMNMX3.S16x2; then max over the 16 windows
-    unsigned m2[16];
+    p[0] = d3[0] * 0xFFFFu + C;    p[1] = d3[1] * 0xFFFFu + C;    p[2] = d2[2] * 0xFFFFu + C;     p[3] = d1[3] * 0xFFFFu + C;
+    p[4] = c[3] * 0xFFFFu + C;     p[5] = u1[3] * 0xFFFFu + C;    p[6] = u2[2] * 0xFFFFu + C;     p[7] = u3[1] * 0xFFFFu + C;
+    p[8] = u3[0] * 0xFFFFu + C;    p[9] = u3[-1] * 0xFFFFu + C;   p[10] = u2[-2] * 0xFFFFu + C;   p[11] = u1[-3] * 0xFFFFu + C;
+    p[12] = c[-3] * 0xFFFFu + C;   p[13] = d1[-3] * 0xFFFFu + C;  p[14] = d2[-2] * 0xFFFFu + C;   p[15] = d3[-1] * 0xFFFFu + C;
+    // min over every window of 9 consecutive (circular) values as three windows of three (3-input VIMNMX3.S16x2: 16 + 16
+    // instructions instead of the 48 of a doubling scheme); then max over the 16 windows
+    unsigned m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m2[k] = __vmins2(p[k], p[(k + 1) & 15]);
-    unsigned m4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
     unsigned best = 0u;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        const unsigned a = __vimin3_s16x2(m4[k], m4[(k + 4) & 15], p[(k + 8) & 15]);
-        const unsigned b = __vimin3_s16x2(m4[k + 1], m4[(k + 5) & 15], p[(k + 9) & 15]);
+        const unsigned a = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        const unsigned b = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
         best = __vimax3_s16x2(best, a, b);
     }
     const int A = (int)(best & 0xffffu) - 256, B = (int)(best >> 16) - 256;

@@ -1,9 +1,11 @@
 // Left/right stereo matching for a batch of frames (sm_100a). Replaces Frame::ComputeStereoMatch (src/Frame.cpp:150-328).
 //
-// k_stereo_rows: one CTA per frame. Counting sort of the right keypoints by image row floor(yR) into a compact record
-//     array (uR, row band [minr, maxr], octave, iR) + row_start[] — the device form of vRowIndices (src/Frame.cpp:154-168).
-//     A right keypoint can only be a candidate of left row `row` if |floor(yR) - row| <= ceil(10 * scale[last]) + 1, so the
-//     match kernel scans one contiguous slice of the sorted records (~16 % of them) instead of all right keypoints.
+// k_stereo_rows: one CTA per frame. Counting sort of the right keypoints by (octave, image row floor(yR)) into a compact record
+//     array (uR, row band [minr, maxr], octave, iR) + row_start[octave * h + row] — the device form of vRowIndices
+//     (src/Frame.cpp:154-168). A right keypoint of octave o can only be a candidate of left row `row` if
+//     |floor(yR) - row| <= ceil(10 * scale[o]) + 1, and only for left keypoints of octaves o - 1 .. o + 1, so the match kernel
+//     scans three short slices of the sorted records (~2-3 % of them; a row-only table with the band of the coarsest octave made
+//     it 16 %) instead of all right keypoints.
 // k_stereo_match: one warp per left keypoint.
 //   * candidate gate, evaluated exactly as the reference does on every record of that slice:
 //     row band floor(yR - r) <= (int)vL <= ceil(yR + r) with r = 10 * scale[octR]  (src/Frame.cpp:160-168),
@@ -34,31 +36,33 @@ struct StereoArgs {
     float bf, baseline;
     float* u_right; float* depth; int* best_dist; int* best_r;
     size_t out_stride;
-    int* row_start;                                // [frame][h + 2]: first sorted record of each image row (+ end)
-    uint4* recs;                                   // [frame][rec_stride] records sorted by row
+    int* row_start;                                // [frame][n_levels * h + 2]: first sorted record of each (octave, image row) (+ end)
+    uint4* recs;                                   // [frame][rec_stride] records sorted by (octave, row)
     size_t rec_stride;
-    int band;                                      // ceil(10 * scale[last level]) + 2
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // row table of the right keypoints: record = (uR bits, minr | maxr << 16, iR | octave << 24, row)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ StereoArgs A, const __grid_constant__ Plan P) {
-    extern __shared__ int s_row[];                 // h + 1 counters, then reused as running offsets
-    const int f = blockIdx.x, tid = threadIdx.x, h = P.h;
+    extern __shared__ int s_row[];                 // n_levels * h + 1 counters, then reused as running offsets
+    const int f = blockIdx.x, tid = threadIdx.x, h = P.h, bins = P.n_levels * h;
     const int nr = A.nr ? A.nr[(size_t)f * A.count_stride] : A.nr_fixed;
     const mcv_keypoint* kr = A.kr + (size_t)f * A.frame_kp_stride;
-    int* row_start = A.row_start + (size_t)f * (h + 2);
+    int* row_start = A.row_start + (size_t)f * (bins + 2);
     uint4* recs = A.recs + (size_t)f * A.rec_stride;
-    for (int i = tid; i <= h; i += 256) s_row[i] = 0;
+    auto bin_of = [&](const mcv_keypoint& k) {
+        return min(max(k.octave, 0), P.n_levels - 1) * h + min(max((int)floorf(k.y), 0), h - 1);
+    };
+    for (int i = tid; i <= bins; i += 256) s_row[i] = 0;
     __syncthreads();
-    for (int i = tid; i < nr; i += 256) atomicAdd(&s_row[min(max((int)floorf(kr[i].y), 0), h - 1)], 1);
+    for (int i = tid; i < nr; i += 256) atomicAdd(&s_row[bin_of(kr[i])], 1);
     __syncthreads();
-    // exclusive scan over h rows: 256 threads x ceil(h / 256) consecutive rows each, warp shuffles + one smem hop
+    // exclusive scan over the bins: 256 threads x ceil(bins / 256) consecutive bins each, warp shuffles + one smem hop
     __shared__ int s_warp[8];
-    const int per = (h + 255) / 256, r0 = tid * per;
+    const int per = (bins + 255) / 256, r0 = tid * per;
     int sum = 0;
-    for (int r = r0; r < min(r0 + per, h); ++r) sum += s_row[r];
+    for (int r = r0; r < min(r0 + per, bins); ++r) sum += s_row[r];
     int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
@@ -66,18 +70,17 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
     __syncthreads();
     int base = incl - sum;
     for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
-    for (int r = r0; r < min(r0 + per, h); ++r) { const int c = s_row[r]; s_row[r] = base; row_start[r] = base; base += c; }
-    if (tid == 255) { row_start[h] = nr; row_start[h + 1] = nr; }
+    for (int r = r0; r < min(r0 + per, bins); ++r) { const int c = s_row[r]; s_row[r] = base; row_start[r] = base; base += c; }
+    if (tid == 255) { row_start[bins] = nr; row_start[bins + 1] = nr; }
     __syncthreads();
     for (int i = tid; i < nr; i += 256) {
         const float uR = kr[i].x, yR = kr[i].y;
         const int oct = kr[i].octave;
         const float r = __fmul_rn(10.f, P.lv[oct].scale);
         const int maxr = (int)ceilf(__fadd_rn(yR, r)), minr = (int)floorf(__fsub_rn(yR, r));
-        const int row = min(max((int)floorf(yR), 0), h - 1);
-        const int pos = atomicAdd(&s_row[row], 1);
+        const int pos = atomicAdd(&s_row[bin_of(kr[i])], 1);
         // rows are clamped to 16 bits: |minr|, |maxr| < 32768 for any supported image (<= 4128 rows)
-        recs[pos] = make_uint4(__float_as_uint(uR), (unsigned)(minr & 0xffff) | ((unsigned)maxr << 16), (unsigned)i | ((unsigned)oct << 24), (unsigned)row);
+        recs[pos] = make_uint4(__float_as_uint(uR), (unsigned)(minr & 0xffff) | ((unsigned)maxr << 16), (unsigned)i | ((unsigned)oct << 24), 0u);
     }
 }
 
@@ -109,11 +112,25 @@ __global__ void __launch_bounds__(32 * ST_WARPS) k_stereo_match(const __grid_con
     const unsigned SENT = 999u << 20;
     unsigned k0 = SENT, k1 = SENT;
     {
-        const int* row_start = A.row_start + (size_t)f * (n_rows + 2);
+        const int* row_start = A.row_start + (size_t)f * (P.n_levels * n_rows + 2);
         const uint4* recs = A.recs + (size_t)f * A.rec_stride;
-        const int p_end = row_start[min(row + A.band + 1, n_rows)];
-        for (int p = row_start[max(row - A.band, 0)] + lane; p < p_end; p += 32) {
-            const uint4 rec = __ldg(recs + p);
+        // the slices of octaves levelL - 1 .. levelL + 1: rows row -+ (ceil(10 * scale[o]) + 2) of each, one concatenated index space
+        int beg[3], cum[3];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int o = levelL - 1 + k;
+            beg[k] = 0;
+            if (o >= 0 && o < P.n_levels) {
+                const int b = (int)ceilf(__fmul_rn(10.f, P.lv[o].scale)) + 2;
+                beg[k] = __ldg(row_start + o * n_rows + max(row - b, 0));
+                total += __ldg(row_start + o * n_rows + min(row + b + 1, n_rows)) - beg[k];
+            }
+            cum[k] = total;
+        }
+        for (int p = lane; p < total; p += 32) {
+            const int idx = p < cum[0] ? beg[0] + p : (p < cum[1] ? beg[1] + (p - cum[0]) : beg[2] + (p - cum[1]));
+            const uint4 rec = __ldg(recs + idx);
             const float uR = __uint_as_float(rec.x);
             const int minr = (int)(short)(rec.y & 0xffffu), maxr = (int)rec.y >> 16;
             const int octR = (int)(rec.z >> 24), iR = (int)(rec.z & 0xffffffu);
@@ -160,10 +177,15 @@ __global__ void __launch_bounds__(32 * ST_WARPS) k_stereo_match(const __grid_con
 #pragma unroll
         for (int s = 0; s < 11; ++s) sad[s] += abs(lv - ((int)rr[s - L] - (int)rrow_c[s - L]));
     }
+    // warp sums, two shifts per register (a full SAD is at most 121 * 510 = 61710 < 2^16: no carry between the halves)
 #pragma unroll
-    for (int s = 0; s < 11; ++s)
+    for (int s = 0; s < 11; s += 2) {
+        unsigned pr = (unsigned)sad[s] | (s + 1 < 11 ? (unsigned)sad[s + 1] << 16 : 0u);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sad[s] += __shfl_xor_sync(0xffffffffu, sad[s], o);
+        for (int o = 16; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
+        sad[s] = (int)(pr & 0xffffu);
+        if (s + 1 < 11) sad[s + 1] = (int)(pr >> 16);
+    }
     int bestDist = 0x7fffffff, bestinc = 0;
 #pragma unroll
     for (int s = 0; s < 11; ++s) if (sad[s] < bestDist) { bestDist = sad[s]; bestinc = s - L; }
@@ -231,7 +253,7 @@ __global__ void __launch_bounds__(256) k_stereo_median(const __grid_constant__ S
 }
 
 size_t stereo_scratch_bytes(const Plan& P, int n_frames, int max_right) {
-    return (size_t)n_frames * ((size_t)(P.h + 2) * sizeof(int) + (size_t)max_right * sizeof(uint4)) + 256;
+    return (size_t)n_frames * (((size_t)P.n_levels * P.h + 2) * sizeof(int) + (size_t)max_right * sizeof(uint4)) + 256;
 }
 
 static int run_stereo(StereoArgs A, const Plan& P, int n_frames, int max_left, int max_right, void* scratch, cudaStream_t s, cudaEvent_t mid = nullptr) {
@@ -239,8 +261,7 @@ static int run_stereo(StereoArgs A, const Plan& P, int n_frames, int max_left, i
     A.recs = reinterpret_cast<uint4*>(scratch);
     A.rec_stride = (size_t)max_right;
     A.row_start = reinterpret_cast<int*>(A.recs + (size_t)n_frames * max_right);
-    A.band = (int)ceilf(10.f * P.lv[P.n_levels - 1].scale) + 2;
-    const size_t smem = (size_t)(P.h + 1) * sizeof(int);
+    const size_t smem = ((size_t)P.n_levels * P.h + 1) * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_stereo_rows<<<n_frames, 256, smem, s>>>(A, P);
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, n_frames);
