@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
 // ---------------------------------------------------------------------------------------------------------
 // sparse NMS: one warp per strip (same strip table as k_fast_score).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int NMS_WARPS = 4;
+#ifndef MCV_NMS_WARPS
+#define MCV_NMS_WARPS 4
+#endif
+constexpr int NMS_WARPS = MCV_NMS_WARPS;
 constexpr int NMS_TP = 144;                     // tile pitch in bytes: strip column k at byte 4 + k, ring columns at bytes 3 and 132
 constexpr int NMS_TR = FS_ROWS + 2;             // tile rows: the strip's rows + one above and below
 constexpr int NMS_TILE_BYTES = NMS_TR * NMS_TP;
@@ -325,7 +328,10 @@ __global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __
 // ---------------------------------------------------------------------------------------------------------
 // per-cell threshold fallback + (y, x) ordering: one warp per cell. cell_raw -> cell_pts, cell_cnt updated in place.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ORD_WARPS = 8;
+#ifndef MCV_ORD_WARPS
+#define MCV_ORD_WARPS 8
+#endif
+constexpr int ORD_WARPS = MCV_ORD_WARPS;
 
 __global__ void __launch_bounds__(32 * ORD_WARPS) k_cell_order(const uint32_t* __restrict__ cell_raw, uint32_t* __restrict__ cell_pts,
                                                                int* __restrict__ cell_cnt, const __grid_constant__ Plan P, int* __restrict__ fallback) {

@@ -23,7 +23,18 @@
 
 namespace mcv {
 
-constexpr int ST_WARPS = 8;
+// The kernel is bound by the latency of its chain of dependent loads (keypoint -> row table -> records -> descriptors -> patches),
+// not by issue slots: what helps is more warps in flight. 4 warps per CTA (a CTA holds its slot until its slowest warp is done)
+// and 40 registers (48 warps per SM; a few spills outside the loops). B200, 128 frames: 8 warps / 51 registers 0.350 ms,
+// 4 / 51: 0.340, 2 / 51: 0.326, 8 / 40: 0.298, 4 / 40: 0.280, 4 / 32: 0.313. Issuing the left patch loads ahead of the
+// candidate scan and taking the winner's uR from its lane instead of kr[] (one round trip less) was bit-exact and no faster.
+#ifndef MCV_ST_WARPS
+#define MCV_ST_WARPS 4
+#endif
+#ifndef MCV_ST_MINB
+#define MCV_ST_MINB 12
+#endif
+constexpr int ST_WARPS = MCV_ST_WARPS;
 
 struct StereoArgs {
     const uint8_t* pyr_l; const uint8_t* pyr_r;    // image-0 pyramid bases; frame f adds f * frame_pyr_stride
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
     }
 }
 
-__global__ void __launch_bounds__(32 * ST_WARPS) k_stereo_match(const __grid_constant__ StereoArgs A, const __grid_constant__ Plan P) {
+__global__ void __launch_bounds__(32 * ST_WARPS, MCV_ST_MINB) k_stereo_match(const __grid_constant__ StereoArgs A, const __grid_constant__ Plan P) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int iL = blockIdx.x * ST_WARPS + (threadIdx.x >> 5);
     const int nl = A.nl ? A.nl[(size_t)f * A.count_stride] : A.nl_fixed;
