@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matching", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3, help="e2e leg: steps kept in flight through mcv_rig_submit (<= 8)")
+    ap.add_argument("--inflight", type=int, default=4, help="e2e leg: steps kept in flight through mcv_rig_submit (<= 8)")
     ap.add_argument("--chunk", type=int, default=None, help="frames per pipelined chunk inside the engine (default: engine default 32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -456,7 +456,7 @@ def main():
             step_host()
         barrier()
         e2e_sync_s = time.perf_counter() - t0
-        run_host_pipelined(3)
+        run_host_pipelined(max(3, 2 * NF + 2))   # every slot the steps rotate over has its buffers before the timed region
         barrier()
         t0 = time.perf_counter()
         run_host_pipelined(args.steps)

@@ -1205,6 +1205,10 @@ struct mcv_rig {
     int use_slots = RIG_SLOTS;      // synchronous host path: slots in rotation (env MCV_RIG_SLOTS). B200, 128 frames per mcv_rig_process call:
                                     // 3 slots 25.1 k frames/s, 4 slots 27.7 k, 6 slots 29.4 k (a chunk no longer waits for the D2H of the chunk
                                     // that used its slot before); mcv_rig_submit keeps whole steps in flight and rotates over three
+    int use_slots_submit = 4;       // mcv_rig_submit: whole steps in flight rotate over this many slots (env MCV_RIG_SLOTS_SUBMIT). A step is
+                                    // H2D -> kernels -> D2H on its slot's stream; with three steps in flight one of them is always in a
+                                    // copy, so only two overlap their kernels. B200, 128-frame steps: 3 slots / 3 in flight 40.9 k
+                                    // frames/s, 4 / 4: 42.7 k, 5 / 5: 42.7 k, 6 / 8: 42.8 k (device-resident 45.7 k)
     int use_slots_dev = 3;          // device-resident path (env MCV_RIG_SLOTS_DEV): consecutive calls rotate over three
                                     // streams, so the latency-bound quadtree of one batch runs beside the stencils of the next
                                     // ones. B200, 128-frame calls: BASELINE config one stream 36.4 k frames/s, two 41.1 k, three
@@ -1401,6 +1405,7 @@ mcv_status mcv_rig_create(const mcv_rig_params* p, int device, void* stream, mcv
     if (const char* e = getenv("MCV_RIG_SLOTS")) r->use_slots = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     if (const char* e = getenv("MCV_RIG_STAGGER")) r->no_stagger = atoi(e) == 0;
     if (const char* e = getenv("MCV_RIG_GRAPH_MAX")) r->graph_max_frames = atoi(e);
+    if (const char* e = getenv("MCV_RIG_SLOTS_SUBMIT")) r->use_slots_submit = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     if (const char* e = getenv("MCV_RIG_SLOTS_DEV")) r->use_slots_dev = std::max(1, std::min(RIG_SLOTS, atoi(e)));
     *out = r;
     return MCV_OK;
@@ -1553,7 +1558,7 @@ mcv_status mcv_rig_submit(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, 
     if (cap >= (1 << 20)) return MCV_ERR_BAD_ARG;
     MCV_CUDA(cudaSetDevice(r->device));
     const int chunk = r->slot[0].orb->profile || r->submit_chunk <= 0 ? n_frames : std::min(n_frames, r->submit_chunk);
-    mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, 0, kps_out, desc_out, counts, u_right, depth_left, cap, 0, chunk, std::min(3, r->use_slots));   // whole steps in flight: three slots are enough
+    mcv_status st = rig_enqueue_host(r, imgs, n_frames, w, hgt, 0, kps_out, desc_out, counts, u_right, depth_left, cap, 0, chunk, r->use_slots_submit);
     if (st) return st;
     // completion = every slot's stream has drained what this call put on it
     const long long id = ++r->submitted;

@@ -124,11 +124,20 @@ __global__ void __launch_bounds__(256) k_resize_level(uint8_t* __restrict__ pyr,
 // ~1.7 output rows at scale 1.2). Vertical pass per pixel: 2 IMAD.HI + IADD3 + SHF, i.e. exactly
 // (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2 of cv::resize's 11-bit fixed-point path.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int RS_ROWS = 16;   // output rows per warp (<= 32: lane j holds row j's coefficients)
-constexpr int RS_WARPS = 4;
+#ifndef MCV_RS_ROWS
+#define MCV_RS_ROWS 16
+#endif
+#ifndef MCV_RS_WARPS
+#define MCV_RS_WARPS 4
+#endif
+#ifndef MCV_RS_MINB
+#define MCV_RS_MINB 1
+#endif
+constexpr int RS_ROWS = MCV_RS_ROWS;   // output rows per warp (<= 32: lane j holds row j's coefficients)
+constexpr int RS_WARPS = MCV_RS_WARPS;
 constexpr int RS_PREF = 4;    // source rows in flight per lane
 
-__global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
+__global__ void __launch_bounds__(32 * RS_WARPS, MCV_RS_MINB) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
                                                                  int sw, int sh, int spitch, int soff, int dw, int dh, int dpitch, int doff,
                                                                  int strips_x, int n_strips) {
     const int img = blockIdx.y, lane = threadIdx.x & 31;
