@@ -18,7 +18,10 @@ __constant__ int8_t c_pattern[1024] = {
 #include "rbrief_pattern.inc"
 };
 
-constexpr int DESC_WARPS = 4;
+#ifndef MCV_DESC_WARPS
+#define MCV_DESC_WARPS 3
+#endif
+constexpr int DESC_WARPS = MCV_DESC_WARPS;
 constexpr int DESC_KPW = 4;      // keypoints per warp and round: one per group of 8 lanes
 #ifndef DESC_WAVES
 #define DESC_WAVES 4             // persistent grid: about this many waves of resident CTAs (3 per SM), split evenly over the images
@@ -52,6 +55,7 @@ constexpr int IC_BYTES = IC_ROWS * IC_PITCH;                          // 1488
 constexpr int BUF_IC_OFF = (TILE_BYTES + 127) & ~127;                 // TMA destinations are 128-byte aligned
 constexpr int BUF_BYTES = BUF_IC_OFF + ((IC_BYTES + 127) & ~127);     // per keypoint
 constexpr int DESC_DYN_SMEM = DESC_WARPS * DESC_KPW * BUF_BYTES;
+constexpr int DESC_RESIDENT = (227 * 1024) / (DESC_DYN_SMEM + 6 * 1024);   // CTAs per SM (dynamic windows + ~5 KB of static tables each)
 
 struct DescMaps {                 // per level: (pitch, h, n_images) u8 tensors over the pyramid and the blurred pyramid
     CUtensorMap pyr[MAX_LEVELS];
@@ -223,7 +227,7 @@ int launch_orient_desc(const Plan& P, const uint8_t* d_pyr, const uint8_t* d_blu
     const int n_seeds = seeds ? seeds->n_seeds : 0;
     const int max_kp = std::max(1, std::min(cap, P.max_quad_kp + n_seeds));
     constexpr int per_cta = DESC_WARPS * DESC_KPW;
-    const int ctas_per_image = std::max(1, std::min((max_kp + per_cta - 1) / per_cta, (DESC_WAVES * 3 * NUM_SMS + n_images - 1) / n_images));
+    const int ctas_per_image = std::max(1, std::min((max_kp + per_cta - 1) / per_cta, (DESC_WAVES * DESC_RESIDENT * NUM_SMS + n_images - 1) / n_images));
     dim3 grid(ctas_per_image, n_images);
     DescMaps maps;
     memset(&maps, 0, sizeof(maps));

@@ -130,14 +130,11 @@ __global__ void __launch_bounds__(256) k_resize_level(uint8_t* __restrict__ pyr,
 #ifndef MCV_RS_WARPS
 #define MCV_RS_WARPS 4
 #endif
-#ifndef MCV_RS_MINB
-#define MCV_RS_MINB 1
-#endif
 constexpr int RS_ROWS = MCV_RS_ROWS;   // output rows per warp (<= 32: lane j holds row j's coefficients)
 constexpr int RS_WARPS = MCV_RS_WARPS;
 constexpr int RS_PREF = 4;    // source rows in flight per lane
 
-__global__ void __launch_bounds__(32 * RS_WARPS, MCV_RS_MINB) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
+__global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
                                                                  int sw, int sh, int spitch, int soff, int dw, int dh, int dpitch, int doff,
                                                                  int strips_x, int n_strips) {
     const int img = blockIdx.y, lane = threadIdx.x & 31;
@@ -279,8 +276,8 @@ int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t
 // Register-marching separable filter, no shared memory: a warp owns a 128-px wide strip (lane = one aligned 4-px word) and
 // marches down GB_ROWS rows. Per row every lane loads ONE coalesced 32-bit word, gets its left/right neighbour words by
 // warp shuffle, forms the 7-tap horizontal sums with two dp4a per pixel, and keeps the last 7 rows of sums in registers
-// (statically indexed ring); the vertical pass is 4 IMAD + 3 IADD per pixel on that ring. HBM traffic = 1 read + 1 write
-// per pixel plus the 6-row halo (19 %).
+// (statically indexed ring, two consecutive rows' 16-bit sums per register); the vertical pass is 3 DP2A + 1 IMAD per pixel on
+// that ring. HBM traffic = 1 read + 1 write per pixel plus the 6-row halo (19 %).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GB_ROWS = 36;              // output rows per warp; GB_ROWS + 6 is a multiple of the 7-row ring
 constexpr int GB_WARPS = 4;
@@ -347,11 +344,14 @@ __global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t
         pw[d] = active ? __ldg(reinterpret_cast<const uint32_t*>(row + x0)) : 0u;
         pe[d] = edge ? __ldg(reinterpret_cast<const uint32_t*>(row + ex)) : 0u;
     }
+    // ring[j][k]: the horizontal sums (< 2^16) of the row ring slot j was written for in the HIGH half and of the row before it in
+    // the LOW half, so that the vertical pass is three DP2A (two rows each) + one IMAD per pixel instead of 3 IADD + 4 IMAD
     uint32_t ring[7][4];
 #pragma unroll
     for (int j = 0; j < 7; ++j)
 #pragma unroll
         for (int k = 0; k < 4; ++k) ring[j][k] = 0;
+    const uint32_t VA = 18u | (34u << 8) | (48u << 16) | (56u << 24), VB = 48u | (34u << 8);
 
 #pragma unroll 1
     for (int rb = 0; rb < GB_ROWS + 6; rb += 7) {
@@ -370,17 +370,19 @@ __global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t
             const uint32_t w0 = __byte_perm(w0r, w1r, sel0), w1 = __byte_perm(w0r, w1r, sel1);
             const uint32_t w2 = __byte_perm(w2_from_w0w1 ? w0r : w1r, w2_from_w0w1 ? w1r : w2r, sel2);
             // horizontal 7-tap: px k uses bytes [k-3, k] of (w0:w1) and [k+1, k+4] of (w1:w2)
-            ring[j][0] = __dp4a(__funnelshift_r(w0, w1, 8), TA, __dp4a(__funnelshift_r(w1, w2, 8), TB, 0u));
-            ring[j][1] = __dp4a(__funnelshift_r(w0, w1, 16), TA, __dp4a(__funnelshift_r(w1, w2, 16), TB, 0u));
-            ring[j][2] = __dp4a(__funnelshift_r(w0, w1, 24), TA, __dp4a(__funnelshift_r(w1, w2, 24), TB, 0u));
-            ring[j][3] = __dp4a(w1, TA, __dp4a(w2, TB, 0u));
+            uint32_t hs[4];
+            hs[0] = __dp4a(__funnelshift_r(w0, w1, 8), TA, __dp4a(__funnelshift_r(w1, w2, 8), TB, 0u));
+            hs[1] = __dp4a(__funnelshift_r(w0, w1, 16), TA, __dp4a(__funnelshift_r(w1, w2, 16), TB, 0u));
+            hs[2] = __dp4a(__funnelshift_r(w0, w1, 24), TA, __dp4a(__funnelshift_r(w1, w2, 24), TB, 0u));
+            hs[3] = __dp4a(w1, TA, __dp4a(w2, TB, 0u));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ring[j][k] = __byte_perm(ring[(j + 6) % 7][k], hs[k], 0x5432);   // (previous row, this row)
             const int y = y0 + r - 6;                       // output row whose window ends at input row r
             if (r >= 6 && y < h) {
                 uint32_t acc[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    acc[k] = 18u * (ring[(j + 1) % 7][k] + ring[j][k]) + 34u * (ring[(j + 2) % 7][k] + ring[(j + 6) % 7][k]) +
-                             48u * (ring[(j + 3) % 7][k] + ring[(j + 5) % 7][k]) + 56u * ring[(j + 4) % 7][k] + 32768u;
+                for (int k = 0; k < 4; ++k)                 // rows r-6 .. r: 18 34 | 48 56 | 48 34 | 18
+                    acc[k] = __dp2a_lo(ring[(j + 6) % 7][k], VB, __dp2a_hi(ring[(j + 4) % 7][k], VA, __dp2a_lo(ring[(j + 2) % 7][k], VA, hs[k] * 18u + 32768u)));
                 // byte 2 of each accumulator -> one word
                 const uint32_t o = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
                 uint8_t* d = dst + y * pitch;
