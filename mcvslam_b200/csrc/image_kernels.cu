@@ -288,10 +288,10 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// (…, 1): without a residency target ptxas stops at 87 registers; with it it takes 91 and issues 10 % fewer instructions
-// (B200: 0.48 -> 0.43 ms per 384 images; asking for 6-8 CTAs/SM spills and is slower)
+// Residency target: 6 CTAs per SM = 80 registers (one 4-byte spill outside the loop). B200, 384 images, with the DP2A vertical
+// pass: no target 85 registers 0.394 ms, 6 -> 0.368, 7 (72 registers) -> 0.477, 8 -> 0.516.
 #ifndef GB_MINB
-#define GB_MINB 1
+#define GB_MINB 6
 #endif
 __global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
                                                            const __grid_constant__ Plan P, const __grid_constant__ StripTable T) {
