@@ -16,7 +16,7 @@ constexpr int BORDER = 16;           // EDGE_THRESHOLD - 3: origin of FAST candi
 constexpr int MAX_DIM = 4096 + 2 * BORDER;  // candidate coordinates are packed in 12 bits
 constexpr int NUM_SMS = 148;
 #ifndef MCV_FS_ROWS
-#define MCV_FS_ROWS 36
+#define MCV_FS_ROWS 29
 #endif
 constexpr int FS_ROWS = MCV_FS_ROWS;            // rows per FAST strip; FS_ROWS + 6 is a multiple of the kernel's 7-row register ring
 constexpr int OCT_S_BYTES = 2 * 2064;    // quadtree: bucket prefix sums per (image, level) task (<= 2048 buckets + 1, u16)

@@ -37,9 +37,16 @@
 
 namespace mcv {
 
-constexpr int FS_WARPS = 4;
+#ifndef MCV_FS_WARPS
+#define MCV_FS_WARPS 1
+#endif
+constexpr int FS_WARPS = MCV_FS_WARPS;
+// One warp per CTA and 32 resident CTAs per SM (64 registers, a few spills outside the marching loop): the kernel is bound by
+// latency (the scorer's 16 dependent byte loads, the shuffles of the marching loop), and a CTA of several warps keeps its slot
+// until its slowest strip is done. B200, 128-frame step, 36-row strips: 4 warps x 5 CTAs (96 registers) 0.717 ms, x 6 0.674,
+// x 7 0.667, x 8 0.716; 2 warps x 14 0.670; 1 warp x 28 0.628; 29-row strips: 1 x 24 0.648, 1 x 28 0.626, 1 x 32 0.623.
 #ifndef FS_MINB
-#define FS_MINB 7                 // resident CTAs per SM the register allocation aims at (72 registers; B200: 5 -> 0.717, 6 -> 0.674, 7 -> 0.668, 8 -> 0.716, 10 -> 0.733 ms)
+#define FS_MINB 32
 #endif
 constexpr int FS_QCAP = 32 + 7 * 128;   // leftover (< 32) + every pixel of a 7-row block
 
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(32 * FS_WARPS, FS_MINB) k_fast_score(const uin
 // shared-memory loads per pixel cost more than the ~25 ALU instructions they replace); 1 / 2 / 8 warps per CTA: 0.329 / 0.332 / 0.355.
 // ---------------------------------------------------------------------------------------------------------
 #ifndef MCV_NMS_WARPS
-#define MCV_NMS_WARPS 4
+#define MCV_NMS_WARPS 2
 #endif
 constexpr int NMS_WARPS = MCV_NMS_WARPS;
 constexpr int NMS_TP = 144;                     // tile pitch in bytes: strip column k at byte 4 + k, ring columns at bytes 3 and 132
