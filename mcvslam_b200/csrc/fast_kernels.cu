@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(32 * NMS_WARPS) k_nms_sparse(const uint8_t* __
 // per-cell threshold fallback + (y, x) ordering: one warp per cell. cell_raw -> cell_pts, cell_cnt updated in place.
 // ---------------------------------------------------------------------------------------------------------
 #ifndef MCV_ORD_WARPS
-#define MCV_ORD_WARPS 8
+#define MCV_ORD_WARPS 4
 #endif
 constexpr int ORD_WARPS = MCV_ORD_WARPS;
 

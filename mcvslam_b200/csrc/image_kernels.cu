@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_resize_level(uint8_t* __restrict__ pyr,
 #define MCV_RS_ROWS 16
 #endif
 #ifndef MCV_RS_WARPS
-#define MCV_RS_WARPS 4
+#define MCV_RS_WARPS 1
 #endif
 constexpr int RS_ROWS = MCV_RS_ROWS;   // output rows per warp (<= 32: lane j holds row j's coefficients)
 constexpr int RS_WARPS = MCV_RS_WARPS;
@@ -279,8 +279,14 @@ int launch_pyramid(const Plan& P, const uint8_t* d_src, size_t src_pitch, size_t
 // (statically indexed ring, two consecutive rows' 16-bit sums per register); the vertical pass is 3 DP2A + 1 IMAD per pixel on
 // that ring. HBM traffic = 1 read + 1 write per pixel plus the 6-row halo (19 %).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int GB_ROWS = 36;              // output rows per warp; GB_ROWS + 6 is a multiple of the 7-row ring
-constexpr int GB_WARPS = 4;
+#ifndef MCV_GB_ROWS
+#define MCV_GB_ROWS 50
+#endif
+#ifndef MCV_GB_WARPS
+#define MCV_GB_WARPS 1
+#endif
+constexpr int GB_ROWS = MCV_GB_ROWS;              // output rows per warp; GB_ROWS + 6 is a multiple of the 7-row ring
+constexpr int GB_WARPS = MCV_GB_WARPS;
 
 __device__ __forceinline__ int reflect101(int p, int len) {
     if (len == 1) return 0;
@@ -288,10 +294,12 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// Residency target: 6 CTAs per SM = 80 registers (one 4-byte spill outside the loop). B200, 384 images, with the DP2A vertical
-// pass: no target 85 registers 0.394 ms, 6 -> 0.368, 7 (72 registers) -> 0.477, 8 -> 0.516.
+// One warp per CTA, 24 resident CTAs per SM = 80 registers (one 4-byte spill outside the loop), 50-row strips (12 % halo rows).
+// B200, 384 images, with the DP2A vertical pass: 4 warps x 36 rows, no register target (85 registers) 0.394 ms; 4 x 6 CTAs
+// (80 registers) 0.368; x 7 (72) 0.477; 1 warp x 24 CTAs 0.364, x 28 0.390; 1 x 24 with 29 / 50 / 64 / 78 / 120 rows:
+// 0.372 / 0.343 / 0.358 / 0.357 / 0.352.
 #ifndef GB_MINB
-#define GB_MINB 6
+#define GB_MINB 24
 #endif
 __global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
                                                            const __grid_constant__ Plan P, const __grid_constant__ StripTable T) {
