@@ -19,7 +19,7 @@ __constant__ int8_t c_pattern[1024] = {
 };
 
 #ifndef MCV_DESC_WARPS
-#define MCV_DESC_WARPS 3
+#define MCV_DESC_WARPS 4
 #endif
 constexpr int DESC_WARPS = MCV_DESC_WARPS;
 constexpr int DESC_KPW = 4;      // keypoints per warp and round: one per group of 8 lanes
@@ -47,13 +47,15 @@ constexpr int DESC_KPW = 4;      // keypoints per warp and round: one per group 
 // History (ncu, 384 images, 770 k keypoints): warp-per-keypoint with global gathers 0.83 ms (636 warp-instructions per
 // keypoint, l1tex 96 %); the same with cp.async staging 0.88 ms (810 per keypoint, short-scoreboard bound); quarter-warp + TMA,
 // one CTA per 16 keypoints 0.91 ms (table prologue per CTA, 18 % occupancy); persistent 0.58 ms (424 per keypoint; l1tex 78 %,
-// L2 56 %: what moves is ~3.9 KB of window per keypoint, 3 GB per launch).
+// L2 56 %: what moves is ~3.9 KB of window per keypoint, 3 GB per launch); the two windows one after the other through ONE
+// buffer per keypoint (2.4 instead of 3.9 KB: 20 resident warps per SM instead of 12) 0.567 -> 0.532 ms.
 constexpr int TILE_R = 18, TILE_ROWS = 2 * TILE_R + 1, TILE_PITCH = 64;
 constexpr int IC_ROWS = 31, IC_PITCH = 48;
 constexpr int TILE_BYTES = TILE_ROWS * TILE_PITCH;                    // 2368
 constexpr int IC_BYTES = IC_ROWS * IC_PITCH;                          // 1488
-constexpr int BUF_IC_OFF = (TILE_BYTES + 127) & ~127;                 // TMA destinations are 128-byte aligned
-constexpr int BUF_BYTES = BUF_IC_OFF + ((IC_BYTES + 127) & ~127);     // per keypoint
+constexpr int BUF_BYTES = (TILE_BYTES + 127) & ~127;                  // per keypoint; TMA destinations are 128-byte aligned. ONE buffer:
+                                                                      // the unblurred patch (IC_BYTES) first, then the blurred window over it
+static_assert(IC_BYTES <= BUF_BYTES, "the orientation patch shares the descriptor window's buffer");
 constexpr int DESC_DYN_SMEM = DESC_WARPS * DESC_KPW * BUF_BYTES;
 constexpr int DESC_RESIDENT = (227 * 1024) / (DESC_DYN_SMEM + 6 * 1024);   // CTAs per SM (dynamic windows + ~5 KB of static tables each)
 
@@ -151,13 +153,13 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_orient_desc(const __grid_co
     for (; round < n_rounds; round += round_stride) {                   // warp-uniform
         const int slot = round * DESC_KPW + grp;
         const unsigned n_valid = __popc(__ballot_sync(0xffffffffu, valid)) >> 3;   // groups with a keypoint (>= 1 here)
-        if (lane == 0) mbar_expect_tx(mbar, n_valid * (unsigned)(TILE_BYTES + IC_BYTES));
+        // Two passes over the SAME shared-memory buffer (2.4 KB per keypoint instead of 3.9 KB for two: 20 resident warps per SM
+        // instead of 12, which is what this latency- and shared-memory-bound kernel wants): the unblurred patch for IC_Angle,
+        // then — once the moments are summed — the blurred window for rBRIEF, whose flight covers atan2 / sincosf.
+        if (lane == 0) mbar_expect_tx(mbar, n_valid * (unsigned)IC_BYTES);
         __syncwarp();
-        if (valid && l8 == 0) {
-            tma_load_3d(buf_s, &maps.blur[level], (cx - TILE_R) & ~15, cy - TILE_R, img, mbar);
-            tma_load_3d(buf_s + BUF_IC_OFF, &maps.pyr[level], (cx - 15) & ~15, cy - 15, img, mbar);
-        }
-        // the warp's next round: its windows go to L2 now
+        if (valid && l8 == 0) tma_load_3d(buf_s, &maps.pyr[level], (cx - 15) & ~15, cy - 15, img, mbar);
+        // the warp's next round
         decode(slot + round_stride * DESC_KPW, valid_n, level_n, cx_n, cy_n, seed_idx_n, pt_n);
         if (DESC_PREFETCH && valid_n && l8 == 0) {
             tma_prefetch_3d(&maps.blur[level_n], (cx_n - TILE_R) & ~15, cy_n - TILE_R, img);
@@ -165,36 +167,48 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_orient_desc(const __grid_co
         }
         mbar_wait(mbar, parity);
         parity ^= 1u;
-        if (valid) {                                                    // whole groups; the shuffles below are group-wide
-            const LevelGeom& g = P.lv[level];
-            mcv_keypoint kp;
+        int m10 = 0, m01 = 0;
+        if (valid && seed_idx < 0) {                                    // whole groups; the shuffles below are group-wide
+            // IC_Angle: lane l8 owns patch columns 4 l8 .. 4 l8 + 3 of every row; the row's 31 patch bytes start `ox` bytes
+            // into the staged row. The four groups walk the rows with an offset of grp so that their loads (buffers are
+            // 128-byte aligned) spread over the banks.
+            const int ox = (cx - 15) & 15, a8 = (ox & 3) * 8;
+            const unsigned* ic = reinterpret_cast<const unsigned*>(buf) + (ox >> 2) + l8;
+#pragma unroll
+            for (int i = 0; i < IC_ROWS; ++i) {
+                int row = i + grp;
+                row = row >= IC_ROWS ? row - IC_ROWS : row;
+                const unsigned w = __funnelshift_r(ic[row * (IC_PITCH / 4)], ic[row * (IC_PITCH / 4) + 1], a8);
+                m10 = dp4a_us(w, s_wu[row][l8], m10);
+                m01 = dp4a_us(w, s_wv[row][l8], m01);
+            }
+        }
+        // the patch has been read (generic proxy): the blurred window may land on it (async proxy)
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) mbar_expect_tx(mbar, n_valid * (unsigned)TILE_BYTES);
+        __syncwarp();
+        if (valid && l8 == 0) tma_load_3d(buf_s, &maps.blur[level], (cx - TILE_R) & ~15, cy - TILE_R, img, mbar);
+        mcv_keypoint kp;
+        float a = 1.f, bs = 0.f;
+        if (valid) {
             if (seed_idx < 0) {
                 kp.x = (float)cx; kp.y = (float)cy;
-                kp.size = (float)g.kp_size; kp.response = (float)pt_r(pt); kp.octave = level; kp.class_id = -1;
-                // IC_Angle: lane l8 owns patch columns 4 l8 .. 4 l8 + 3 of every row; the row's 31 patch bytes start `ox` bytes
-                // into the staged row. The four groups walk the rows with an offset of grp so that their loads (buffers are
-                // 128-byte aligned) spread over the banks.
-                const int ox = (cx - 15) & 15, a8 = (ox & 3) * 8;
-                const unsigned* ic = reinterpret_cast<const unsigned*>(buf + BUF_IC_OFF) + (ox >> 2) + l8;
-                int m10 = 0, m01 = 0;
-#pragma unroll
-                for (int i = 0; i < IC_ROWS; ++i) {
-                    int row = i + grp;
-                    row = row >= IC_ROWS ? row - IC_ROWS : row;
-                    const unsigned w = __funnelshift_r(ic[row * (IC_PITCH / 4)], ic[row * (IC_PITCH / 4) + 1], a8);
-                    m10 = dp4a_us(w, s_wu[row][l8], m10);
-                    m01 = dp4a_us(w, s_wv[row][l8], m01);
-                }
+                kp.size = (float)P.lv[level].kp_size; kp.response = (float)pt_r(pt); kp.octave = level; kp.class_id = -1;
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) { m10 += __shfl_xor_sync(gmask, m10, o); m01 += __shfl_xor_sync(gmask, m01, o); }
                 kp.angle = fast_atan2_deg((float)m01, (float)m10);
             } else {
                 kp = seeds[seed_idx];
             }
-            // steered BRIEF
             const float ang = __fmul_rn(kp.angle, 0.017453292519943295f);  // factorPI = (float)(CV_PI / 180.f)
-            float a, bs;
             sincosf_glibc(ang, &bs, &a);  // a = cos, bs = sin
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        if (valid) {
+            const LevelGeom& g = P.lv[level];
+            // steered BRIEF
             // cvRound by the 1.5 * 2^23 trick (round-half-even like cvRound's lrint; |v| < 19): integer = float bits -
             // 0x4B400000, and that constant, times 65 for row * 64 + column, is folded into the window's base offset (mod 2^32)
             constexpr float MAGIC = 12582912.0f;
