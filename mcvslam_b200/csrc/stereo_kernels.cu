@@ -24,15 +24,15 @@
 namespace mcv {
 
 // The kernel is bound by the latency of its chain of dependent loads (keypoint -> row table -> records -> descriptors -> patches),
-// not by issue slots: what helps is more warps in flight. 4 warps per CTA (a CTA holds its slot until its slowest warp is done)
+// not by issue slots: what helps is more warps in flight. 2 warps per CTA (a CTA holds its slot until its slowest warp is done)
 // and 40 registers (48 warps per SM; a few spills outside the loops). B200, 128 frames: 8 warps / 51 registers 0.350 ms,
-// 4 / 51: 0.340, 2 / 51: 0.326, 8 / 40: 0.298, 4 / 40: 0.280, 4 / 32: 0.313. Issuing the left patch loads ahead of the
+// 4 / 51: 0.340, 2 / 51: 0.326, 8 / 40: 0.298, 4 / 40: 0.280, 2 / 40: 0.275, 4 / 32: 0.313. Issuing the left patch loads ahead of the
 // candidate scan and taking the winner's uR from its lane instead of kr[] (one round trip less) was bit-exact and no faster.
 #ifndef MCV_ST_WARPS
-#define MCV_ST_WARPS 4
+#define MCV_ST_WARPS 2
 #endif
 #ifndef MCV_ST_MINB
-#define MCV_ST_MINB 12
+#define MCV_ST_MINB 24
 #endif
 constexpr int ST_WARPS = MCV_ST_WARPS;
 
