@@ -1,10 +1,11 @@
 // Orientation, steered rBRIEF descriptor and final keypoint assembly for a batch of images (sm_100a).
 //
-// A quarter-warp per output keypoint (see "Design" below). Replaces, for every keypoint:
+// A quarter-warp per output keypoint for the scalar work and the orientation, the whole warp per keypoint for the descriptor
+// (see "Design" below). Replaces, for every keypoint:
 //   * the post-distribution fix-up (ORBextractor.cc:640-649): pt += 16, octave, size = (int)(31 * scale);
 //   * IC_Angle (ORBextractor.cc:75-98): int32 moments over the 15-px circular patch -> cv::fastAtan2;
 //   * computeOrbDescriptor (ORBextractor.cc:101-141) on the 7x7-Gaussian-smoothed level: 256 steered point pairs,
-//     lane l of the keypoint's 8 lanes produces descriptor bytes 4l .. 4l + 3;
+//     lane b of the warp produces descriptor byte b of each of the warp's four keypoints in turn;
 //   * the level-major assembly of operator() (ORBextractor.cc:845-897): quadtree keypoints of a level in heap-pop order,
 //     then the caller's pre-seeded keypoints of that octave, pt *= scale for level != 0.
 #include <string.h>
@@ -19,7 +20,7 @@ __constant__ int8_t c_pattern[1024] = {
 };
 
 #ifndef MCV_DESC_WARPS
-#define MCV_DESC_WARPS 4
+#define MCV_DESC_WARPS 3
 #endif
 constexpr int DESC_WARPS = MCV_DESC_WARPS;
 constexpr int DESC_KPW = 4;      // keypoints per warp and round: one per group of 8 lanes
@@ -30,10 +31,12 @@ constexpr int DESC_KPW = 4;      // keypoints per warp and round: one per group 
 #define DESC_PREFETCH 0          // cp.async.bulk.prefetch.tensor of the warp's next round: measured slower (0.78 vs 0.58 ms per 384
 #endif                           // images) — it doubles the row requests the TMA engine has to generate
 
-// Design. A quarter-warp (8 lanes) owns one keypoint, so the scalar part of the work (slot decoding, cv::fastAtan2, sincosf,
-// keypoint assembly) is paid once per FOUR keypoints of a warp instead of once per keypoint, and a lane produces four
-// descriptor bytes. Both pixel neighbourhoods of the keypoint are fetched by the TMA engine (cp.async.bulk.tensor, one
-// instruction per window, issued by the group's first lane, completion on the warp's mbarrier) from per-level 3-D tensor
+// Design. A quarter-warp (8 lanes) owns one keypoint for the scalar part of the work (slot decoding, IC_Angle, cv::fastAtan2,
+// sincosf, keypoint assembly), which is therefore paid once per FOUR keypoints of a warp instead of once per keypoint; for the
+// descriptor the warp turns to its four keypoints one after the other, lane b computing byte b from the 16 pattern points it
+// keeps in registers (the group leaders' cos / sin / window offset arrive by shuffle). Both pixel neighbourhoods of the keypoint
+// are fetched by the TMA engine (cp.async.bulk.tensor, one instruction per window, issued by the group's first lane, completion
+// on the warp's mbarrier) — one after the other into the SAME shared-memory buffer — from per-level 3-D tensor
 // maps (x, y, image) over the pyramid / blurred-pyramid buffers:
 //  * blurred window for rBRIEF: the pattern points lie within radius 18.4 of the centre, so every steered sample falls inside
 //    37 x 37; box 64 x 37 starting at ((cx - 18) & ~15, cy - 18) — the TMA start coordinate of the byte dimension must be a
@@ -48,7 +51,8 @@ constexpr int DESC_KPW = 4;      // keypoints per warp and round: one per group 
 // keypoint, l1tex 96 %); the same with cp.async staging 0.88 ms (810 per keypoint, short-scoreboard bound); quarter-warp + TMA,
 // one CTA per 16 keypoints 0.91 ms (table prologue per CTA, 18 % occupancy); persistent 0.58 ms (424 per keypoint; l1tex 78 %,
 // L2 56 %: what moves is ~3.9 KB of window per keypoint, 3 GB per launch); the two windows one after the other through ONE
-// buffer per keypoint (2.4 instead of 3.9 KB: 20 resident warps per SM instead of 12) 0.567 -> 0.532 ms.
+// buffer per keypoint (2.4 instead of 3.9 KB: 20 resident warps per SM instead of 12) 0.567 -> 0.532 ms; lane per descriptor
+// byte with the pattern in registers 0.532 -> 0.498 ms, 3 warps per CTA 0.486 ms.
 constexpr int TILE_R = 18, TILE_ROWS = 2 * TILE_R + 1, TILE_PITCH = 64;
 constexpr int IC_ROWS = 31, IC_PITCH = 48;
 constexpr int TILE_BYTES = TILE_ROWS * TILE_PITCH;                    // 2368
@@ -75,8 +79,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_orient_desc(const __grid_co
                                                                  mcv_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
                                                                  int* __restrict__ counts, int cap, const __grid_constant__ Plan P) {
     extern __shared__ __align__(128) uint8_t s_buf[];                   // [warp][group][BUF_BYTES]
-    // pattern: s_pat[k][l8] = point 64 * l8 + k (the 64 points = 32 pairs = 4 descriptor bytes of lane l8): the 8 lanes of a
-    // group read 8 consecutive float2, the four groups the same ones (broadcast)
+    // pattern staging: s_pat[k][q] = point 64 * q + k; read once per CTA — lane b keeps points 16 b .. 16 b + 15 in registers
     __shared__ float2 s_pat[64][8];
     // IC_Angle weights of the 31x31 circular patch, by row (v + 15) and 4-px word k (u = -15 + 4k ...): s_wu = u, s_wv = v
     // inside the circle (|u| <= umax[|v|], ORBextractor.cc:444-456), 0 outside, as signed bytes for dp4a
@@ -118,6 +121,9 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_orient_desc(const __grid_co
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the init is visible to the TMA engine
     }
     __syncthreads();
+    float2 pat[16];                                                     // this lane's 16 pattern points (descriptor byte `lane`)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pat[j] = s_pat[16 * (lane & 3) + j][lane >> 2];
     const int total = min(s_end[P.n_levels], cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) counts[img] = total;
     const int grp = lane >> 3, l8 = lane & 7;
@@ -206,25 +212,36 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_orient_desc(const __grid_co
         }
         mbar_wait(mbar, parity);
         parity ^= 1u;
-        if (valid) {
-            const LevelGeom& g = P.lv[level];
-            // steered BRIEF
-            // cvRound by the 1.5 * 2^23 trick (round-half-even like cvRound's lrint; |v| < 19): integer = float bits -
-            // 0x4B400000, and that constant, times 65 for row * 64 + column, is folded into the window's base offset (mod 2^32)
+        // steered BRIEF: the whole warp on one keypoint at a time, lane b = descriptor byte b (pattern points 16 b .. 16 b + 15 sit
+        // in this lane's registers: no pattern loads in the loop; a quarter-warp per keypoint with the pattern in shared memory
+        // spent 64 of its ~190 shared-memory instructions per round on them).
+        // cvRound by the 1.5 * 2^23 trick (round-half-even like cvRound's lrint; |v| < 19): integer = float bits -
+        // 0x4B400000, and that constant, times 65 for row * 64 + column, is folded into the window's base offset (mod 2^32)
+        {
             constexpr float MAGIC = 12582912.0f;
             const unsigned base = (unsigned)(TILE_R * TILE_PITCH + TILE_R + ((cx - TILE_R) & 15)) - (unsigned)(TILE_PITCH + 1) * 0x4B400000u;
-            unsigned val = 0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const float2 q0 = s_pat[2 * k][l8], q1 = s_pat[2 * k + 1][l8];
-                const unsigned r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q0.x, bs), __fmul_rn(q0.y, a)), MAGIC));
-                const unsigned c0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q0.x, a), __fmul_rn(q0.y, bs)), MAGIC));
-                const unsigned r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q1.x, bs), __fmul_rn(q1.y, a)), MAGIC));
-                const unsigned c1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q1.x, a), __fmul_rn(q1.y, bs)), MAGIC));
-                const int t0 = buf[r0 * TILE_PITCH + c0 + base], t1 = buf[r1 * TILE_PITCH + c1 + base];
-                val |= (unsigned)(t0 < t1) << k;
+#pragma unroll
+            for (int gg = 0; gg < DESC_KPW; ++gg) {
+                if (!__shfl_sync(0xffffffffu, (int)valid, 8 * gg)) continue;           // warp-uniform
+                const float ag = __shfl_sync(0xffffffffu, a, 8 * gg), bg = __shfl_sync(0xffffffffu, bs, 8 * gg);
+                const unsigned base_g = __shfl_sync(0xffffffffu, base, 8 * gg);
+                const uint8_t* wb = s_buf + (size_t)(warp * DESC_KPW + gg) * BUF_BYTES;
+                unsigned val = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float2 q0 = pat[2 * k], q1 = pat[2 * k + 1];
+                    const unsigned r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q0.x, bg), __fmul_rn(q0.y, ag)), MAGIC));
+                    const unsigned c0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q0.x, ag), __fmul_rn(q0.y, bg)), MAGIC));
+                    const unsigned r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q1.x, bg), __fmul_rn(q1.y, ag)), MAGIC));
+                    const unsigned c1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q1.x, ag), __fmul_rn(q1.y, bg)), MAGIC));
+                    const int t0 = wb[r0 * TILE_PITCH + c0 + base_g], t1 = wb[r1 * TILE_PITCH + c1 + base_g];
+                    val |= (unsigned)(t0 < t1) << k;
+                }
+                desc[((size_t)img * cap + (size_t)round * DESC_KPW + gg) * 32 + lane] = (uint8_t)val;
             }
-            reinterpret_cast<unsigned*>(desc + ((size_t)img * cap + slot) * 32)[l8] = val;   // bytes 4 l8 .. 4 l8 + 3, little endian
+        }
+        if (valid) {
+            const LevelGeom& g = P.lv[level];
             if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }
             if (l8 == 0) kps[(size_t)img * cap + slot] = kp;
         }
