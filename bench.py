@@ -548,7 +548,7 @@ def main():
         dom_bytes = STAGE_BYTES_PER_IMAGE[dom] * 3 * B
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
-        for name in ("r03_ncu_traffic.json", "r02_ncu_traffic.json", "r01_ncu_traffic.json"):   # DRAM bytes of the same kernel from the committed ncu --set full capture
+        for name in ("r04_ncu_traffic.json", "r03_ncu_traffic.json", "r02_ncu_traffic.json", "r01_ncu_traffic.json"):   # DRAM bytes of the same kernel from the committed ncu --set full capture
             try:
                 traffic = json.load(open(os.path.join(ROOT, "profiles", name)))["per_image"][dom] * 3 * B
                 traffic_src = "profiles/%s (ncu --set full, per launch)" % name

@@ -97,7 +97,10 @@ static_assert(FS_EDGE_BYTES >= 256 + 2 * FS_ROWS && FS_EDGE_BYTES % 16 == 0, "ed
 // Queue entry of a candidate: b | lane << 5 | yb << 16 — bit b of lane `lane`'s candidate word of the 7-row block whose last
 // row + 1 is yb. Bit b = 8 k + 7 - j stands for row j of the block and column k of a lane's word; row j's bits were handed
 // (k_fast_score) to the lane 5 j places down, so the pixel's own lane is (lane + 5 j) & 31.
-constexpr int FS_ROT = 5;
+#ifndef MCV_FS_ROT
+#define MCV_FS_ROT 5
+#endif
+constexpr int FS_ROT = MCV_FS_ROT;
 
 // Scores queued pixels 32 at a time (one lane each) while at least `keep_below` + 1 are queued. Pixels with score >= Tm go,
 // packed x | y << 12 | score << 24 (level coordinates), to the strip's list, and to the strip's edge record when they lie on
