@@ -233,7 +233,8 @@ mcv_status mcv_rig_process_async(mcv_rig* r, const uint8_t* d_imgs, int n_frames
  * capture thread running ahead of Frame construction, src/System.cpp:60-66). The outputs of a submit are complete after
  * mcv_rig_wait(ticket) (or mcv_rig_sync). The caller keeps the buffers alive and untouched until then. Tickets complete in
  * submission order; the library tracks the last 8 individually — waiting on an older one waits for the later ticket that
- * took over its slot (never returns early). Chunk size: env MCV_RIG_SUBMIT_CHUNK (default 128 frames). */
+ * took over its slot (never returns early). Chunk size: env MCV_RIG_SUBMIT_CHUNK (default 128 frames); whole steps rotate over
+ * four internal slots (env MCV_RIG_SLOTS_SUBMIT), so four steps in flight keep three of them in their kernels. */
 mcv_status mcv_rig_submit(mcv_rig* r, const uint8_t* imgs, int n_frames, int w, int hgt, mcv_keypoint* kps_out, uint8_t* desc_out,
                           int32_t* counts, float* u_right, float* depth_left, int cap, long long* ticket);
 mcv_status mcv_rig_wait(mcv_rig* r, long long ticket);
