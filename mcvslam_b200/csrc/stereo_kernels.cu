@@ -18,6 +18,8 @@
 //     disparity / depth                                                            (src/Frame.cpp:228-303).
 // k_stereo_median: one CTA per frame; the (size/2)-th smallest SAD via a two-pass radix select, then invalidates matches
 //     with SAD > 1.6 * median or < 0.4 * median                                    (src/Frame.cpp:307-323).
+#include <stdlib.h>
+#include <algorithm>
 #include "devmath.cuh"
 #include "engine.h"
 
@@ -47,7 +49,9 @@ struct StereoArgs {
     float bf, baseline;
     float* u_right; float* depth; int* best_dist; int* best_r;
     size_t out_stride;
-    int* row_start;                                // [frame][n_levels * h + 2]: first sorted record of each (octave, image row) (+ end)
+    int* row_start;                                // [frame][n_levels * hb + 2]: first sorted record of each (octave, row bin) (+ end)
+    int row_shift, hb;                             // row bin = row >> row_shift, hb bins per octave (shift 0 unless the table would
+                                                   // not fit the rows kernel's shared memory: many levels of a very tall image)
     uint4* recs;                                   // [frame][rec_stride] records sorted by (octave, row)
     size_t rec_stride;
 };
@@ -57,13 +61,13 @@ struct StereoArgs {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ StereoArgs A, const __grid_constant__ Plan P) {
     extern __shared__ int s_row[];                 // n_levels * h + 1 counters, then reused as running offsets
-    const int f = blockIdx.x, tid = threadIdx.x, h = P.h, bins = P.n_levels * h;
+    const int f = blockIdx.x, tid = threadIdx.x, h = P.h, bins = P.n_levels * A.hb;
     const int nr = A.nr ? A.nr[(size_t)f * A.count_stride] : A.nr_fixed;
     const mcv_keypoint* kr = A.kr + (size_t)f * A.frame_kp_stride;
     int* row_start = A.row_start + (size_t)f * (bins + 2);
     uint4* recs = A.recs + (size_t)f * A.rec_stride;
     auto bin_of = [&](const mcv_keypoint& k) {
-        return min(max(k.octave, 0), P.n_levels - 1) * h + min(max((int)floorf(k.y), 0), h - 1);
+        return min(max(k.octave, 0), P.n_levels - 1) * A.hb + (min(max((int)floorf(k.y), 0), h - 1) >> A.row_shift);
     };
     for (int i = tid; i <= bins; i += 256) s_row[i] = 0;
     __syncthreads();
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, MCV_ST_MINB) k_stereo_match(con
     const unsigned SENT = 999u << 20;
     unsigned k0 = SENT, k1 = SENT;
     {
-        const int* row_start = A.row_start + (size_t)f * (P.n_levels * n_rows + 2);
+        const int* row_start = A.row_start + (size_t)f * (P.n_levels * A.hb + 2);
         const uint4* recs = A.recs + (size_t)f * A.rec_stride;
         // the slices of octaves levelL - 1 .. levelL + 1: rows row -+ (ceil(10 * scale[o]) + 2) of each, one concatenated index space
         int beg[3], cum[3];
@@ -134,8 +138,8 @@ __global__ void __launch_bounds__(32 * ST_WARPS, MCV_ST_MINB) k_stereo_match(con
             beg[k] = 0;
             if (o >= 0 && o < P.n_levels) {
                 const int b = (int)ceilf(__fmul_rn(10.f, P.lv[o].scale)) + 2;
-                beg[k] = __ldg(row_start + o * n_rows + max(row - b, 0));
-                total += __ldg(row_start + o * n_rows + min(row + b + 1, n_rows)) - beg[k];
+                beg[k] = __ldg(row_start + o * A.hb + (max(row - b, 0) >> A.row_shift));
+                total += __ldg(row_start + o * A.hb + (min(row + b, n_rows - 1) >> A.row_shift) + 1) - beg[k];
             }
             cum[k] = total;
         }
@@ -272,7 +276,13 @@ static int run_stereo(StereoArgs A, const Plan& P, int n_frames, int max_left, i
     A.recs = reinterpret_cast<uint4*>(scratch);
     A.rec_stride = (size_t)max_right;
     A.row_start = reinterpret_cast<int*>(A.recs + (size_t)n_frames * max_right);
-    const size_t smem = ((size_t)P.n_levels * P.h + 1) * sizeof(int);
+    // one bin per (octave, row) while that table fits 64 KB of the rows kernel's shared memory; coarser row bins beyond (the match
+    // kernel's gate is exact either way, it only scans a few more records). MCV_STEREO_ROW_SHIFT forces a shift (tests).
+    A.row_shift = 0;
+    while (((size_t)P.n_levels * (((P.h - 1) >> A.row_shift) + 1) + 1) * sizeof(int) > 64 * 1024) ++A.row_shift;
+    if (const char* e = getenv("MCV_STEREO_ROW_SHIFT")) A.row_shift = std::max(A.row_shift, std::min(8, atoi(e)));
+    A.hb = ((P.h - 1) >> A.row_shift) + 1;
+    const size_t smem = ((size_t)P.n_levels * A.hb + 1) * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_stereo_rows<<<n_frames, 256, smem, s>>>(A, P);
     dim3 grid((max_left + ST_WARPS - 1) / ST_WARPS, n_frames);

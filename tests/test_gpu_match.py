@@ -96,6 +96,24 @@ def test_stereo(api, oracle, seed):
     assert np.array_equal(ur.view(np.uint32), uro.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dpo.view(np.uint32))
 
 
+@pytest.mark.parametrize("shift", [1, 3])
+def test_stereo_coarse_row_bins(api, oracle, shift, monkeypatch):
+    """The right keypoints' (octave, row) table falls back to coarser row bins when it would not fit the rows kernel's shared memory
+    (many levels of a very tall image); the candidate gate stays exact, so the result must not change. MCV_STEREO_ROW_SHIFT forces it."""
+    monkeypatch.setenv("MCV_STEREO_ROW_SHIFT", str(shift))
+    trip = synth.triplet(23)
+    EL, ER = api.ORB(2000, 1.2, 8, 28, 15), api.ORB(2000, 1.2, 8, 28, 15)
+    OL, OR = oracle.Orb(2000, 1.2, 8, 28, 15), oracle.Orb(2000, 1.2, 8, 28, 15)
+    nl, kl, dl = EL.Extract(trip[0]); nr, kr, dr = ER.Extract(trip[1])
+    OL.extract(trip[0]); OR.extract(trip[1])
+    bf, b = 955.40503, 1.0
+    ur, dp, bd, br = api.ComputeStereoMatch(EL, ER, kl, dl, kr, dr, bf, b)
+    n, uro, dpo, bdo, bro = oracle.stereo_match(OL, OR, kl, dl, kr, dr, 480, bf, b)
+    assert n > 200
+    assert np.array_equal(bd, bdo) and np.array_equal(br, bro)
+    assert np.array_equal(ur.view(np.uint32), uro.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dpo.view(np.uint32))
+
+
 def test_rig_batch(api, oracle):
     frames = np.stack([synth.triplet(s) for s in (31, 32, 33)])
     R = api.Rig()
