@@ -24,6 +24,10 @@ def test_flat_and_crowded_images(api, oracle):
         "salt": ((rng.random((300, 400)) < 0.02).astype(np.uint8) * 255, (3000, 1.2, 3, 20, 7)),  # list / arena capacities
         "checker": (((np.add.outer(np.arange(240) // 5, np.arange(320) // 5) % 2) * 200 + 20).astype(np.uint8), (800, 1.3, 3, 28, 15)),
     }
+    # thresholds >= 128 take the other instantiation of k_fast_score (the per-byte "> T" test flips from OR to AND of its carry terms)
+    cases["checker_hi"] = (cases["checker"][0], (800, 1.3, 3, 180, 130))
+    cases["salt_hi"] = (cases["salt"][0], (3000, 1.2, 3, 150, 60))
+    cases["noise_hi"] = (cases["noise"][0], (1500, 1.2, 4, 128, 127))
     for name, (img, prm) in cases.items():
         E = api.ORB(*prm); O = oracle.Orb(*prm, debug=True)
         n, k, d = E.Extract(img)
