@@ -446,7 +446,7 @@ def main():
         stage_ms, n_calls = rig.stage_ms()
         rig.set_profiling(False)
         # e2e leg: host buffers through the C ABI, copies inside the timed region. (a) one synchronous mcv_rig_process call per
-        # step; (b) the throughput API: mcv_rig_submit / mcv_rig_wait, --inflight (default 3) steps in flight — (b) is the headline e2e
+        # step; (b) the throughput API: mcv_rig_submit / mcv_rig_wait, --inflight (default 4) steps in flight — (b) is the headline e2e
         for _ in range(2):
             step_host()
         barrier()
