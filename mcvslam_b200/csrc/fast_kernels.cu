@@ -9,14 +9,15 @@
 //    threshold T iff S >= T. Register-marching stencil, no shared-memory tile: a warp owns a 128-px strip (lane = one aligned
 //    4-px word) and marches down the rows keeping the last 7 row words in a register ring. Per row: one coalesced 32-bit
 //    load, two shuffles, and a 4-pixels-at-once compass reject built on VABSDIFF4 (a 9-arc always contains two compass
-//    pixels that are 90 degrees apart, so a corner needs |v - p| > T on two adjacent compass points). The few survivors are
-//    pushed to a per-warp queue and scored 32 at a time (one lane per pixel) so the expensive arc min/max network never runs
-//    divergent.
+//    pixels that are 90 degrees apart, so a corner needs |v - p| > T on two adjacent compass points). The survivors (about
+//    twice the true corners) are pushed to a per-warp queue and scored 32 at a time (one lane per pixel) so the expensive arc
+//    min/max network never runs divergent. Corners come in clusters: before the per-lane emission loop, row j's pass bits of a
+//    7-row block are handed to the lane 5 j places down, so that no lane has a whole cluster to emit while the others wait.
 //
 //    There is NO dense score map (round 1 wrote one — 97 % zeros — and the NMS read it back: 0.8 GB of DRAM traffic per
 //    128-frame step). Every pixel with S >= threshold (3-7 % of the pixels) is appended to the strip's own list segment (the
 //    warp owns the strip, so the fill count is a register: no atomics); the scores on the strip's four BORDER lines (first /
-//    last row, first / last column) are also written to a 336-byte edge record per strip, which is all a neighbouring
+//    last row, first / last column) are also written to a 320-byte edge record per strip, which is all a neighbouring
 //    strip's NMS needs to know about this one.
 //
 //  k_nms_sparse — one warp per strip: rebuilds the strip's score tile (+1 px ring) in shared memory from the strip's own
