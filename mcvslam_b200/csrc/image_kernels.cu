@@ -297,7 +297,7 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // One warp per CTA, 24 resident CTAs per SM = 80 registers (one 4-byte spill outside the loop), 50-row strips (12 % halo rows).
 // B200, 384 images, with the DP2A vertical pass: 4 warps x 36 rows, no register target (85 registers) 0.394 ms; 4 x 6 CTAs
 // (80 registers) 0.368; x 7 (72) 0.477; 1 warp x 24 CTAs 0.364, x 28 0.390; 1 x 24 with 29 / 50 / 64 / 78 / 120 rows:
-// 0.372 / 0.343 / 0.358 / 0.357 / 0.352.
+// 0.372 / 0.343 / 0.358 / 0.357 / 0.352. Leftover columns folded (several bands per warp): 0.343 -> 0.318 ms.
 #ifndef GB_MINB
 #define GB_MINB 24
 #endif
@@ -310,15 +310,30 @@ __global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t
     while (level + 1 < P.n_levels && sid >= T.first[level + 1]) ++level;
     const LevelGeom& g = P.lv[level];
     const int t = sid - T.first[level];
-    const int x0 = (t % T.strips_x[level]) * 128 + lane * 4, y0 = (t / T.strips_x[level]) * GB_ROWS;
     const int w = g.w, h = g.h, pitch = g.pitch;
+    // Strips of a level: first its FULL 128-px strips (strips_x per band of GB_ROWS rows), then the columns that are left over
+    // (w mod 128, rl lanes wide) FOLDED: a warp takes 32 / rl bands of them side by side, so that a level whose width is not a
+    // multiple of 128 does not leave the rest of a warp idle on every band (levels 1-7 of 640x480: 177 -> 162 warps per image).
+    const int nxf = T.strips_x[level], n_bands = (h + GB_ROWS - 1) / GB_ROWS, n_full = nxf * n_bands;
+    int x0, y0;
+    bool first_l, right_l;                                  // lane fetches the outer neighbour word on its left / right itself
+    if (t < n_full) {
+        x0 = (t % nxf) * 128 + lane * 4; y0 = (t / nxf) * GB_ROWS;
+        first_l = lane == 0; right_l = lane == 31;
+    } else {
+        const int rl = (w - nxf * 128 + 3) >> 2, fold = 32 / rl, grp = lane / rl, lg = lane - grp * rl;
+        const int band = (t - n_full) * fold + grp;
+        const bool mine = grp < fold && band < n_bands;
+        x0 = mine ? nxf * 128 + lg * 4 : w + 64; y0 = mine ? band * GB_ROWS : 0;
+        first_l = lg == 0; right_l = false;                 // a group's last lane is at the image's right edge: reflected, no neighbour
+    }
     const uint8_t* src = pyr + (size_t)img * P.pyr_bytes + g.img_off;
     uint8_t* dst = blur + (size_t)img * P.pyr_bytes + g.img_off + x0;
     const bool active = x0 < w;
     const int n_valid = min(4, w - x0);                     // pixels of this lane's word inside the image (<= 0: none)
-    // lanes 0 / 31 fetch the strip's outer neighbour words themselves (one predicated load per row)
-    const int ex = lane == 0 ? x0 - 4 : x0 + 4;
-    const bool edge = (lane == 0 && x0 > 0) || (lane == 31 && x0 + 4 < pitch);
+    // the first / last lane of a strip fetch the strip's outer neighbour words themselves (one predicated load per row)
+    const int ex = first_l ? x0 - 4 : x0 + 4;
+    const bool edge = active && ((first_l && x0 > 0) || (right_l && x0 + 4 < pitch));
     const uint32_t TA = 18u | (34u << 8) | (48u << 16) | (56u << 24), TB = 48u | (34u << 8) | (18u << 16);
     // BORDER_REFLECT_101 in x without branches in the row loop: per-lane byte-permute selectors, built once.
     // Window bytes b[-4..7] = (w0, w1, w2). Left edge (x0 == 0): b[-i] = b[i]. Right edge at e = w - 1 - x0: b[i] = b[2e - i], i > e.
@@ -335,8 +350,6 @@ __global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t
             sel2 |= (uint32_t)((w2_from_w0w1 ? s2 + 4 : s2) & 7) << (4 * i);
         }
     }
-    const int dec = (t / T.strips_x[level]) * GB_ROWS;      // == y0, kept separate so that row offsets stay 32-bit
-    (void)dec;
 
     auto row_ptr = [&](int r) {                             // reflected input row y0 - 3 + r, clamped for rows that feed nothing
         int y = y0 - 3 + r;
@@ -373,8 +386,8 @@ __global__ void __launch_bounds__(32 * GB_WARPS, GB_MINB) k_gauss7(const uint8_t
                 pe[j] = edge ? __ldg(reinterpret_cast<const uint32_t*>(row + ex)) : 0u;
             }
             uint32_t w0r = __shfl_up_sync(0xffffffffu, w1r, 1), w2r = __shfl_down_sync(0xffffffffu, w1r, 1);
-            w0r = lane == 0 ? we : w0r;
-            w2r = lane == 31 ? we : w2r;
+            w0r = first_l ? we : w0r;
+            w2r = right_l ? we : w2r;
             const uint32_t w0 = __byte_perm(w0r, w1r, sel0), w1 = __byte_perm(w0r, w1r, sel1);
             const uint32_t w2 = __byte_perm(w2_from_w0w1 ? w0r : w1r, w2_from_w0w1 ? w1r : w2r, sel2);
             // horizontal 7-tap: px k uses bytes [k-3, k] of (w0:w1) and [k+1, k+4] of (w1:w2)
@@ -410,8 +423,9 @@ int launch_blur(const Plan& P, const uint8_t* d_pyr, uint8_t* d_blur, int n_imag
     int n = 0;
     for (int l = 0; l < P.n_levels; ++l) {
         T.first[l] = n;
-        T.strips_x[l] = (P.lv[l].w + 127) / 128;
-        n += T.strips_x[l] * ((P.lv[l].h + GB_ROWS - 1) / GB_ROWS);
+        T.strips_x[l] = P.lv[l].w / 128;                    // FULL strips per band; the remaining columns are folded (k_gauss7)
+        const int n_bands = (P.lv[l].h + GB_ROWS - 1) / GB_ROWS, rl = (P.lv[l].w - T.strips_x[l] * 128 + 3) / 4;
+        n += T.strips_x[l] * n_bands + (rl ? (n_bands + 32 / rl - 1) / (32 / rl) : 0);
     }
     for (int l = P.n_levels; l <= MAX_LEVELS; ++l) T.first[l] = n;
     dim3 grid((n + GB_WARPS - 1) / GB_WARPS, n_images);
