@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(256) k_resize_level(uint8_t* __restrict__ pyr,
 constexpr int RS_ROWS = MCV_RS_ROWS;   // output rows per warp (<= 32: lane j holds row j's coefficients)
 constexpr int RS_WARPS = MCV_RS_WARPS;
 constexpr int RS_PREF = 4;    // source rows in flight per lane
+// Tried and dropped (bit-exact, B200): the leftover columns of a level folded as in k_gauss7 (32 / width bands per warp: 433 -> 373
+// warps per image). Each lane group then needs its own row schedule, so the row coefficients come from the tables per lane (three
+// dependent loads per output row instead of three shuffles from "lane j") and the emission loop diverges between groups: pyramid
+// stage 0.394 -> 0.435 ms.
 
 __global__ void __launch_bounds__(32 * RS_WARPS) k_resize_march(uint8_t* __restrict__ pyr, int pyr_bytes, const int* __restrict__ tab,
                                                                  int sw, int sh, int spitch, int soff, int dw, int dh, int dpitch, int doff,
